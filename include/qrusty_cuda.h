@@ -1,0 +1,180 @@
+/*
+ * qrusty_cuda.h -- C ABI of the B200 (sm_100a) implementation of qrusty's
+ * SparsePauliOp -> CSR hot path and the matrix-free Pauli-sum apply H.v.
+ *
+ * This is the boundary a `qrusty::cuda` Rust module binds with `extern "C"`
+ * (see INTEGRATION.md and rust/cuda.rs).  Plain pointers and sizes only.
+ * File:line citations are into the reference repository (chetmurthy/qrusty).
+ *
+ * Conventions
+ *  - every function returns an int status (QR_OK = 0); on failure
+ *    qr_last_error() returns a thread-local message.  Nothing aborts or throws
+ *    across this boundary (the reference panics/returns QrustyErr instead,
+ *    qrusty/src/lib.rs:34-52).
+ *  - complex128 is two consecutive doubles (re, im), as num_complex::Complex64.
+ *  - the library never frees caller memory and never keeps caller pointers
+ *    after a call returns (asynchronous calls: until the stream reaches them).
+ *  - a plan is not re-entrant; distinct plans are independent.  Callable from
+ *    any host thread.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with QR_ERR_CUDA.
+ */
+#ifndef QRUSTY_CUDA_H
+#define QRUSTY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define QR_API __attribute__((visibility("default")))
+#else
+#define QR_API
+#endif
+
+#define QR_OK               0
+#define QR_ERR_INVALID      1   /* bad argument                                 */
+#define QR_ERR_CUDA         2   /* CUDA runtime / launch failure, no device     */
+#define QR_ERR_NCCL         3   /* NCCL missing or failed                       */
+#define QR_ERR_OOM          4   /* host or device allocation failed             */
+#define QR_ERR_UNSUPPORTED  5   /* e.g. n_qubits > 32                           */
+
+#define QR_VERSION 100          /* 0.1.0 */
+
+/* One Pauli term as rowwise::make_params emits it (qrusty/src/accel.rs:141-157):
+ * (z_indices, x_indices, coeff') with coeff' = (-i)^phase * coeff already applied
+ * by the host (Pauli::{phase,x_indices,z_indices}, qrusty/src/lib.rs:161-181).
+ * Bit k of x/z is qubit k = k-th label character from the right (lib.rs:144). */
+typedef struct qr_term {
+    uint64_t z;
+    uint64_t x;
+    double   re;
+    double   im;
+} qr_term;
+
+typedef struct qr_plan qr_plan;     /* opaque: canonicalised operator resident on one GPU */
+typedef struct qr_comm qr_comm;     /* opaque: NCCL communicator, one rank per process     */
+
+typedef struct qr_plan_info_t {
+    int32_t  n_qubits;
+    int32_t  device;
+    uint64_t dim;        /* 2^n_qubits rows and columns                                   */
+    uint64_t n_terms;    /* T                                                             */
+    uint64_t n_groups;   /* G = distinct X-masks = stored entries per row                 */
+    uint64_t nnz;        /* G * dim: explicit zeros are kept, as accel.rs:171-210 does    */
+} qr_plan_info_t;
+
+/* ---- plan: replaces make_params' consumer side + the grouping that make_row
+ * redoes per row with a sort (accel.rs:174-205).  Uploads the T terms, runs the
+ * canonicalisation kernel (stable radix sort by X-mask, head-flag scan -> groups,
+ * rank tables) on `device`, and waits for it.  n_qubits in [1, 32], n_terms >= 1
+ * (SparsePauliOp::new, lib.rs:354-376), every x and z < 2^n_qubits. */
+QR_API int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms, int device,
+                   uint32_t flags, qr_plan **out);
+QR_API int qr_plan_destroy(qr_plan *plan);
+QR_API int qr_plan_info(const qr_plan *plan, qr_plan_info_t *info);
+
+/* Canonicalisation output, for inspection/tests: the G distinct X-masks in
+ * ascending order, group_offsets[G+1] into the sorted term list, and
+ * term_order[T] = original index of each sorted term (stable: original order
+ * inside a group).  Any pointer may be NULL.  Synchronous. */
+QR_API int qr_plan_groups(const qr_plan *plan, uint64_t *xmask, uint32_t *group_offsets,
+                   uint32_t *term_order);
+
+/* Re-runs the canonicalisation kernel from the raw term table already in HBM,
+ * asynchronously on `stream` (a cudaStream_t, NULL = default stream).  Lets a
+ * caller time the whole device sequence canonicalise -> fill. */
+QR_API int qr_plan_canonicalise_async(qr_plan *plan, void *stream);
+
+/* ---- CSR build: replaces rowwise::make_unsafe_vectors_chunked
+ * (accel.rs:267-336) for rows [row_lo, row_hi).  Output layout is that of
+ * UnsafeVectors (accel.rs:15-20) / CsMatI<Complex64,u64,u64> (lib.rs:558-571):
+ *   d_indptr  u64[row_hi-row_lo+1]
+ *   d_indices u64[(row_hi-row_lo)*G]   GLOBAL column ids, ascending inside a row
+ *   d_data    complex128[(row_hi-row_lo)*G]
+ * indptr values: with QR_INDPTR_LOCAL (default) the shard is a self-contained
+ * CSR, d_indptr[i] = i*G; with QR_INDPTR_GLOBAL d_indptr[i] = (row_lo+i)*G as in
+ * the full matrix.  d_indptr may be NULL (skip).  Device pointers, 16-byte
+ * aligned; asynchronous on `stream`. */
+#define QR_INDPTR_LOCAL   0u
+#define QR_INDPTR_GLOBAL  1u
+#define QR_FILL_DIRECT    2u    /* force the unstaged kernel (debug / comparison)  */
+QR_API int qr_build_rows_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
+                         uint64_t *d_indptr, uint64_t *d_indices, double *d_data,
+                         uint32_t flags, void *stream);
+
+/* Same, into caller-allocated HOST buffers (what the Rust shim hands to
+ * CsMatI::new_unchecked): builds on the device in row windows and copies back.
+ * Synchronous.  Pinned host buffers (qr_malloc_host) copy fastest. */
+QR_API int qr_build_host(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
+                  uint64_t *indptr, uint64_t *indices, double *data, uint32_t flags);
+
+/* ---- matrix-free H.v: replaces build + rowwise::spmat_dot_densevec
+ * (accel.rs:338-370) without reading a matrix.  d_v is the FULL vector
+ * (complex128[dim]); d_y receives rows [row_lo,row_hi) (complex128[row_hi-row_lo]).
+ * Asynchronous on `stream`. */
+QR_API int qr_apply_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
+                    const double *d_v, double *d_y, void *stream);
+QR_API int qr_apply_host(qr_plan *plan, const double *v, double *y);   /* full vector, host buffers */
+
+/* diag(H) for rows [row_lo,row_hi) (SpMat.diagonal, pyqrusty/src/lib.rs:118-125). */
+QR_API int qr_diagonal_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi, double *d_diag, void *stream);
+
+/* CSR SpMV on a device-resident CSR shard, the reference's own H.v
+ * (accel.rs:338-370): y[r] = sum_k data[k]*v[indices[k]] in stored order,
+ * starting from zero; indptr may be local or global (rebased by d_indptr[0]). */
+QR_API int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const uint64_t *d_indices,
+                   const double *d_data, const double *d_v, double *d_y, void *stream);
+
+/* Lanczos/Davidson vector kernels (accel.rs:374-393): z = a*x + b*y, a*x + y, a*x. */
+QR_API int qr_axpby_device(uint64_t n, const double a[2], const double *d_x, const double b[2],
+                    const double *d_y, double *d_z, void *stream);
+QR_API int qr_axpy_device(uint64_t n, const double a[2], const double *d_x, const double *d_y,
+                   double *d_z, void *stream);
+QR_API int qr_ax_device(uint64_t n, const double a[2], const double *d_x, double *d_z, void *stream);
+/* <x,y> = sum conj(x_i) y_i  -> d_out[2] (numpy.vdot; the reference leaves this to numpy). */
+QR_API int qr_dotc_device(uint64_t n, const double *d_x, const double *d_y, double *d_out, void *stream);
+
+/* ---- multi-GPU, one process per GPU.  NCCL is dlopen'ed on first use.  The
+ * CSR build needs no communication; H.v all-gathers the row-sharded vector. */
+#define QR_UNIQUE_ID_BYTES 128
+QR_API int qr_comm_unique_id(void *id_out /* QR_UNIQUE_ID_BYTES */);
+QR_API int qr_comm_create(const void *id, int n_ranks, int rank, int device, qr_comm **out);
+QR_API int qr_comm_destroy(qr_comm *comm);
+/* d_v_shard: this rank's dim/n_ranks elements; d_v_full: scratch of dim elements;
+ * d_y_shard: this rank's rows of H.v.  ncclAllGather then the local apply. */
+QR_API int qr_apply_distributed(qr_plan *plan, qr_comm *comm, const double *d_v_shard,
+                         double *d_v_full, double *d_y_shard, void *stream);
+QR_API int qr_allreduce_sum_f64(qr_comm *comm, double *d_buf, size_t count, void *stream);
+
+/* ---- runtime helpers for hosts without a CUDA binding of their own ---- */
+QR_API int qr_device_count(int *count);
+QR_API int qr_device_name(int device, char *buf, size_t buf_len);
+QR_API int qr_set_device(int device);
+QR_API int qr_malloc_device(void **ptr, size_t bytes);
+QR_API int qr_free_device(void *ptr);
+QR_API int qr_malloc_host(void **ptr, size_t bytes);     /* page-locked */
+QR_API int qr_free_host(void *ptr);
+QR_API int qr_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);  /* async if stream != NULL... */
+QR_API int qr_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+QR_API int qr_memset_device(void *dst, int value, size_t bytes, void *stream);
+QR_API int qr_stream_create(void **stream);
+QR_API int qr_stream_destroy(void *stream);
+QR_API int qr_stream_synchronize(void *stream);          /* NULL = whole device */
+QR_API int qr_event_create(void **event);
+QR_API int qr_event_destroy(void *event);
+QR_API int qr_event_record(void *event, void *stream);
+QR_API int qr_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchronises on `stop` */
+
+/* Number of this library's kernels launched by the calling process so far. */
+QR_API uint64_t qr_kernel_launches(void);
+QR_API const char *qr_last_error(void);
+QR_API int qr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRUSTY_CUDA_H */

@@ -1,0 +1,448 @@
+"""qrusty_b200 -- host-side mirror of the pyqrusty interface over the sm_100a library.
+
+Same names, argument meaning and error behaviour as the reference's Python module
+(pyqrusty/src/lib.rs, pyqrusty/python/pyqrusty/__init__.py) for the hot path:
+
+    Pauli, SparsePauliOp, SpMat, csr_matrix, spmat_dot_densevec, axpby, axpy, ax
+
+plus what the CUDA path adds: to_matrix_mode("Cuda") / ("Cuda/<ngpus>"), and the
+matrix-free SparsePauliOp.apply(v).  Every matrix is built by the CUDA kernels in
+csrc/ through the C ABI of include/qrusty_cuda.h; there is no CPU implementation
+here, so the reference's CPU-strategy mode strings ("", "Rowwise", "RowwiseUnsafeChunked/n",
+...) are accepted and executed by the same CUDA build -- they all denote the same matrix.
+
+Out of scope: MatrixMarket I/O, SpMat +/-/scale, a_spmat_p_b_spmat,
+count_zeros/eliminate_zeros, precond.
+"""
+import ctypes as C
+import re
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import QrustyCudaError, call, lib
+from ._runtime import DeviceBuffer, HostBuffer, PINNED, device_name, pinned_empty, synchronize
+
+__all__ = ["Pauli", "SparsePauliOp", "SpMat", "csr_matrix", "spmat_dot_densevec",
+           "axpby", "axpy", "ax", "QrustyCudaError"]
+
+TERM_DTYPE = np.dtype([("z", "<u8"), ("x", "<u8"), ("re", "<f8"), ("im", "<f8")])   # == qr_term
+
+_LABEL_RE = re.compile(r"^([+-]?)1?([ij]?)([IXYZ]+)$")            # lib.rs:127
+# AccelMode::try_from (lib.rs:293-331); the two chunked forms are unanchored is_match.
+_MODES_EXACT = {"Binary", "Accel", "Rowwise", "RowwiseUnsafe", "Reduce", "Rayon"}
+_MODES_RE = [re.compile(r"RowwiseUnsafeChunked/(\d+)"), re.compile(r"RayonChunked/(\d+)")]
+_CUDA_RE = re.compile(r"^Cuda(?:/(\d+))?$")
+
+
+def _rust_f64(x):
+    """Rust `{}` of an f64 (util.rs:140-142 complex64_to_string): shortest round-trip,
+    never scientific, no trailing '.0'."""
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "inf" if x > 0 else "-inf"
+    s = repr(float(x))
+    if "e" in s or "E" in s:
+        from decimal import Decimal
+        s = format(Decimal(s), "f")
+    return s[:-2] if s.endswith(".0") else s
+
+
+class Pauli:
+    """pyqrusty.Pauli (pyqrusty/src/lib.rs:262-303) over qrusty::Pauli (lib.rs:117-267)."""
+
+    def __init__(self, label):
+        m = _LABEL_RE.match(label) if isinstance(label, str) else None
+        if not m:
+            raise Exception("error: malformed label")                  # lib.rs:129
+        sign, imag, body = m.groups()
+        self.base_phase = (1 if imag else 0) + (2 if sign == "-" else 0)  # lib.rs:135-141
+        self._body = body
+        x = z = ny = 0
+        for k, ch in enumerate(reversed(body)):                        # qubit k = k-th char from the right
+            if ch in "XY":
+                x |= 1 << k
+            if ch in "YZ":
+                z |= 1 << k
+            if ch == "Y":
+                ny += 1
+        self._x, self._z, self._ny = x, z, ny
+
+    def num_qubits(self):
+        return len(self._body)
+
+    def label(self):
+        return self._body                                               # lib.rs:150-154 (prefix dropped)
+
+    def x_indices(self):
+        return self._x
+
+    def z_indices(self):
+        return self._z
+
+    def phase(self):
+        return (self.base_phase + self._ny) % 4                        # lib.rs:179-181
+
+    def __repr__(self):
+        return "Pauli('%s')" % self._body
+
+    def __str__(self):
+        return self._body
+
+    def to_matrix(self):
+        return SparsePauliOp([self], [1.0 + 0.0j]).to_matrix()
+
+
+def _parse_mode(mode):
+    """-> ("cuda", ngpus).  Unknown strings raise like pyqrusty (pyqrusty/src/lib.rs:406-415)."""
+    if mode == "":
+        return 1
+    m = _CUDA_RE.match(mode)
+    if m:
+        n = int(m.group(1)) if m.group(1) else 1
+        if n < 1:
+            raise Exception("to_matrix_mode: unrecognized mode %s" % mode)
+        return n
+    if mode in _MODES_EXACT or any(r.search(mode) for r in _MODES_RE):
+        return 1
+    raise Exception("to_matrix_mode: unrecognized mode %s" % mode)
+
+
+class _Plan:
+    """Owns a qr_plan handle."""
+
+    def __init__(self, n_qubits, terms, device):
+        self.terms = np.ascontiguousarray(terms, dtype=TERM_DTYPE)
+        h = C.c_void_p()
+        call("qr_plan_create", n_qubits, self.terms.ctypes.data, len(self.terms), device, 0, C.byref(h))
+        self.handle = h.value
+        info = _ffi.PlanInfo()
+        call("qr_plan_info", self.handle, C.byref(info))
+        self.n_qubits, self.device = info.n_qubits, info.device
+        self.dim, self.n_terms, self.n_groups, self.nnz = info.dim, info.n_terms, info.n_groups, info.nnz
+
+    def groups(self):
+        x = np.zeros(self.n_groups, np.uint64)
+        off = np.zeros(self.n_groups + 1, np.uint32)
+        order = np.zeros(self.n_terms, np.uint32)
+        call("qr_plan_groups", self.handle, x.ctypes.data, off.ctypes.data, order.ctypes.data)
+        return x, off, order
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib.qr_plan_destroy(self.handle)
+            self.handle = None
+
+
+class SparsePauliOp:
+    """pyqrusty.SparsePauliOp (pyqrusty/src/lib.rs:305-433) over qrusty::SparsePauliOp
+    (lib.rs:345-586)."""
+
+    def __init__(self, paulis, coeffs):
+        paulis, coeffs = list(paulis), list(coeffs)
+        if len(paulis) != len(coeffs):
+            raise Exception("SparsePauliOp::new: paulis and coeffs must have same length")
+        if len(paulis) == 0:
+            raise Exception("SparsePauliOp::new: at least one pauli must be supplied")
+        n = paulis[0].num_qubits()
+        if any(p.num_qubits() != n for p in paulis):
+            raise Exception("SparsePauliOp::new: all supplied paulis must have the same #qubits")
+        self._members = [(p, complex(c)) for p, c in zip(paulis, coeffs)]
+        self._terms = None
+        self._plans = {}
+
+    @classmethod
+    def from_terms(cls, n_qubits, terms):
+        """Builds an operator straight from make_params-style tuples (z, x, c') --
+        the synthetic-Hamiltonian generators use this; labels are not materialised."""
+        self = cls.__new__(cls)
+        self._members = None
+        self._n_qubits = int(n_qubits)
+        self._terms = np.ascontiguousarray(terms, dtype=TERM_DTYPE)
+        if len(self._terms) == 0:
+            raise Exception("SparsePauliOp::new: at least one pauli must be supplied")
+        self._plans = {}
+        return self
+
+    # -- container protocol --------------------------------------------------------
+    def __len__(self):
+        return len(self._terms) if self._members is None else len(self._members)
+
+    def __getitem__(self, idx):
+        if self._members is None:
+            raise Exception("__getitem__: operator was built from raw terms")
+        if isinstance(idx, slice):
+            start, stop, step = idx.indices(len(self._members))
+            return self._members[start:stop][::step]                   # pyqrusty/src/lib.rs:357-366
+        if not (0 <= idx < len(self._members)):
+            raise Exception("__getitem__ called on invalid index %d" % idx)
+        return self._members[idx]
+
+    def num_qubits(self):
+        return self._n_qubits if self._members is None else self._members[0][0].num_qubits()
+
+    def __repr__(self):
+        labels = "','".join(p.label() for p, _ in self._members)
+        coeffs = ", ".join("%s+%sj" % (_rust_f64(c.real), _rust_f64(c.imag)) for _, c in self._members)
+        return "SparsePauliOp('%s', [%s])" % (labels, coeffs)
+
+    __str__ = __repr__
+
+    def __add__(self, other):                                          # lib.rs:588-593
+        return SparsePauliOp([p for p, _ in self._members + other._members],
+                             [c for _, c in self._members + other._members])
+
+    # -- make_params (accel.rs:141-157) --------------------------------------------
+    def terms(self):
+        """qr_term[T]: (z, x, c') with c' = coeff * (+i)^base_phase * (-i)^#Y.
+
+        The (-i)^#Y factor is accel.rs:147-153.  For the base phase this follows the
+        reference's default to_matrix, base_coeff = (+i)^base_phase (lib.rs:182-190,211);
+        the row-wise code uses (-i)^base_phase instead, which differs only for labels with
+        an i/j prefix -- parity is defined against to_matrix."""
+        if self._terms is None:
+            unit = [(1.0, 0.0), (0.0, -1.0), (-1.0, 0.0), (0.0, 1.0)]
+            t = np.zeros(len(self._members), TERM_DTYPE)
+            for i, (p, c) in enumerate(self._members):
+                ur, ui = unit[(p._ny - p.base_phase) % 4]
+                t[i] = (p._z, p._x, ur * c.real - ui * c.imag, ur * c.imag + ui * c.real)
+            self._terms = t
+        return self._terms
+
+    def plan(self, device=0):
+        if device not in self._plans:
+            n = self.num_qubits()
+            if n > 32:
+                raise QrustyCudaError(_ffi.QR_ERR_UNSUPPORTED, "n_qubits > 32 is not supported")
+            self._plans[device] = _Plan(n, self.terms(), device)
+        return self._plans[device]
+
+    # -- matrix build ----------------------------------------------------------------
+    def to_matrix(self):
+        return self.to_matrix_mode("Cuda")
+
+    def to_matrix_mode(self, mode=""):
+        """Mode strings of AccelMode::try_from (lib.rs:293-331) plus "Cuda" and
+        "Cuda/<ngpus>" (row blocks over the first <ngpus> devices of this process)."""
+        ngpus = _parse_mode(mode)
+        dim = 1 << self.num_qubits()
+        if ngpus > dim or dim % ngpus:
+            raise Exception("to_matrix_mode: %d GPUs do not divide %d rows" % (ngpus, dim))
+        shards = []
+        for d in range(ngpus):
+            plan = self.plan(d)
+            lo, hi = dim // ngpus * d, dim // ngpus * (d + 1)
+            shards.append(_Shard.build(plan, lo, hi))
+        for s in shards:
+            call("qr_set_device", s.device)
+            synchronize()
+        return SpMat._from_shards((dim, dim), shards)
+
+    # -- matrix-free H.v -------------------------------------------------------------
+    def apply(self, v, device=0):
+        """y = H v without building H (host vectors in, host vector out)."""
+        plan = self.plan(device)
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        if v.shape != (plan.dim,):
+            raise Exception("apply: vector has the wrong length")
+        y = np.empty(plan.dim, np.complex128)
+        call("qr_apply_host", plan.handle, v.ctypes.data, y.ctypes.data)
+        return y
+
+    def diagonal(self, device=0):
+        plan = self.plan(device)
+        d = DeviceBuffer(plan.dim * 16, device)
+        call("qr_diagonal_device", plan.handle, 0, plan.dim, d.ptr, None)
+        return d.download(np.empty(plan.dim, np.complex128))
+
+
+class _Shard:
+    """Rows [lo,hi) of the CSR, resident on one device."""
+
+    def __init__(self, plan, lo, hi, indptr, indices, data):
+        self.plan, self.lo, self.hi = plan, lo, hi
+        self.device = plan.device if plan is not None else indptr.device
+        self.indptr, self.indices, self.data = indptr, indices, data
+        self.nnz = (hi - lo) * plan.n_groups if plan is not None else None
+
+    @classmethod
+    def build(cls, plan, lo, hi):
+        rows, G = hi - lo, plan.n_groups
+        indptr = DeviceBuffer((rows + 1) * 8, plan.device)
+        indices = DeviceBuffer(rows * G * 8, plan.device)
+        data = DeviceBuffer(rows * G * 16, plan.device)
+        call("qr_build_rows_device", plan.handle, lo, hi, indptr.ptr, indices.ptr, data.ptr,
+             _ffi.QR_INDPTR_GLOBAL, None)
+        return cls(plan, lo, hi, indptr, indices, data)
+
+
+class SpMat:
+    """pyqrusty.SpMat (pyqrusty/src/lib.rs:33-260): a boxed CSR that export() moves out.
+    Here the CSR lives in HBM (one shard per GPU) until export() copies it to the host."""
+
+    def __init__(self):
+        self._shape = None
+        self._shards = None
+
+    @classmethod
+    def _from_shards(cls, shape, shards):
+        m = cls()
+        m._shape, m._shards = shape, shards
+        return m
+
+    @staticmethod
+    def new_unchecked(shape, data, indices, indptr, device=0):
+        """pyqrusty/src/lib.rs:104-116: wraps caller arrays without validation (uploads them)."""
+        data = np.ascontiguousarray(data, dtype=np.complex128)
+        indices = np.ascontiguousarray(indices, dtype=np.uint64)
+        indptr = np.ascontiguousarray(indptr, dtype=np.uint64)
+        bufs = []
+        for a in (indptr, indices, data):
+            b = DeviceBuffer(max(a.nbytes, 16), device)
+            b.upload(a)
+            bufs.append(b)
+        sh = _Shard(None, 0, int(shape[0]), *bufs)
+        sh.nnz = len(data)
+        return SpMat._from_shards((int(shape[0]), int(shape[1])), [sh])
+
+    def _live(self, what):
+        if self._shards is None:
+            raise Exception(what)
+        return self._shards
+
+    def shape(self):
+        self._live("SpMat.shape(): matrix is already dropped")
+        return self._shape
+
+    def nnz(self):
+        return sum(s.nnz for s in self._live("cannot get NNZ of an exported sparse matrix"))
+
+    def __repr__(self):
+        if self._shards is None:
+            return "<already-dropped sparse matrix of type Complex64>"
+        return ("<%dx%d sparse matrix of type Complex64\n\twith %d stored elements in Compressed Sparse Row format>"
+                % (self._shape[0], self._shape[1], self.nnz()))
+
+    __str__ = __repr__
+
+    def __copy__(self):
+        shards = []
+        for s in self._live("cannot copy an exported sparse matrix"):
+            bufs = []
+            for b in (s.indptr, s.indices, s.data):
+                nb = DeviceBuffer(b.nbytes, b.device)
+                tmp = np.empty(b.nbytes, np.uint8)
+                b.download(tmp)
+                nb.upload(tmp)
+                bufs.append(nb)
+            c = _Shard(s.plan, s.lo, s.hi, *bufs)
+            c.nnz = s.nnz
+            shards.append(c)
+        return SpMat._from_shards(self._shape, shards)
+
+    def diagonal(self):
+        shards = self._live("SpMat.diagonal(): already-exported sparse matrix")
+        out = np.empty(min(self._shape), np.complex128)
+        for s in shards:
+            if s.plan is None:      # caller-supplied CSR (new_unchecked): generic sparse algebra, off the path
+                shape, data, indices, indptr = self.__copy__().export()
+                from scipy.sparse import csr_matrix as _csr
+                return _csr((data, indices, indptr), shape=shape).diagonal()
+            d = DeviceBuffer((s.hi - s.lo) * 16, s.device)
+            call("qr_diagonal_device", s.plan.handle, s.lo, s.hi, d.ptr, None)
+            d.download(out[s.lo:s.hi])
+        return out
+
+    def export(self):
+        """-> ((rows, cols), data, indices, indptr), then the matrix is gone
+        (pyqrusty/src/lib.rs:190-214).  Arrays live in pinned host memory."""
+        shards = self._live("cannot export from an already-exported sparse matrix")
+        nnz = self.nnz()
+        data = pinned_empty(nnz, np.complex128)
+        indices = pinned_empty(nnz, np.uint64)
+        indptr = pinned_empty(self._shape[0] + 1, np.uint64)
+        off = 0
+        streams = []
+        for s in shards:
+            rows = s.hi - s.lo
+            call("qr_set_device", s.device)
+            st = C.c_void_p()
+            call("qr_stream_create", C.byref(st))
+            streams.append((s.device, st))
+            s.data.download(data[off:off + s.nnz], stream=st)
+            s.indices.download(indices[off:off + s.nnz], stream=st)
+            s.indptr.download(indptr[s.lo:s.lo + rows + 1], stream=st)
+            off += s.nnz
+        for dev, st in streams:
+            call("qr_set_device", dev)
+            call("qr_stream_synchronize", st)
+            call("qr_stream_destroy", st)
+        shape = self._shape
+        self._shards = None
+        return shape, data, indices, indptr
+
+
+def csr_matrix(m):
+    """pyqrusty/python/pyqrusty/__init__.py:14-17."""
+    (shape, data, indices, indptr) = m.export()
+    from scipy.sparse import csr_matrix as _csr
+    return _csr((data, indices, indptr), shape=shape, dtype=complex)
+
+
+def spmat_dot_densevec(spmat, x):
+    """pyqrusty spmat_dot_densevec (pyqrusty/src/lib.rs:476-491) -> accel.rs:338-370:
+    CSR SpMV over the device-resident matrix, sequential per row in stored order."""
+    shards = spmat._live("cannot multiply with an exported sparse matrix")
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    y = np.empty(spmat._shape[0], np.complex128)
+    for s in shards:
+        rows = s.hi - s.lo
+        dv = DeviceBuffer(max(x.nbytes, 16), s.device)
+        dv.upload(x)
+        dy = DeviceBuffer(max(rows * 16, 16), s.device)
+        call("qr_spmv_device", rows, s.indptr.ptr, s.indices.ptr, s.data.ptr, dv.ptr, dy.ptr, None)
+        dy.download(y[s.lo:s.hi])
+    return y
+
+
+def _c2(a):
+    a = complex(a)
+    return (C.c_double * 2)(a.real, a.imag)
+
+
+def _vec_op(name, n, scalars, inputs):
+    bufs = []
+    for v in inputs:
+        b = DeviceBuffer(max(n * 16, 16))
+        b.upload(v)
+        bufs.append(b)
+    z = DeviceBuffer(max(n * 16, 16))
+    args = [n]
+    it_s, it_b = iter(scalars), iter(bufs)
+    for kind in {"qr_axpby_device": "svsv", "qr_axpy_device": "svv", "qr_ax_device": "sv"}[name]:
+        args.append(next(it_s) if kind == "s" else next(it_b).ptr)
+    call(name, *args, z.ptr, None)
+    return z.download(np.empty(n, np.complex128))
+
+
+def _vec(x):
+    return np.ascontiguousarray(x, dtype=np.complex128)
+
+
+def axpby(a, x, b, y):
+    """z = a*x + b*y (accel.rs:374-379)."""
+    x, y = _vec(x), _vec(y)
+    return _vec_op("qr_axpby_device", len(x), [_c2(a), _c2(b)], [x, y])
+
+
+def axpy(a, x, y):
+    """z = a*x + y (accel.rs:381-386)."""
+    x, y = _vec(x), _vec(y)
+    return _vec_op("qr_axpy_device", len(x), [_c2(a)], [x, y])
+
+
+def ax(a, x):
+    """z = a*x (accel.rs:388-393)."""
+    x = _vec(x)
+    return _vec_op("qr_ax_device", len(x), [_c2(a)], [x])

@@ -1,0 +1,146 @@
+// canonicalise.cuh -- K1: term canonicalisation on the GPU.
+//
+// Replaces what rowwise::make_row redoes for EVERY row with a stable sort of all
+// T terms (qrusty/src/accel.rs:174-205): group the terms by X-mask once, keeping
+// the original term order inside a group (that order is the reference's
+// left-to-right summation order, accel.rs:191-205), and precompute the tables the
+// fill kernel needs to place a group in a row without sorting (plan.cuh).
+//
+// One CTA of 512 threads; T is at most tens of thousands (a Hamiltonian's term
+// list), the output of this kernel is what 2^n rows then share.
+//   1. stable LSD radix sort of (x, original index), 8-bit digits, ceil(n/8) passes:
+//      histogram (shared atomics) -> bin scan -> per-tile stable ranking with
+//      __match_any_sync + per-warp digit counts -> scatter.
+//   2. head flags + CTA scan (scan.cuh) -> group ids, gx[], goff[], G.
+//   3. rank tables cnt[g][b] by two binary searches on the sorted masks, lr5[g][j].
+#pragma once
+#include "plan.cuh"
+#include "scan.cuh"
+
+namespace qr {
+
+constexpr int K1_THREADS = 512;
+constexpr int K1_WARPS = K1_THREADS / 32;
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint32_t key)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *a, uint32_t n, uint32_t key)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
+{
+    __shared__ uint32_t hist[256];                  // digit histogram, then running bin base
+    __shared__ uint16_t wcount[K1_WARPS][256];      // per-warp digit counts of the current tile
+    __shared__ uint32_t woffset[K1_WARPS][256];     // per-warp digit start positions
+    __shared__ uint32_t scan_scratch[33];
+    __shared__ uint32_t max_group;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t T = p.n_terms;
+
+    // ---- 0. keys = X-masks, payload = original index ---------------------------------
+    for (uint32_t i = tid; i < T; i += K1_THREADS) { p.key_a[i] = (uint32_t)p.raw[i].x; p.idx_a[i] = i; }
+    for (uint32_t i = tid; i < K1_WARPS * 256; i += K1_THREADS) (&wcount[0][0])[i] = 0;
+    if (tid == 0) max_group = 0;
+    __syncthreads();
+
+    // ---- 1. stable LSD radix sort -----------------------------------------------------
+    uint32_t *kin = p.key_a, *kout = p.key_b, *iin = p.idx_a, *iout = p.idx_b;
+    const int passes = (p.n_qubits + 7) / 8;
+    for (int pass = 0; pass < passes; pass++) {
+        const int shift = 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < T; i += K1_THREADS) atomicAdd(&hist[(kin[i] >> shift) & 255u], 1u);
+        __syncthreads();
+        uint32_t total;
+        uint32_t h = tid < 256 ? hist[tid] : 0u;
+        uint32_t excl = block_exclusive_scan(h, scan_scratch, &total);
+        if (tid < 256) hist[tid] = excl;            // hist[d] = next free output position of digit d
+        __syncthreads();
+
+        for (uint32_t tile = 0; tile < T; tile += K1_THREADS) {
+            const uint32_t i = tile + tid;
+            const bool valid = i < T;
+            uint32_t key = 0, idx = 0, d = 0xffffffffu;     // invalid lanes form their own match group
+            if (valid) { key = kin[i]; idx = iin[i]; d = (key >> shift) & 255u; }
+            const unsigned peers = __match_any_sync(FULL_MASK, d);
+            const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank_in_warp == 0) wcount[warp][d] = (uint16_t)__popc(peers);
+            __syncthreads();
+            if (tid < 256) {                        // digit tid: prefix over warps, in element order
+                uint32_t run = hist[tid];
+#pragma unroll 4
+                for (int w = 0; w < K1_WARPS; w++) {
+                    uint32_t c = wcount[w][tid];
+                    wcount[w][tid] = 0;
+                    woffset[w][tid] = run;
+                    run += c;
+                }
+                hist[tid] = run;
+            }
+            __syncthreads();
+            if (valid) { uint32_t pos = woffset[warp][d] + rank_in_warp; kout[pos] = key; iout[pos] = idx; }
+            __syncthreads();
+        }
+        uint32_t *t = kin; kin = kout; kout = t;
+        t = iin; iin = iout; iout = t;
+    }
+    // sorted (key, idx) now in (kin, iin)
+
+    // ---- 2. head flags -> groups; gather the sorted term table ------------------------
+    uint32_t carry = 0;
+    for (uint32_t tile = 0; tile < T; tile += K1_THREADS) {
+        const uint32_t i = tile + tid;
+        const bool valid = i < T;
+        uint32_t key = valid ? kin[i] : 0u;
+        uint32_t head = (valid && (i == 0 || kin[i - 1] != key)) ? 1u : 0u;
+        uint32_t total;
+        uint32_t excl = block_exclusive_scan(head, scan_scratch, &total);
+        if (valid) {
+            uint32_t gid = carry + excl;            // index of the group that starts at or before i ...
+            if (head) { p.gx[gid] = key; p.goff[gid] = i; }
+            uint32_t src = iin[i];
+            p.perm[i] = src;
+            p.tz[i] = (uint32_t)p.raw[src].z;
+            p.tc[i] = make_double2(p.raw[src].re, p.raw[src].im);
+        }
+        carry += total;
+    }
+    const uint32_t G = carry;
+    if (tid == 0) { p.goff[G] = T; p.meta[0] = G; }
+    __syncthreads();
+
+    // ---- 3. rank tables ---------------------------------------------------------------
+    const uint32_t nq = (uint32_t)p.n_qubits;
+    for (uint32_t q = tid; q < G * 32u; q += K1_THREADS) {
+        const uint32_t g = q >> 5, b = q & 31u;
+        uint32_t c = 0;
+        if (b < nq) {
+            const uint32_t low = (1u << b) - 1u;
+            const uint32_t lo = (p.gx[g] ^ (1u << b)) & ~low;     // same prefix above b, bit b flipped
+            c = upper_bound_u32(p.gx, G, lo | low) - lower_bound_u32(p.gx, G, lo);
+        }
+        p.cnt[q] = c;
+    }
+    for (uint32_t g = tid; g < G; g += K1_THREADS) atomicMax(&max_group, p.goff[g + 1] - p.goff[g]);
+    __syncthreads();
+    for (uint32_t q = tid; q < G * 32u; q += K1_THREADS) {
+        const uint32_t g = q >> 5, j = q & 31u;
+        uint32_t s = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < 5; b++) s += ((j >> b) & 1u) ? p.cnt[g * 32u + b] : 0u;
+        p.lr5[q] = s;
+    }
+    if (tid == 0) { p.meta[1] = max_group; p.meta[2] = 0; p.meta[3] = 0; }
+}
+
+}  // namespace qr

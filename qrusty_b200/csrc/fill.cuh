@@ -1,0 +1,155 @@
+// fill.cuh -- K3: the CSR fill kernels (indices + data + indptr).
+//
+// Replaces the per-row work of rowwise::make_row (qrusty/src/accel.rs:171-210)
+// and the assembly of make_unsafe_vectors_chunked (accel.rs:267-336): no per-row
+// sort, no per-row allocation, no concat passes -- every (row, group) value is
+// computed in registers and lands at its final position.
+//
+// Thread mapping (both kernels): lane <-> row.  A warp owns 32 consecutive,
+// 32-aligned rows and walks the groups, so everything that depends only on the
+// group (mask, term list, rank-table row) is warp-uniform: no divergence in the
+// term loop, broadcast loads of the term table.
+//
+//   col   = r ^ gx[g]                                            accel.rs:176
+//   value = sum over the group's terms, in original term order,  accel.rs:177-184,
+//           of (popc(r & z_t) odd ? -c'_t : c'_t)                :191-205
+//           -- sign applied by flipping the IEEE sign bit, adds are __dadd_rn,
+//           the first term is taken as is (no 0 + x), so data is bit-identical
+//           to the reference's fold, signed zeros included.
+//   slot  = sum_b cnt[g][b] * bit_b(gx[g] ^ r)                   (plan.cuh)
+//           bits >= 5 are warp-uniform: lane b contributes bit b, one REDUX;
+//           bits < 5 come from lr5[g][(gx[g]^lane)&31].
+#pragma once
+#include "plan.cuh"
+
+namespace qr {
+
+__device__ __forceinline__ double flip_sign(double d, uint32_t sign_bit)
+{
+    return __hiloint2double(__double2hiint(d) ^ (int)sign_bit, __double2loint(d));
+}
+
+// Value of group [t0,t1) in row r.  t1 > t0 always (a group has >= 1 term).
+__device__ __forceinline__ double2 group_value(const uint32_t *__restrict__ tz,
+                                               const double2 *__restrict__ tc,
+                                               uint32_t t0, uint32_t t1, uint32_t r)
+{
+    double2 c = __ldg(&tc[t0]);
+    uint32_t s = (uint32_t)(__popc(r & __ldg(&tz[t0])) & 1) << 31;
+    double re = flip_sign(c.x, s), im = flip_sign(c.y, s);
+    for (uint32_t t = t0 + 1; t < t1; t++) {
+        c = __ldg(&tc[t]);
+        s = (uint32_t)(__popc(r & __ldg(&tz[t])) & 1) << 31;
+        re = __dadd_rn(re, flip_sign(c.x, s));
+        im = __dadd_rn(im, flip_sign(c.y, s));
+    }
+    return make_double2(re, im);
+}
+
+// Slot of group g in each of the warp's 32 rows (all 32 lanes must call).
+// warp_row_base: the warp's first row (multiple of 32).
+__device__ __forceinline__ uint32_t group_slot(const PlanDev &p, uint32_t g, uint32_t x,
+                                               uint32_t warp_row_base, uint32_t lane)
+{
+    const uint32_t c = __ldg(&p.cnt[g * 32u + lane]);
+    const uint32_t bit = ((x ^ warp_row_base) >> lane) & 1u;
+    const uint32_t hi = __reduce_add_sync(0xffffffffu, (lane >= 5u && bit) ? c : 0u);
+    return hi + __ldg(&p.lr5[g * 32u + ((x ^ lane) & 31u)]);
+}
+
+// ---------------------------------------------------------------------------------
+// Direct kernel: any row range, any G.  Stores go straight to global memory: a
+// warp's 32 stores of one group are G*16 B apart, so this is the correctness
+// baseline and the edge/large-G path, not the fast path.
+// ---------------------------------------------------------------------------------
+constexpr int FILL_DIRECT_THREADS = 256;
+
+__global__ void __launch_bounds__(FILL_DIRECT_THREADS)
+fill_direct_kernel(PlanDev p, uint32_t G, uint64_t lo, uint64_t hi, uint64_t out_row0, uint64_t req_hi,
+                   uint64_t indptr_base, uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
+                   double2 *__restrict__ data)
+{
+    // rows [lo,hi) of a request [out_row0, req_hi): outputs are indexed relative to out_row0
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp_id = (uint64_t)blockIdx.x * (FILL_DIRECT_THREADS / 32) + (threadIdx.x >> 5);
+    const uint64_t wbase64 = (lo & ~(uint64_t)31) + warp_id * 32u;
+    if (wbase64 >= hi) return;                                   // warp-uniform
+    const uint32_t wbase = (uint32_t)wbase64;
+    const uint64_t r64 = wbase64 + lane;
+    const uint32_t r = (uint32_t)r64;
+    const bool live = r64 >= lo && r64 < hi;
+    const uint64_t out_row = (r64 - out_row0) * G;               // garbage when !live, never used
+
+    for (uint32_t g = 0; g < G; g++) {
+        const uint32_t x = __ldg(&p.gx[g]);
+        const uint32_t slot = group_slot(p, g, x, wbase, lane);
+        const double2 v = group_value(p.tz, p.tc, __ldg(&p.goff[g]), __ldg(&p.goff[g + 1]), r);
+        if (live) {
+            indices[out_row + slot] = (uint64_t)(r ^ x);
+            data[out_row + slot] = v;
+        }
+    }
+    if (indptr != nullptr && live) {
+        indptr[r64 - out_row0] = indptr_base + (r64 - out_row0) * G;
+        if (r64 + 1 == req_hi) indptr[req_hi - out_row0] = indptr_base + (req_hi - out_row0) * G;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Staged kernel: a CTA owns a tile of R = 32*RW whole rows (aligned to R).  The
+// tile's R*G entries are contiguous in BOTH output arrays, so the CTA assembles
+// them in shared memory in final order and one thread hands each array to the
+// TMA as a single bulk copy (cp.async.bulk.global.shared::cta): HBM sees only
+// full-line, perfectly sequential writes and no LSU instruction is spent on them.
+// The GW warps of a row strip split the groups (g = gw, gw+GW, ...).
+// Requires R*G*24 B of shared memory; the host picks (RW, GW) from G.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_store_smem_to_global(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+template <int RW, int GW>
+__global__ void __launch_bounds__(32 * RW * GW)
+fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
+                   uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
+                   double2 *__restrict__ data, uint64_t indptr_last_row)
+{
+    constexpr uint32_t R = 32u * RW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                         // R*G * 16 B
+    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)R * G * 16u);  // R*G *  8 B
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t rw = warp % RW, gw = warp / RW;
+    const uint64_t tile_base = tile_row0 + (uint64_t)blockIdx.x * R;
+    const uint32_t wbase = (uint32_t)tile_base + 32u * rw;
+    const uint32_t r = wbase + lane;
+    const uint32_t srow = (32u * rw + lane) * G;
+
+    for (uint32_t g = gw; g < G; g += GW) {
+        const uint32_t x = __ldg(&p.gx[g]);
+        const uint32_t slot = group_slot(p, g, x, wbase, lane);
+        const double2 v = group_value(p.tz, p.tc, __ldg(&p.goff[g]), __ldg(&p.goff[g + 1]), r);
+        sidx[srow + slot] = (uint64_t)(r ^ x);
+        sdat[srow + slot] = v;
+    }
+    if (gw == 0 && indptr != nullptr) {
+        const uint64_t lr = tile_base + 32u * rw + lane - row_lo;
+        indptr[lr] = indptr_base + lr * G;
+        if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+    }
+    // generic-proxy writes -> visible to the async proxy, then one thread issues the copies
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t off = (tile_base - row_lo) * G;
+        bulk_store_smem_to_global(data + off, sdat, R * G * 16u);
+        bulk_store_smem_to_global(indices + off, sidx, R * G * 8u);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
+    }
+}
+
+}  // namespace qr

@@ -1,0 +1,42 @@
+// plan.cuh -- device-side view of a canonicalised operator (what every kernel reads).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/qrusty_cuda.h"
+
+namespace qr {
+
+// HBM layout of one plan.  All tables are tiny next to the CSR (<= 300 B per
+// term) and stay L2-resident during a build.
+//
+//   raw   qr_term[T]      the caller's terms, original order (make_params output)
+//   tz    u32[T]          Z-masks, sorted by X-mask, original order inside a group
+//   tc    double2[T]      coefficients c', same order
+//   perm  u32[T]          original index of each sorted term
+//   gx    u32[G]          distinct X-masks, ascending
+//   goff  u32[G+1]        group g owns sorted terms [goff[g], goff[g+1])
+//   cnt   u32[G][32]      cnt[g][b] = #{h != g : msb(gx[g]^gx[h]) == b}
+//   lr5   u32[G][32]      lr5[g][j] = sum_{b<5} cnt[g][b] * bit_b(j)
+//   meta  u32[4]          {G, max terms in a group, 0, 0}
+//
+// Slot of group g in row r (columns ascending, accel.rs:188):
+//   slot(r,g) = sum_b cnt[g][b] * bit_b(gx[g] ^ r)
+// because h precedes g in row r  <=>  (r^gx[h]) < (r^gx[g])  <=>  at the most
+// significant bit where gx[h] and gx[g] differ, r^gx[g] has a 1.
+struct PlanDev {
+    int       n_qubits;
+    uint32_t  n_terms;
+    const qr_term *raw;
+    uint32_t *key_a, *key_b, *idx_a, *idx_b;   // radix-sort ping-pong, u32[T]
+    uint32_t *tz;
+    double2  *tc;
+    uint32_t *perm;
+    uint32_t *gx;
+    uint32_t *goff;
+    uint32_t *cnt;
+    uint32_t *lr5;
+    uint32_t *meta;
+};
+
+}  // namespace qr

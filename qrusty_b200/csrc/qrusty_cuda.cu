@@ -1,0 +1,661 @@
+// qrusty_cuda.cu -- the extern "C" boundary (include/qrusty_cuda.h) over the sm_100a kernels.
+// No torch, no CPU compute path: every compute entry point launches kernels or fails.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h>   // types only; the library is dlopen'ed (see NcclApi)
+
+#include "../../include/qrusty_cuda.h"
+#include "apply.cuh"
+#include "canonicalise.cuh"
+#include "fill.cuh"
+#include "plan.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define QR_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? QR_ERR_OOM : QR_ERR_CUDA,          \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+    } while (0)
+
+#define QR_LAUNCH_CHECK(name)                                                                 \
+    do {                                                                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(QR_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr size_t MAX_SMEM = 227 * 1024;
+
+}  // namespace
+
+struct qr_plan {
+    qr::PlanDev dev{};
+    int device = 0;
+    int n_qubits = 0;
+    uint64_t dim = 0, n_terms = 0, n_groups = 0;
+    void *slab = nullptr;             // one allocation holding every table of PlanDev
+    // staged-fill configuration chosen from G
+    int rw = 0, gw = 0;
+    // lazily allocated scratch
+    double2 *dot_partials = nullptr;
+    void *win_buf[2] = {nullptr, nullptr};
+    size_t win_bytes = 0;
+    cudaStream_t win_stream[2] = {nullptr, nullptr};
+};
+
+struct qr_comm {
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0, device = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------
+// staged fill: template dispatch
+// ---------------------------------------------------------------------------------
+using StagedFn = void (*)(qr::PlanDev, uint32_t, uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *,
+                          double2 *, uint64_t);
+struct StagedCfg { int rw, gw; StagedFn fn; };
+const StagedCfg kStaged[] = {
+    {1, 4, qr::fill_staged_kernel<1, 4>},  {1, 8, qr::fill_staged_kernel<1, 8>},
+    {1, 16, qr::fill_staged_kernel<1, 16>}, {2, 2, qr::fill_staged_kernel<2, 2>},
+    {2, 4, qr::fill_staged_kernel<2, 4>},  {2, 8, qr::fill_staged_kernel<2, 8>},
+    {4, 1, qr::fill_staged_kernel<4, 1>},  {4, 2, qr::fill_staged_kernel<4, 2>},
+    {4, 4, qr::fill_staged_kernel<4, 4>},  {8, 1, qr::fill_staged_kernel<8, 1>},
+    {8, 2, qr::fill_staged_kernel<8, 2>},
+};
+
+const StagedCfg *find_staged(int rw, int gw)
+{
+    for (const auto &c : kStaged) if (c.rw == rw && c.gw == gw) return &c;
+    return nullptr;
+}
+
+// Pick (RW, GW) from G: as many resident warps per SM as the R*G*24-byte tile allows.
+void choose_staged(qr_plan *pl)
+{
+    pl->rw = pl->gw = 0;
+    const uint64_t G = pl->n_groups;
+    if (const char *env = getenv("QR_FILL_CFG")) {           // "RW,GW" override for experiments
+        int rw = 0, gw = 0;
+        if (sscanf(env, "%d,%d", &rw, &gw) == 2 && find_staged(rw, gw) && (uint64_t)32 * rw * G * 24 <= MAX_SMEM) {
+            pl->rw = rw; pl->gw = gw; return;
+        }
+    }
+    const uint64_t row_bytes = G * 24;
+    if (64 * row_bytes <= 56 * 1024)       { pl->rw = 2; pl->gw = 4; }   // >= 4 CTAs/SM of 8 warps
+    else if (32 * row_bytes <= 113 * 1024) { pl->rw = 1; pl->gw = 8; }   // 2+ CTAs/SM
+    else if (32 * row_bytes <= MAX_SMEM)   { pl->rw = 1; pl->gw = 16; }  // 1 CTA/SM
+}
+
+int launch_direct(const qr_plan *pl, uint64_t lo, uint64_t hi, uint64_t out_row0, uint64_t req_hi,
+                  uint64_t indptr_base, uint64_t *indptr, uint64_t *indices, double2 *data, cudaStream_t st);
+
+}  // namespace
+
+// =====================================================================================
+// error / misc
+// =====================================================================================
+extern "C" const char *qr_last_error(void) { return g_err.c_str(); }
+extern "C" int qr_version(void) { return QR_VERSION; }
+extern "C" uint64_t qr_kernel_launches(void) { return g_launches.load(); }
+
+// =====================================================================================
+// plan
+// =====================================================================================
+static int run_canonicalise(qr_plan *pl, cudaStream_t st)
+{
+    qr::canonicalise_kernel<<<1, qr::K1_THREADS, 0, st>>>(pl->dev);
+    QR_LAUNCH_CHECK("canonicalise_kernel");
+    return QR_OK;
+}
+
+extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms, int device,
+                              uint32_t flags, qr_plan **out)
+{
+    (void)flags;
+    if (!out) return fail(QR_ERR_INVALID, "qr_plan_create: out is NULL");
+    *out = nullptr;
+    if (!terms || n_terms == 0)
+        return fail(QR_ERR_INVALID, "qr_plan_create: at least one term must be supplied");   // lib.rs:358-360
+    if (n_qubits < 1) return fail(QR_ERR_INVALID, "qr_plan_create: n_qubits must be >= 1");
+    if (n_qubits > 32) return fail(QR_ERR_UNSUPPORTED, "qr_plan_create: n_qubits > 32 is not supported");
+    if (n_terms > 0x7fffffffu / 32) return fail(QR_ERR_UNSUPPORTED, "qr_plan_create: too many terms");
+    const uint64_t dim = 1ull << n_qubits;
+    for (size_t t = 0; t < n_terms; t++)
+        if (terms[t].x >= dim || terms[t].z >= dim)
+            return fail(QR_ERR_INVALID, "qr_plan_create: term mask has bits outside n_qubits");
+
+    QR_CUDA(cudaSetDevice(device));
+    qr_plan *pl = new (std::nothrow) qr_plan();
+    if (!pl) return fail(QR_ERR_OOM, "qr_plan_create: host allocation failed");
+    pl->device = device; pl->n_qubits = n_qubits; pl->dim = dim; pl->n_terms = n_terms;
+
+    const size_t T = n_terms;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_raw = carve(T * sizeof(qr_term));
+    const size_t o_ka = carve(T * 4), o_kb = carve(T * 4), o_ia = carve(T * 4), o_ib = carve(T * 4);
+    const size_t o_tz = carve(T * 4), o_tc = carve(T * 16), o_perm = carve(T * 4);
+    const size_t o_gx = carve(T * 4), o_goff = carve((T + 1) * 4);
+    const size_t o_cnt = carve(T * 128), o_lr5 = carve(T * 128), o_meta = carve(16);
+    cudaError_t e = cudaMalloc(&pl->slab, off);
+    if (e != cudaSuccess) { delete pl; return fail(QR_ERR_OOM, std::string("qr_plan_create: cudaMalloc: ") + cudaGetErrorString(e)); }
+    char *b = static_cast<char *>(pl->slab);
+    qr::PlanDev &d = pl->dev;
+    d.n_qubits = n_qubits; d.n_terms = (uint32_t)T;
+    d.raw = reinterpret_cast<const qr_term *>(b + o_raw);
+    d.key_a = reinterpret_cast<uint32_t *>(b + o_ka); d.key_b = reinterpret_cast<uint32_t *>(b + o_kb);
+    d.idx_a = reinterpret_cast<uint32_t *>(b + o_ia); d.idx_b = reinterpret_cast<uint32_t *>(b + o_ib);
+    d.tz = reinterpret_cast<uint32_t *>(b + o_tz); d.tc = reinterpret_cast<double2 *>(b + o_tc);
+    d.perm = reinterpret_cast<uint32_t *>(b + o_perm);
+    d.gx = reinterpret_cast<uint32_t *>(b + o_gx); d.goff = reinterpret_cast<uint32_t *>(b + o_goff);
+    d.cnt = reinterpret_cast<uint32_t *>(b + o_cnt); d.lr5 = reinterpret_cast<uint32_t *>(b + o_lr5);
+    d.meta = reinterpret_cast<uint32_t *>(b + o_meta);
+
+    auto bail = [&](int code) { cudaFree(pl->slab); delete pl; return code; };
+    e = cudaMemcpy(b + o_raw, terms, T * sizeof(qr_term), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: H2D: ") + cudaGetErrorString(e)));
+    int rc = run_canonicalise(pl, nullptr);
+    if (rc != QR_OK) return bail(rc);
+    uint32_t meta[4] = {0, 0, 0, 0};
+    e = cudaMemcpy(meta, d.meta, sizeof(meta), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: canonicalise: ") + cudaGetErrorString(e)));
+    pl->n_groups = meta[0];
+    if (pl->n_groups == 0 || pl->n_groups > T) return bail(fail(QR_ERR_CUDA, "qr_plan_create: canonicalisation produced no groups"));
+    choose_staged(pl);
+    *out = pl;
+    return QR_OK;
+}
+
+extern "C" int qr_plan_destroy(qr_plan *pl)
+{
+    if (!pl) return QR_OK;
+    cudaSetDevice(pl->device);
+    for (int i = 0; i < 2; i++) {
+        if (pl->win_buf[i]) cudaFree(pl->win_buf[i]);
+        if (pl->win_stream[i]) cudaStreamDestroy(pl->win_stream[i]);
+    }
+    if (pl->dot_partials) cudaFree(pl->dot_partials);
+    if (pl->slab) cudaFree(pl->slab);
+    delete pl;
+    return QR_OK;
+}
+
+extern "C" int qr_plan_info(const qr_plan *pl, qr_plan_info_t *info)
+{
+    if (!pl || !info) return fail(QR_ERR_INVALID, "qr_plan_info: NULL argument");
+    info->n_qubits = pl->n_qubits; info->device = pl->device; info->dim = pl->dim;
+    info->n_terms = pl->n_terms; info->n_groups = pl->n_groups; info->nnz = pl->n_groups * pl->dim;
+    return QR_OK;
+}
+
+extern "C" int qr_plan_groups(const qr_plan *pl, uint64_t *xmask, uint32_t *group_offsets, uint32_t *term_order)
+{
+    if (!pl) return fail(QR_ERR_INVALID, "qr_plan_groups: NULL plan");
+    QR_CUDA(cudaSetDevice(pl->device));
+    const size_t G = pl->n_groups, T = pl->n_terms;
+    if (xmask) {
+        std::vector<uint32_t> tmp(G);
+        QR_CUDA(cudaMemcpy(tmp.data(), pl->dev.gx, G * 4, cudaMemcpyDeviceToHost));
+        for (size_t g = 0; g < G; g++) xmask[g] = tmp[g];
+    }
+    if (group_offsets) QR_CUDA(cudaMemcpy(group_offsets, pl->dev.goff, (G + 1) * 4, cudaMemcpyDeviceToHost));
+    if (term_order) QR_CUDA(cudaMemcpy(term_order, pl->dev.perm, T * 4, cudaMemcpyDeviceToHost));
+    return QR_OK;
+}
+
+extern "C" int qr_plan_canonicalise_async(qr_plan *pl, void *stream)
+{
+    if (!pl) return fail(QR_ERR_INVALID, "qr_plan_canonicalise_async: NULL plan");
+    QR_CUDA(cudaSetDevice(pl->device));
+    return run_canonicalise(pl, as_stream(stream));
+}
+
+// =====================================================================================
+// CSR build
+// =====================================================================================
+namespace {
+
+int launch_direct(const qr_plan *pl, uint64_t lo, uint64_t hi, uint64_t out_row0, uint64_t req_hi,
+                  uint64_t indptr_base, uint64_t *indptr, uint64_t *indices, double2 *data, cudaStream_t st)
+{
+    if (hi <= lo) return QR_OK;
+    const uint64_t first = lo & ~(uint64_t)31;
+    const uint64_t warps = (hi - first + 31) / 32;
+    const uint64_t per_cta = qr::FILL_DIRECT_THREADS / 32;
+    const uint64_t ctas = (warps + per_cta - 1) / per_cta;
+    if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_direct: row window too large for one launch");
+    qr::fill_direct_kernel<<<(unsigned)ctas, qr::FILL_DIRECT_THREADS, 0, st>>>(
+        pl->dev, (uint32_t)pl->n_groups, lo, hi, out_row0, req_hi, indptr_base, indptr, indices, data);
+    QR_LAUNCH_CHECK("fill_direct_kernel");
+    return QR_OK;
+}
+
+int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr, uint64_t *d_indices,
+               double2 *d_data, uint32_t flags, cudaStream_t st)
+{
+    const uint64_t G = pl->n_groups;
+    const uint64_t indptr_base = (flags & QR_INDPTR_GLOBAL) ? row_lo * G : 0;
+    uint64_t lo = row_lo, hi = row_hi;
+    const StagedCfg *cfg = (flags & QR_FILL_DIRECT) || pl->rw == 0 ? nullptr : find_staged(pl->rw, pl->gw);
+    if (cfg) {
+        const uint64_t R = 32ull * cfg->rw;
+        const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
+        if (s1 > s0) {
+            const size_t smem = (size_t)(R * G * 24);
+            const uint64_t tiles = (s1 - s0) / R;
+            if (tiles > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_staged: row window too large for one launch");
+            QR_CUDA(cudaFuncSetAttribute(cfg->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // prefix / suffix rows that do not fill a tile
+            int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+            if (rc != QR_OK) return rc;
+            cfg->fn<<<(unsigned)tiles, 32 * cfg->rw * cfg->gw, smem, st>>>(
+                pl->dev, (uint32_t)G, s0, row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo);
+            QR_LAUNCH_CHECK("fill_staged_kernel");
+            lo = s1; hi = row_hi;
+        }
+    }
+    return launch_direct(pl, lo, hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+}
+
+}  // namespace
+
+extern "C" int qr_build_rows_device(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr,
+                                    uint64_t *d_indices, double *d_data, uint32_t flags, void *stream)
+{
+    if (!pl || !d_indices || !d_data) return fail(QR_ERR_INVALID, "qr_build_rows_device: NULL argument");
+    if (row_lo >= row_hi || row_hi > pl->dim) return fail(QR_ERR_INVALID, "qr_build_rows_device: bad row range");
+    if (((uintptr_t)d_indices | (uintptr_t)d_data) & 15) return fail(QR_ERR_INVALID, "qr_build_rows_device: outputs must be 16-byte aligned");
+    QR_CUDA(cudaSetDevice(pl->device));
+    return build_rows(pl, row_lo, row_hi, d_indptr, d_indices, reinterpret_cast<double2 *>(d_data), flags, as_stream(stream));
+}
+
+extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *indptr,
+                             uint64_t *indices, double *data, uint32_t flags)
+{
+    if (!pl || !indices || !data) return fail(QR_ERR_INVALID, "qr_build_host: NULL argument");
+    if (row_lo >= row_hi || row_hi > pl->dim) return fail(QR_ERR_INVALID, "qr_build_host: bad row range");
+    QR_CUDA(cudaSetDevice(pl->device));
+    const uint64_t G = pl->n_groups, rows = row_hi - row_lo;
+    // Row windows through two device buffers / two streams, so the fill of window
+    // k+1 overlaps the PCIe copy of window k (host buffers should be pinned for that).
+    const uint64_t per_row = G * 24 + 8;
+    uint64_t win_rows = (256ull << 20) / per_row;
+    if (win_rows >= rows) win_rows = rows;
+    else { win_rows = win_rows / 256 * 256; if (win_rows == 0) win_rows = 32; }
+    const size_t idx_bytes = align_up(win_rows * G * 8, 256), dat_bytes = align_up(win_rows * G * 16, 256);
+    const size_t ptr_bytes = align_up((win_rows + 1) * 8, 256);
+    const size_t need = idx_bytes + dat_bytes + ptr_bytes;
+    if (pl->win_bytes < need) {
+        for (int i = 0; i < 2; i++) { if (pl->win_buf[i]) cudaFree(pl->win_buf[i]); pl->win_buf[i] = nullptr; }
+        pl->win_bytes = 0;
+        for (int i = 0; i < 2; i++) QR_CUDA(cudaMalloc(&pl->win_buf[i], need));
+        pl->win_bytes = need;
+    }
+    for (int i = 0; i < 2; i++)
+        if (!pl->win_stream[i]) QR_CUDA(cudaStreamCreateWithFlags(&pl->win_stream[i], cudaStreamNonBlocking));
+
+    int k = 0;
+    for (uint64_t w0 = row_lo; w0 < row_hi; w0 += win_rows, k ^= 1) {
+        const uint64_t w1 = w0 + win_rows < row_hi ? w0 + win_rows : row_hi, n = w1 - w0;
+        char *buf = static_cast<char *>(pl->win_buf[k]);
+        double2 *dd = reinterpret_cast<double2 *>(buf);
+        uint64_t *di = reinterpret_cast<uint64_t *>(buf + dat_bytes);
+        uint64_t *dp = reinterpret_cast<uint64_t *>(buf + dat_bytes + idx_bytes);
+        cudaStream_t st = pl->win_stream[k];
+        // window indptr is built "global" relative to the request, then rebased below
+        int rc = build_rows(pl, w0, w1, indptr ? dp : nullptr, di, dd, QR_INDPTR_GLOBAL, st);
+        if (rc != QR_OK) return rc;
+        const uint64_t o = (w0 - row_lo) * G;
+        QR_CUDA(cudaMemcpyAsync(data + 2 * o, dd, n * G * 16, cudaMemcpyDeviceToHost, st));
+        QR_CUDA(cudaMemcpyAsync(indices + o, di, n * G * 8, cudaMemcpyDeviceToHost, st));
+        if (indptr) QR_CUDA(cudaMemcpyAsync(indptr + (w0 - row_lo), dp, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 2; i++) QR_CUDA(cudaStreamSynchronize(pl->win_stream[i]));
+    if (indptr && !(flags & QR_INDPTR_GLOBAL)) {       // windows wrote r*G; local shards want (r-row_lo)*G
+        const uint64_t base = row_lo * G;
+        if (base) for (uint64_t i = 0; i <= rows; i++) indptr[i] -= base;
+    }
+    return QR_OK;
+}
+
+// =====================================================================================
+// H.v and friends
+// =====================================================================================
+static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double2 *v, double2 *y, cudaStream_t st)
+{
+    const uint64_t rows = row_hi - row_lo;
+    const uint64_t ctas = (rows + qr::APPLY_THREADS - 1) / qr::APPLY_THREADS;
+    if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "apply: row window too large for one launch");
+    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y);
+    QR_LAUNCH_CHECK("apply_direct_kernel");
+    return QR_OK;
+}
+
+extern "C" int qr_apply_device(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double *d_v, double *d_y, void *stream)
+{
+    if (!pl || !d_v || !d_y) return fail(QR_ERR_INVALID, "qr_apply_device: NULL argument");
+    if (row_lo >= row_hi || row_hi > pl->dim) return fail(QR_ERR_INVALID, "qr_apply_device: bad row range");
+    if (((uintptr_t)d_v | (uintptr_t)d_y) & 15) return fail(QR_ERR_INVALID, "qr_apply_device: vectors must be 16-byte aligned");
+    QR_CUDA(cudaSetDevice(pl->device));
+    return apply_rows(pl, row_lo, row_hi, reinterpret_cast<const double2 *>(d_v), reinterpret_cast<double2 *>(d_y), as_stream(stream));
+}
+
+extern "C" int qr_apply_host(qr_plan *pl, const double *v, double *y)
+{
+    if (!pl || !v || !y) return fail(QR_ERR_INVALID, "qr_apply_host: NULL argument");
+    QR_CUDA(cudaSetDevice(pl->device));
+    void *dv = nullptr, *dy = nullptr;
+    const size_t bytes = pl->dim * 16;
+    QR_CUDA(cudaMalloc(&dv, bytes));
+    cudaError_t e = cudaMalloc(&dy, bytes);
+    if (e != cudaSuccess) { cudaFree(dv); return fail(QR_ERR_OOM, "qr_apply_host: cudaMalloc failed"); }
+    int rc = QR_OK;
+    e = cudaMemcpy(dv, v, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = apply_rows(pl, 0, pl->dim, static_cast<const double2 *>(dv), static_cast<double2 *>(dy), nullptr);
+        if (rc == QR_OK) e = cudaMemcpy(y, dy, bytes, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dv); cudaFree(dy);
+    if (rc != QR_OK) return rc;
+    if (e != cudaSuccess) return fail(QR_ERR_CUDA, std::string("qr_apply_host: ") + cudaGetErrorString(e));
+    return QR_OK;
+}
+
+extern "C" int qr_diagonal_device(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, double *d_diag, void *stream)
+{
+    if (!pl || !d_diag) return fail(QR_ERR_INVALID, "qr_diagonal_device: NULL argument");
+    if (row_lo >= row_hi || row_hi > pl->dim) return fail(QR_ERR_INVALID, "qr_diagonal_device: bad row range");
+    QR_CUDA(cudaSetDevice(pl->device));
+    const uint64_t ctas = (row_hi - row_lo + 255) / 256;
+    qr::diagonal_kernel<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(pl->dev, row_lo, row_hi, reinterpret_cast<double2 *>(d_diag));
+    QR_LAUNCH_CHECK("diagonal_kernel");
+    return QR_OK;
+}
+
+extern "C" int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const uint64_t *d_indices,
+                              const double *d_data, const double *d_v, double *d_y, void *stream)
+{
+    if (!d_indptr || !d_indices || !d_data || !d_v || !d_y) return fail(QR_ERR_INVALID, "qr_spmv_device: NULL argument");
+    if (n_rows == 0) return QR_OK;
+    const uint64_t ctas = (n_rows + 255) / 256;
+    qr::spmv_csr_kernel<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(
+        n_rows, d_indptr, d_indices, reinterpret_cast<const double2 *>(d_data),
+        reinterpret_cast<const double2 *>(d_v), reinterpret_cast<double2 *>(d_y));
+    QR_LAUNCH_CHECK("spmv_csr_kernel");
+    return QR_OK;
+}
+
+static unsigned vec_grid(uint64_t n)
+{
+    uint64_t ctas = (n + 255) / 256;
+    const uint64_t cap = 148ull * 16;
+    return (unsigned)(ctas < cap ? (ctas ? ctas : 1) : cap);
+}
+
+extern "C" int qr_axpby_device(uint64_t n, const double a[2], const double *x, const double b[2],
+                               const double *y, double *z, void *stream)
+{
+    if (!a || !b || !x || !y || !z) return fail(QR_ERR_INVALID, "qr_axpby_device: NULL argument");
+    if (n == 0) return QR_OK;
+    qr::vec_axpby_kernel<0><<<vec_grid(n), 256, 0, as_stream(stream)>>>(
+        n, make_double2(a[0], a[1]), reinterpret_cast<const double2 *>(x), make_double2(b[0], b[1]),
+        reinterpret_cast<const double2 *>(y), reinterpret_cast<double2 *>(z));
+    QR_LAUNCH_CHECK("vec_axpby_kernel");
+    return QR_OK;
+}
+extern "C" int qr_axpy_device(uint64_t n, const double a[2], const double *x, const double *y, double *z, void *stream)
+{
+    if (!a || !x || !y || !z) return fail(QR_ERR_INVALID, "qr_axpy_device: NULL argument");
+    if (n == 0) return QR_OK;
+    qr::vec_axpby_kernel<1><<<vec_grid(n), 256, 0, as_stream(stream)>>>(
+        n, make_double2(a[0], a[1]), reinterpret_cast<const double2 *>(x), make_double2(0, 0),
+        reinterpret_cast<const double2 *>(y), reinterpret_cast<double2 *>(z));
+    QR_LAUNCH_CHECK("vec_axpy_kernel");
+    return QR_OK;
+}
+extern "C" int qr_ax_device(uint64_t n, const double a[2], const double *x, double *z, void *stream)
+{
+    if (!a || !x || !z) return fail(QR_ERR_INVALID, "qr_ax_device: NULL argument");
+    if (n == 0) return QR_OK;
+    qr::vec_axpby_kernel<2><<<vec_grid(n), 256, 0, as_stream(stream)>>>(
+        n, make_double2(a[0], a[1]), reinterpret_cast<const double2 *>(x), make_double2(0, 0),
+        nullptr, reinterpret_cast<double2 *>(z));
+    QR_LAUNCH_CHECK("vec_ax_kernel");
+    return QR_OK;
+}
+
+extern "C" int qr_dotc_device(uint64_t n, const double *x, const double *y, double *d_out, void *stream)
+{
+    if (!x || !y || !d_out) return fail(QR_ERR_INVALID, "qr_dotc_device: NULL argument");
+    static thread_local double2 *partials = nullptr;     // one scratch per host thread (and its device)
+    static thread_local int partials_dev = -1;
+    int dev = 0;
+    QR_CUDA(cudaGetDevice(&dev));
+    const unsigned grid = 148 * 8;
+    if (!partials || partials_dev != dev) {
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&partials), grid * sizeof(double2)));
+        partials_dev = dev;
+    }
+    qr::dotc_partial_kernel<<<grid, qr::DOT_THREADS, 0, as_stream(stream)>>>(
+        n, reinterpret_cast<const double2 *>(x), reinterpret_cast<const double2 *>(y), partials);
+    QR_LAUNCH_CHECK("dotc_partial_kernel");
+    qr::dotc_final_kernel<<<1, qr::DOT_THREADS, 0, as_stream(stream)>>>(grid, partials, reinterpret_cast<double2 *>(d_out));
+    QR_LAUNCH_CHECK("dotc_final_kernel");
+    return QR_OK;
+}
+
+// =====================================================================================
+// NCCL (dlopen'ed: the library loads and the 1-GPU path runs without it)
+// =====================================================================================
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+NcclApi &nccl()
+{
+    static NcclApi api = [] {
+        NcclApi a;
+        const char *names[] = {"libnccl.so.2", "/usr/lib/x86_64-linux-gnu/libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (a.handle) break; }
+        if (!a.handle) { a.why = "cannot dlopen libnccl.so.2"; return a; }
+#define QR_SYM(field, name)                                                       \
+        a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.handle, name));     \
+        if (!a.field) { a.why = std::string("missing NCCL symbol ") + name; return a; }
+        QR_SYM(GetUniqueId, "ncclGetUniqueId")
+        QR_SYM(CommInitRank, "ncclCommInitRank")
+        QR_SYM(CommDestroy, "ncclCommDestroy")
+        QR_SYM(AllGather, "ncclAllGather")
+        QR_SYM(AllReduce, "ncclAllReduce")
+        QR_SYM(GetErrorString, "ncclGetErrorString")
+#undef QR_SYM
+        a.ok = true;
+        return a;
+    }();
+    return api;
+}
+
+#define QR_NCCL(expr)                                                                          \
+    do {                                                                                       \
+        ncclResult_t r__ = (expr);                                                             \
+        if (r__ != ncclSuccess)                                                                \
+            return fail(QR_ERR_NCCL, std::string(#expr) + ": " + nccl().GetErrorString(r__));  \
+    } while (0)
+}  // namespace
+
+extern "C" int qr_comm_unique_id(void *id_out)
+{
+    static_assert(sizeof(ncclUniqueId) == QR_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    if (!id_out) return fail(QR_ERR_INVALID, "qr_comm_unique_id: NULL argument");
+    if (!nccl().ok) return fail(QR_ERR_NCCL, nccl().why);
+    ncclUniqueId id;
+    QR_NCCL(nccl().GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return QR_OK;
+}
+
+extern "C" int qr_comm_create(const void *id, int n_ranks, int rank, int device, qr_comm **out)
+{
+    if (!id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(QR_ERR_INVALID, "qr_comm_create: bad argument");
+    *out = nullptr;
+    if (!nccl().ok) return fail(QR_ERR_NCCL, nccl().why);
+    QR_CUDA(cudaSetDevice(device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t c = nullptr;
+    QR_NCCL(nccl().CommInitRank(&c, n_ranks, uid, rank));
+    qr_comm *cm = new (std::nothrow) qr_comm();
+    if (!cm) return fail(QR_ERR_OOM, "qr_comm_create: host allocation failed");
+    cm->comm = c; cm->n_ranks = n_ranks; cm->rank = rank; cm->device = device;
+    *out = cm;
+    return QR_OK;
+}
+
+extern "C" int qr_comm_destroy(qr_comm *cm)
+{
+    if (!cm) return QR_OK;
+    if (cm->comm && nccl().ok) nccl().CommDestroy(cm->comm);
+    delete cm;
+    return QR_OK;
+}
+
+extern "C" int qr_apply_distributed(qr_plan *pl, qr_comm *cm, const double *d_v_shard, double *d_v_full,
+                                    double *d_y_shard, void *stream)
+{
+    if (!pl || !cm || !d_v_shard || !d_v_full || !d_y_shard) return fail(QR_ERR_INVALID, "qr_apply_distributed: NULL argument");
+    const uint64_t P = (uint64_t)cm->n_ranks;
+    if (pl->dim % P) return fail(QR_ERR_INVALID, "qr_apply_distributed: dim is not divisible by n_ranks");
+    const uint64_t shard = pl->dim / P;
+    QR_CUDA(cudaSetDevice(pl->device));
+    // accel.rs has no counterpart: the reference is single-process.  Rows are
+    // block-sharded; the only exchange the path needs is this all-gather of v.
+    QR_NCCL(nccl().AllGather(d_v_shard, d_v_full, 2 * shard, ncclDouble, cm->comm, as_stream(stream)));
+    return apply_rows(pl, shard * cm->rank, shard * (cm->rank + 1), reinterpret_cast<const double2 *>(d_v_full),
+                      reinterpret_cast<double2 *>(d_y_shard), as_stream(stream));
+}
+
+extern "C" int qr_allreduce_sum_f64(qr_comm *cm, double *d_buf, size_t count, void *stream)
+{
+    if (!cm || !d_buf) return fail(QR_ERR_INVALID, "qr_allreduce_sum_f64: NULL argument");
+    QR_NCCL(nccl().AllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, cm->comm, as_stream(stream)));
+    return QR_OK;
+}
+
+// =====================================================================================
+// runtime helpers
+// =====================================================================================
+extern "C" int qr_device_count(int *count)
+{
+    if (!count) return fail(QR_ERR_INVALID, "qr_device_count: NULL argument");
+    *count = 0;
+    QR_CUDA(cudaGetDeviceCount(count));
+    return QR_OK;
+}
+extern "C" int qr_device_name(int device, char *buf, size_t buf_len)
+{
+    if (!buf || buf_len == 0) return fail(QR_ERR_INVALID, "qr_device_name: NULL argument");
+    cudaDeviceProp prop;
+    QR_CUDA(cudaGetDeviceProperties(&prop, device));
+    snprintf(buf, buf_len, "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+    return QR_OK;
+}
+extern "C" int qr_set_device(int device) { QR_CUDA(cudaSetDevice(device)); return QR_OK; }
+extern "C" int qr_malloc_device(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(QR_ERR_INVALID, "qr_malloc_device: NULL argument");
+    *ptr = nullptr;
+    QR_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
+    return QR_OK;
+}
+extern "C" int qr_free_device(void *ptr) { if (ptr) QR_CUDA(cudaFree(ptr)); return QR_OK; }
+extern "C" int qr_malloc_host(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(QR_ERR_INVALID, "qr_malloc_host: NULL argument");
+    *ptr = nullptr;
+    QR_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return QR_OK;
+}
+extern "C" int qr_free_host(void *ptr) { if (ptr) QR_CUDA(cudaFreeHost(ptr)); return QR_OK; }
+extern "C" int qr_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (stream) QR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    else QR_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return QR_OK;
+}
+extern "C" int qr_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (stream) QR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    else QR_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return QR_OK;
+}
+extern "C" int qr_memset_device(void *dst, int value, size_t bytes, void *stream)
+{
+    QR_CUDA(cudaMemsetAsync(dst, value, bytes, as_stream(stream)));
+    return QR_OK;
+}
+extern "C" int qr_stream_create(void **stream)
+{
+    if (!stream) return fail(QR_ERR_INVALID, "qr_stream_create: NULL argument");
+    cudaStream_t s;
+    QR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return QR_OK;
+}
+extern "C" int qr_stream_destroy(void *stream) { if (stream) QR_CUDA(cudaStreamDestroy(as_stream(stream))); return QR_OK; }
+extern "C" int qr_stream_synchronize(void *stream)
+{
+    if (stream) QR_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    else QR_CUDA(cudaDeviceSynchronize());
+    return QR_OK;
+}
+extern "C" int qr_event_create(void **event)
+{
+    if (!event) return fail(QR_ERR_INVALID, "qr_event_create: NULL argument");
+    cudaEvent_t e;
+    QR_CUDA(cudaEventCreate(&e));
+    *event = e;
+    return QR_OK;
+}
+extern "C" int qr_event_destroy(void *event) { if (event) QR_CUDA(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event))); return QR_OK; }
+extern "C" int qr_event_record(void *event, void *stream)
+{
+    QR_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), as_stream(stream)));
+    return QR_OK;
+}
+extern "C" int qr_event_elapsed_ms(void *start, void *stop, float *ms)
+{
+    if (!ms) return fail(QR_ERR_INVALID, "qr_event_elapsed_ms: NULL argument");
+    QR_CUDA(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(stop)));
+    QR_CUDA(cudaEventElapsedTime(ms, reinterpret_cast<cudaEvent_t>(start), reinterpret_cast<cudaEvent_t>(stop)));
+    return QR_OK;
+}
