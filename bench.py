@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- SparsePauliOp -> CSR throughput (nnz/s) on N B200s, plus the roofline of the
+fill kernel, the matrix-free H.v figure, the end-to-end number through the public API with host
+buffers, and the CPU port of the reference algorithm timed beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C2]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one operator already resident in HBM: the
+canonicalisation kernel (K1) followed by the fill kernel(s) (K3, which also writes indptr),
+writing a device-resident CSR shard.  N=1: BASELINE config 2 (XXZ periodic chain n=20).
+N>1: the same chain with n = 20 + log2(N) qubits, row-block sharded, 2^20 rows per GPU
+(weak scaling; the build needs no collective).  torch is used only for the rendezvous,
+the barrier and the max-over-ranks reduction.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC, UNIT = "csr_build_nnz_per_s", "nnz/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="auto", help="auto | C2 | C4 | xxz<n>")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-hv", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args, world):
+    """-> (name, labels, coeffs).  See module docstring."""
+    from qrusty_b200 import hamiltonians as H
+    cfg = args.config
+    if cfg == "auto":
+        cfg = "xxz%d" % (20 + int(math.log2(world)))
+    if cfg == "C2":
+        cfg = "xxz20"
+    if cfg == "C4":
+        return "tfim_5x5_n25", *H.tfim_lattice(5, 5, 1.0, 3.0)
+    if cfg.startswith("xxz"):
+        n = int(cfg[3:])
+        return "xxz_periodic_n%d_J1_delta0.7" % n, *H.xxz_chain(n, 1.0, 0.7)
+    raise SystemExit("unknown --config " + cfg)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region with NVML (nvidia-smi as a fallback)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, local_rank):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = local_rank
+            if vis and all(p.strip().isdigit() for p in vis.split(",")):
+                idx = int(vis.split(",")[local_rank])
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                       # pragma: no cover - depends on the box
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.ok:
+            self._stop.set()
+            self.t.join()
+
+    def summary(self, window):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "window": window,
+                    "note": "no NVML samples" + (": " + getattr(self, "err", "") if not self.ok else "")}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "window": window}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's port of accel.rs:267-336 on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_build_rate(labels, coeffs, budget_s, max_rows=None):
+    """Times oracle.build_csr (chunk step 1000 as perf_giant.py:34, all host threads) on the whole
+    matrix, or on a leading row window if one build would exceed the budget.  -> dict."""
+    from oracle import oracle as O
+    n, params = O.make_params(labels, coeffs)
+    G = len(np.unique(params["x"]))
+    threads = O.hardware_threads()
+    dim = 1 << n
+    probe = min(dim, 1 << 14)
+    t0 = time.perf_counter(); O.build_csr(params, n, 0, probe, step=1000, groups=G); t_probe = time.perf_counter() - t0
+    rows = dim
+    est = t_probe * dim / probe
+    if est > budget_s / 2:                                        # bounded sample
+        rows = max(probe, int(dim * (budget_s / 2) / est) // 1024 * 1024)
+    if max_rows:
+        rows = min(rows, max_rows)
+    times = []
+    t_start = time.perf_counter()
+    while not times or (time.perf_counter() - t_start < budget_s and len(times) < 5):
+        t0 = time.perf_counter(); O.build_csr(params, n, 0, rows, step=1000, groups=G); times.append(time.perf_counter() - t0)
+    t = float(np.median(times))
+    sample = ("full matrix" if rows == dim else "rows [0,%d) of %d" % (rows, dim)) + ", %d runs, median" % len(times)
+    return {"value": rows * G / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": sample, "seconds_per_run": t}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    name, labels, coeffs = workload(args, world)
+    from oracle import oracle as O
+    n, params = O.make_params(labels, coeffs)
+    G = len(np.unique(params["x"]))
+    dim = 1 << n
+    # per-step sample: whole matrix when one build is ~1 s or less, else a leading row window
+    t0 = time.perf_counter(); O.build_csr(params, n, 0, 1 << 14, step=1000, groups=G); tp = time.perf_counter() - t0
+    rows = dim if tp * dim / (1 << 14) <= 3.0 else max(1 << 14, int((1 << 14) * 3.0 / tp) // 1024 * 1024)
+    for _ in range(args.warmup):
+        O.build_csr(params, n, 0, rows, step=1000, groups=G)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.build_csr(params, n, 0, rows, step=1000, groups=G)
+    t = (time.perf_counter() - t0) / args.steps
+    value = rows * G / t
+    sample = "full matrix per step" if rows == dim else "rows [0,%d) of %d per step" % (rows, dim)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "n_qubits": n, "n_terms": len(labels), "n_groups": G, "nnz": G * dim},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.hardware_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU port (oracle/qrusty_oracle.c) of qrusty accel.rs:267-336 on all host threads; the Rust "
+                    "reference cannot be built here (no cargo; un-vendored git deps)"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile(name):
+    p = ROOT / "profiles" / "fill_traffic.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            if d.get("workload") == name:
+                return d.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+def run_b200(args, rank, local_rank, world):
+    import qrusty_b200 as Q
+    from qrusty_b200 import _ffi
+    from qrusty_b200._ffi import call
+    from qrusty_b200._runtime import DeviceBuffer
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    if _ffi.device_count() <= device:
+        raise SystemExit("bench.py: no CUDA device %d -- there is no CPU fallback" % device)
+    call("qr_set_device", device)
+
+    def barrier():
+        call("qr_stream_synchronize", None)
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    name, labels, coeffs = workload(args, world)
+    op = Q.SparsePauliOp([Q.Pauli(l) for l in labels], coeffs)
+    plan = op.plan(device)
+    n, G, dim = plan.n_qubits, plan.n_groups, plan.dim
+    rows = dim // world
+    lo, hi = rank * rows, (rank + 1) * rows
+    nnz_local, nnz_total = rows * G, dim * G
+    bytes_local = nnz_local * 24 + (rows + 1) * 8          # B_csr
+
+    d_ip, d_ix, d_dt = DeviceBuffer((rows + 1) * 8, device), DeviceBuffer(nnz_local * 8, device), DeviceBuffer(nnz_local * 16, device)
+    stream = C.c_void_p(); call("qr_stream_create", C.byref(stream))
+
+    def ev():
+        e = C.c_void_p(); call("qr_event_create", C.byref(e)); return e
+
+    def elapsed(a, b):
+        ms = C.c_float(); call("qr_event_elapsed_ms", a, b, C.byref(ms)); return ms.value
+
+    def step(e_fill0=None, e_fill1=None):
+        call("qr_plan_canonicalise_async", plan.handle, stream)
+        if e_fill0 is not None:
+            call("qr_event_record", e_fill0, stream)
+        call("qr_build_rows_device", plan.handle, lo, hi, d_ip.ptr, d_ix.ptr, d_dt.ptr, _ffi.QR_INDPTR_GLOBAL, stream)
+        if e_fill1 is not None:
+            call("qr_event_record", e_fill1, stream)
+
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    for _ in range(W):
+        step()
+    call("qr_stream_synchronize", stream)
+    e0, e1 = ev(), ev()
+    fill_ev = [(ev(), ev()) for _ in range(K)]
+    barrier()
+    sampler.start()
+    launches0 = _ffi.kernel_launches()
+    call("qr_event_record", e0, stream)
+    for i in range(K):
+        step(*fill_ev[i])
+    call("qr_event_record", e1, stream)
+    call("qr_stream_synchronize", stream)
+    launches = _ffi.kernel_launches() - launches0
+    barrier()
+    t_ms = max_over_ranks(elapsed(e0, e1))
+    fill_ms = float(np.mean([elapsed(a, b) for a, b in fill_ev]))
+    fill_ms = max_over_ranks(fill_ms)
+
+    # ---- matrix-free H.v on the same operator (compulsory bytes: read v once, write y once) ----
+    hv = None
+    if not args.no_hv:
+        d_v, d_y = DeviceBuffer(dim * 16, device), DeviceBuffer(rows * 16, device)
+        from qrusty_b200 import hamiltonians as H
+        chunk = 1 << 22
+        for c0 in range(0, dim, chunk):
+            v = H.lanczos_start_vector(c0, min(dim, c0 + chunk))
+            call("qr_memcpy_h2d", d_v.ptr + c0 * 16, v.ctypes.data, v.nbytes, None)
+        for _ in range(3):
+            call("qr_apply_device", plan.handle, lo, hi, d_v.ptr, d_y.ptr, stream)
+        h0, h1 = ev(), ev()
+        barrier()
+        reps = 20
+        call("qr_event_record", h0, stream)
+        for _ in range(reps):
+            call("qr_apply_device", plan.handle, lo, hi, d_v.ptr, d_y.ptr, stream)
+        call("qr_event_record", h1, stream)
+        call("qr_stream_synchronize", stream)
+        hv_ms = max_over_ranks(elapsed(h0, h1) / reps)
+        hv = {"workload": name, "ms": hv_ms, "gbs_compulsory": 32.0 * dim / hv_ms / 1e6,
+              "gbs_gather_effective": 16.0 * (G + 1) * dim / hv_ms / 1e6,
+              "note": "local apply on a replicated v (no allgather); vector %s L2" % ("fits" if dim * 16 < 100e6 else "exceeds")}
+        del d_v, d_y
+
+    # ---- e2e: the public API with host buffers, copies inside the timed region -------------------
+    e2e = None
+    if not args.no_e2e:
+        terms = op.terms()
+
+        def e2e_step():
+            o = Q.SparsePauliOp.from_terms(n, terms)              # fresh plan: H2D of the term table + K1
+            m = o.to_matrix_rows(lo, hi, device) if world > 1 else o.to_matrix_mode("Cuda")   # K3, fresh buffers
+            return m.export()                                     # D2H into pinned host memory
+        for _ in range(2):
+            out = e2e_step()
+        del out
+        barrier()
+        reps = max(3, min(K, 10))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = e2e_step()
+            del out
+        call("qr_stream_synchronize", None)
+        t_e2e = max_over_ranks((time.perf_counter() - t0) / reps)
+        e2e = {"value": nnz_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(len(terms) * 32),
+               "d2h_bytes_per_step": int(bytes_local), "ms_per_step": t_e2e * 1e3,
+               "path": "SparsePauliOp.from_terms(terms).to_matrix_mode('Cuda').export(): plan (H2D + K1), K3, D2H of the CSR into pinned host arrays (per rank: its row block)"}
+    sampler.stop()
+    barrier()
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        achieved = bytes_local / (fill_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": nnz_total / (t_ms * 1e-3 / K), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "n_qubits": n, "n_terms": len(labels), "n_groups": G, "nnz": nnz_total,
+                       "rows_per_gpu": rows, "bytes_per_gpu": bytes_local, "parallelism": "row-block x%d, no collective" % world,
+                       "step": "canonicalise kernel + fill kernel(s), outputs device-resident",
+                       "l2": "each step writes %.0f MB per GPU (> 126 MB L2), no flush needed" % (bytes_local / 1e6)},
+            "roofline": {"bound": "hbm", "kernel": "fill_staged_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic_from_profile(name), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_local, "kernel_ms": fill_ms,
+                         "bytes_per_nnz": 24 + 8.0 / G},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary("timed region + H.v + e2e loops"),
+        }
+        if hv:
+            line["hv"] = hv
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_build_rate(labels, coeffs, budget_s=12.0)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and world & (world - 1):
+        raise SystemExit("bench.py: the number of ranks must be a power of two")
+    import __graft_entry__
+    if rank == 0 and not (ROOT / "qrusty_b200" / "lib" / "libqrusty_cuda.so").exists():
+        __graft_entry__.build()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,12 @@ def lib():
         L.oracle_apply_rows.argtypes = [vp, C.c_size_t, vp, C.c_size_t, vp, vp]
         L.oracle_apply_rows.restype = None
         L.oracle_hardware_threads.restype = C.c_int
+        d = C.c_double
+        L.oracle_axpby.argtypes = [d, d, vp, d, d, vp, vp, C.c_size_t]
+        L.oracle_axpy.argtypes = [d, d, vp, vp, vp, C.c_size_t]
+        L.oracle_ax.argtypes = [d, d, vp, vp, C.c_size_t]
+        for f in (L.oracle_axpby, L.oracle_axpy, L.oracle_ax):
+            f.restype = None
         _lib = L
     return _lib
 
@@ -153,3 +159,28 @@ def apply_rows(params, rows, v):
     y = np.zeros(len(rows), np.complex128)
     lib().oracle_apply_rows(_p(params), len(params), _p(rows), len(rows), _p(v), _p(y))
     return y
+
+
+def _cv(x):
+    return np.ascontiguousarray(x, dtype=np.complex128)
+
+
+def axpby(a, x, b, y):
+    """accel.rs:374-379."""
+    x, y = _cv(x), _cv(y); z = np.empty_like(x); a, b = complex(a), complex(b)
+    lib().oracle_axpby(a.real, a.imag, _p(x), b.real, b.imag, _p(y), _p(z), len(x))
+    return z
+
+
+def axpy(a, x, y):
+    """accel.rs:381-386."""
+    x, y = _cv(x), _cv(y); z = np.empty_like(x); a = complex(a)
+    lib().oracle_axpy(a.real, a.imag, _p(x), _p(y), _p(z), len(x))
+    return z
+
+
+def ax(a, x):
+    """accel.rs:388-393."""
+    x = _cv(x); z = np.empty_like(x); a = complex(a)
+    lib().oracle_ax(a.real, a.imag, _p(x), _p(z), len(x))
+    return z

@@ -374,12 +374,12 @@ void oracle_apply_rows(const oracle_param *params, size_t n_terms, const uint64_
 }
 
 /* accel.rs:374-393 */
-void oracle_axpby(c128 a, const c128 *x, c128 b, const c128 *y, c128 *z, size_t n)
-{ for (size_t i = 0; i < n; i++) z[i] = cadd(cmul(a, x[i]), cmul(b, y[i])); }
-void oracle_axpy(c128 a, const c128 *x, const c128 *y, c128 *z, size_t n)
-{ for (size_t i = 0; i < n; i++) z[i] = cadd(cmul(a, x[i]), y[i]); }
-void oracle_ax(c128 a, const c128 *x, c128 *z, size_t n)
-{ for (size_t i = 0; i < n; i++) z[i] = cmul(a, x[i]); }
+void oracle_axpby(double ar, double ai, const c128 *x, double br, double bi, const c128 *y, c128 *z, size_t n)
+{ c128 a = { ar, ai }, b = { br, bi }; for (size_t i = 0; i < n; i++) z[i] = cadd(cmul(a, x[i]), cmul(b, y[i])); }
+void oracle_axpy(double ar, double ai, const c128 *x, const c128 *y, c128 *z, size_t n)
+{ c128 a = { ar, ai }; for (size_t i = 0; i < n; i++) z[i] = cadd(cmul(a, x[i]), y[i]); }
+void oracle_ax(double ar, double ai, const c128 *x, c128 *z, size_t n)
+{ c128 a = { ar, ai }; for (size_t i = 0; i < n; i++) z[i] = cmul(a, x[i]); }
 
 int oracle_hardware_threads(void)
 {

@@ -239,6 +239,17 @@ class SparsePauliOp:
             synchronize()
         return SpMat._from_shards((dim, dim), shards)
 
+    def to_matrix_rows(self, row_lo, row_hi, device=0):
+        """Rows [row_lo,row_hi) as a self-contained (row_hi-row_lo) x 2^n CSR shard on `device`
+        (local indptr, global column ids) -- what one rank of a row-sharded build owns."""
+        plan = self.plan(device)
+        if not (0 <= row_lo < row_hi <= plan.dim):
+            raise Exception("to_matrix_rows: bad row range")
+        sh = _Shard.build(plan, row_lo, row_hi, local=True)
+        call("qr_set_device", device)
+        synchronize()
+        return SpMat._from_shards((row_hi - row_lo, plan.dim), [sh])
+
     # -- matrix-free H.v -------------------------------------------------------------
     def apply(self, v, device=0):
         """y = H v without building H (host vectors in, host vector out)."""
@@ -260,21 +271,22 @@ class SparsePauliOp:
 class _Shard:
     """Rows [lo,hi) of the CSR, resident on one device."""
 
-    def __init__(self, plan, lo, hi, indptr, indices, data):
+    def __init__(self, plan, lo, hi, indptr, indices, data, off=None):
         self.plan, self.lo, self.hi = plan, lo, hi
+        self.off = lo if off is None else off        # first row of this shard inside its SpMat
         self.device = plan.device if plan is not None else indptr.device
         self.indptr, self.indices, self.data = indptr, indices, data
         self.nnz = (hi - lo) * plan.n_groups if plan is not None else None
 
     @classmethod
-    def build(cls, plan, lo, hi):
+    def build(cls, plan, lo, hi, local=False):
         rows, G = hi - lo, plan.n_groups
         indptr = DeviceBuffer((rows + 1) * 8, plan.device)
         indices = DeviceBuffer(rows * G * 8, plan.device)
         data = DeviceBuffer(rows * G * 16, plan.device)
         call("qr_build_rows_device", plan.handle, lo, hi, indptr.ptr, indices.ptr, data.ptr,
-             _ffi.QR_INDPTR_GLOBAL, None)
-        return cls(plan, lo, hi, indptr, indices, data)
+             _ffi.QR_INDPTR_LOCAL if local else _ffi.QR_INDPTR_GLOBAL, None)
+        return cls(plan, lo, hi, indptr, indices, data, off=0 if local else lo)
 
 
 class SpMat:
@@ -336,7 +348,7 @@ class SpMat:
                 b.download(tmp)
                 nb.upload(tmp)
                 bufs.append(nb)
-            c = _Shard(s.plan, s.lo, s.hi, *bufs)
+            c = _Shard(s.plan, s.lo, s.hi, *bufs, off=s.off)
             c.nnz = s.nnz
             shards.append(c)
         return SpMat._from_shards(self._shape, shards)
@@ -351,7 +363,7 @@ class SpMat:
                 return _csr((data, indices, indptr), shape=shape).diagonal()
             d = DeviceBuffer((s.hi - s.lo) * 16, s.device)
             call("qr_diagonal_device", s.plan.handle, s.lo, s.hi, d.ptr, None)
-            d.download(out[s.lo:s.hi])
+            d.download(out[s.off:s.off + s.hi - s.lo])
         return out
 
     def export(self):
@@ -372,7 +384,7 @@ class SpMat:
             streams.append((s.device, st))
             s.data.download(data[off:off + s.nnz], stream=st)
             s.indices.download(indices[off:off + s.nnz], stream=st)
-            s.indptr.download(indptr[s.lo:s.lo + rows + 1], stream=st)
+            s.indptr.download(indptr[s.off:s.off + rows + 1], stream=st)
             off += s.nnz
         for dev, st in streams:
             call("qr_set_device", dev)
@@ -402,7 +414,7 @@ def spmat_dot_densevec(spmat, x):
         dv.upload(x)
         dy = DeviceBuffer(max(rows * 16, 16), s.device)
         call("qr_spmv_device", rows, s.indptr.ptr, s.indices.ptr, s.data.ptr, dv.ptr, dy.ptr, None)
-        dy.download(y[s.lo:s.hi])
+        dy.download(y[s.off:s.off + rows])
     return y
 
 

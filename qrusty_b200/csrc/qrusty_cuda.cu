@@ -262,7 +262,9 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
     if (cfg) {
         const uint64_t R = 32ull * cfg->rw;
         const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
-        if (s1 > s0) {
+        // the bulk copies need 16-byte aligned global addresses: indices + (s0-row_lo)*G*8
+        const bool aligned = (((s0 - row_lo) * G) & 1) == 0;
+        if (s1 > s0 && aligned) {
             const size_t smem = (size_t)(R * G * 24);
             const uint64_t tiles = (s1 - s0) / R;
             if (tiles > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_staged: row window too large for one launch");

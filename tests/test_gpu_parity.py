@@ -1,0 +1,372 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+indptr / indices: bit-exact.  data: bit-exact (same summation order, signed zeros included);
+the 1e-12 tolerance of the north-star is therefore never needed for the build.  H.v
+(matrix-free) sums the groups in a fixed mask order, not the per-row column order of the CSR
+SpMV, so it is checked to 1e-12 * sum_k |a_k||v_k|.
+
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O, oracle_np as N
+import qrusty_b200 as Q
+from qrusty_b200 import _ffi, hamiltonians as H
+from qrusty_b200._runtime import DeviceBuffer
+
+pytestmark = pytest.mark.gpu
+
+
+def u64(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def make_op(labels, coeffs):
+    return Q.SparsePauliOp([Q.Pauli(l) for l in labels], coeffs)
+
+
+def device_build(plan, lo, hi, flags=0, with_indptr=True):
+    """qr_build_rows_device into fresh buffers pre-filled with 0xFF (every slot must be written)."""
+    rows, G = hi - lo, plan.n_groups
+    ip = DeviceBuffer((rows + 1) * 8); ix = DeviceBuffer(rows * G * 8); dt = DeviceBuffer(rows * G * 16)
+    for b in (ip, ix, dt):
+        _ffi.call("qr_memset_device", b.ptr, 0xFF, b.nbytes, None)
+    _ffi.call("qr_build_rows_device", plan.handle, lo, hi, ip.ptr if with_indptr else None, ix.ptr, dt.ptr, flags, None)
+    _ffi.call("qr_stream_synchronize", None)
+    return (ip.download(np.empty(rows + 1, np.uint64)), ix.download(np.empty(rows * G, np.uint64)),
+            dt.download(np.empty(rows * G, np.complex128)))
+
+
+def assert_same(got, ref, what=""):
+    for name, a, b in zip(("indptr", "indices", "data"), got, ref):
+        assert a.shape == b.shape, (what, name, a.shape, b.shape)
+        if not np.array_equal(u64(a), u64(b)):
+            bad = np.flatnonzero(u64(a).reshape(len(a), -1) != u64(b).reshape(len(b), -1))[:5]
+            raise AssertionError(f"{what}: {name} differs at {bad}: {a[bad]} vs {b[bad]}")
+
+
+SMALL = {
+    "C1": lambda fx: H.tfim_chain(12),
+    "xxz_n10": lambda fx: H.xxz_chain(10, 1.0, 0.7),
+    "tfim_3x3": lambda fx: H.tfim_lattice(3, 3, 1.0, 3.0),
+    "random_n10": lambda fx: H.random_pauli_sum(10, 300, 200, 30, 7),
+    "H2": lambda fx: fx["H2"], "H2_rs": lambda fx: fx["H2_rs"],
+    "H4": lambda fx: fx["H4"], "H4_rs": lambda fx: fx["H4_rs"], "H6": lambda fx: fx["H6"],
+}
+
+
+# ---- the reference's cross-mode tests (test_H.py:32-52, lib.rs:815-885) with the Cuda mode ----
+@pytest.mark.parametrize("name", list(SMALL))
+def test_build_matches_oracle_and_goldens(fixtures, golden_sums, name):
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n, step=100)
+    op = make_op(labels, coeffs)
+    m = op.to_matrix_mode("Cuda")
+    assert m.shape() == (1 << n, 1 << n)
+    assert m.nnz() == len(ref[2])
+    shape, data, indices, indptr = m.export()
+    assert_same((indptr, indices, data), ref, name)
+    g = golden_sums[name]
+    for key, arr in (("indptr", indptr), ("indices", indices), ("data", data)):
+        assert hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest() == g[key], key
+
+
+@pytest.mark.parametrize("name", ["H2", "H4", "H6"])
+def test_reference_test_H(fixtures, name):
+    """pyqrusty/tests/test_H.py:32-48 verbatim in spirit: every mode gives the same dense matrix."""
+    labels, coeffs = fixtures[name]
+    op = make_op(labels, coeffs)
+    m1 = Q.csr_matrix(op.to_matrix())
+    assert np.array_equal(m1.todense(), Q.csr_matrix(op.to_matrix_mode(mode="")).todense())
+    m2 = op.to_matrix_mode(mode="RowwiseUnsafeChunked/100")
+    assert np.array_equal(m1.todense(), Q.csr_matrix(m2).todense())
+    assert np.array_equal(m1.todense(), Q.csr_matrix(op.to_matrix_mode("Cuda")).todense())
+    if name != "H6":
+        assert np.array_equal(np.asarray(m1.todense()), N.spop_dense(labels, coeffs))
+
+
+def test_mode_and_export_errors(fixtures):
+    op = make_op(*fixtures["H2"])
+    with pytest.raises(Exception):
+        op.to_matrix_mode("foo")                                   # test_H.py:28-30
+    m = op.to_matrix()
+    assert repr(m) == "<16x16 sparse matrix of type Complex64\n\twith 64 stored elements in Compressed Sparse Row format>"
+    m.export()
+    with pytest.raises(Exception, match="already-exported"):
+        m.export()                                                 # pyqrusty/src/lib.rs:195-197
+    with pytest.raises(Exception):
+        m.shape()
+    assert repr(m) == "<already-dropped sparse matrix of type Complex64>"
+
+
+# ---- lib.rs:721-768: single Pauli strings (G = 1) ----------------------------------------
+@pytest.mark.parametrize("label", ["IX", "XI", "I", "Y", "YY", "ZXYI", "-YZYX", "X", "Z"])
+def test_single_pauli(label):
+    bp, nq, x, z, ny = O.parse_label(label)
+    ref = O.single_pauli(z, x, (-1 if bp == 2 else 1) + 0j, ny % 4, nq)
+    shape, data, indices, indptr = Q.Pauli(label).to_matrix().export()
+    assert np.array_equal(indptr, ref[0]) and np.array_equal(indices, ref[1])
+    assert np.array_equal(data, ref[2])
+    assert np.array_equal(np.asarray(Q.csr_matrix(Q.Pauli(label).to_matrix()).todense()), N.pauli_dense(label))
+
+
+def test_pauli_known_answers():
+    """pyqrusty/tests/test_it.py:60-101."""
+    I = np.array([[1.0, 0.0], [0.0, 1.0]], dtype=complex); Z = np.array([[1.0, 0.0], [0.0, -1.0]], dtype=complex)
+    X = np.array([[0.0, 1.0], [1.0, 0.0]], dtype=complex); Y = np.array([[0.0, -1.0j], [1.0j, 0.0]], dtype=complex)
+    for lab, mat in (("I", I), ("X", X), ("Z", Z), ("Y", Y)):
+        assert np.array_equal(mat, Q.csr_matrix(Q.Pauli(lab).to_matrix()).todense())
+    spop = Q.SparsePauliOp([Q.Pauli("I"), Q.Pauli("Y")], [1.0 + 0.0j, 2.0 + 0.0j])
+    assert np.array_equal(I + 2.0 * Y, Q.csr_matrix(spop.to_matrix()).todense())
+    spop = Q.SparsePauliOp([Q.Pauli("I"), Q.Pauli("X")], [1.0 + 0.0j, 2.0 + 0.0j])
+    assert np.array_equal([[1, 2], [2, 1]], Q.csr_matrix(spop.to_matrix()).todense())   # lib.rs:786-793
+
+
+def test_prefixed_labels_follow_to_matrix():
+    """i/j prefixes use the default to_matrix's (+i)^base_phase."""
+    labels, coeffs = ["iXY", "-jZI", "-XX", "YZ", "+1ZZ"], [0.5 + 0.25j, 1.5 + 0j, -2 + 1j, 0.75 + 0j, 1j]
+    got = np.asarray(Q.csr_matrix(make_op(labels, coeffs).to_matrix()).todense())
+    assert np.array_equal(got, N.spop_dense(labels, coeffs))
+
+
+# ---- tiny dimensions (dim < one warp) and ragged / unaligned row windows ---------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7])
+def test_tiny_dims(n):
+    labels, coeffs = H.random_pauli_sum(n, 40, min(1 << n, 12), 5, 100 + n)
+    nq, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, nq)
+    shape, data, indices, indptr = make_op(labels, coeffs).to_matrix().export()
+    assert_same((indptr, indices, data), ref, f"n={n}")
+
+
+@pytest.mark.parametrize("flags", [0, _ffi.QR_FILL_DIRECT])
+def test_row_windows(fixtures, flags):
+    labels, coeffs = fixtures["H4"]                                  # n=8, G=51
+    n, params = O.make_params(labels, coeffs)
+    plan = make_op(labels, coeffs).plan()
+    G = plan.n_groups
+    full = O.build_csr(params, n)
+    for lo, hi in [(0, 256), (37, 201), (0, 1), (255, 256), (31, 33), (64, 128), (1, 255), (100, 101), (96, 160)]:
+        ip, ix, dt = device_build(plan, lo, hi, flags)
+        assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G), (lo, hi)
+        assert np.array_equal(ix, full[1][lo * G:hi * G]), (lo, hi)
+        assert np.array_equal(u64(dt), u64(full[2][lo * G:hi * G])), (lo, hi)
+        ipg, _, _ = device_build(plan, lo, hi, flags | _ffi.QR_INDPTR_GLOBAL)
+        assert np.array_equal(ipg, (np.arange(hi - lo + 1, dtype=np.uint64) + lo) * G), (lo, hi)
+        _, ix2, dt2 = device_build(plan, lo, hi, flags, with_indptr=False)
+        assert np.array_equal(ix2, ix) and np.array_equal(u64(dt2), u64(dt))
+
+
+def test_direct_equals_staged(fixtures):
+    labels, coeffs = H.xxz_chain(14, 1.0, 0.7)
+    plan = make_op(labels, coeffs).plan()
+    a = device_build(plan, 0, plan.dim, 0)
+    b = device_build(plan, 0, plan.dim, _ffi.QR_FILL_DIRECT)
+    assert_same(a, b, "staged vs direct")
+
+
+def test_build_host_windows(fixtures):
+    labels, coeffs = fixtures["H4"]
+    n, params = O.make_params(labels, coeffs)
+    full = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    G = plan.n_groups
+    for lo, hi in [(0, 256), (3, 250)]:
+        rows = hi - lo
+        ip = np.full(rows + 1, 0xFFFF, np.uint64); ix = np.zeros(rows * G, np.uint64); dt = np.zeros(rows * G, np.complex128)
+        _ffi.call("qr_build_host", plan.handle, lo, hi, ip.ctypes.data, ix.ctypes.data, dt.ctypes.data, 0)
+        assert np.array_equal(ip, np.arange(rows + 1, dtype=np.uint64) * G)
+        assert np.array_equal(ix, full[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(full[2][lo * G:hi * G]))
+
+
+def test_abi_argument_errors(fixtures):
+    plan = make_op(*fixtures["H2"]).plan()
+    buf = DeviceBuffer(1 << 16)
+    for lo, hi in [(5, 5), (7, 3), (0, 17)]:
+        with pytest.raises(Q.QrustyCudaError) as e:
+            _ffi.call("qr_build_rows_device", plan.handle, lo, hi, None, buf.ptr, buf.ptr, 0, None)
+        assert e.value.code == _ffi.QR_ERR_INVALID
+    with pytest.raises(Q.QrustyCudaError):
+        _ffi.call("qr_build_rows_device", plan.handle, 0, 16, None, buf.ptr + 8, buf.ptr, 0, None)
+
+
+# ---- K1: canonicalisation output against a stable sort on the host -----------------------------
+@pytest.mark.parametrize("name", ["H2", "H6", "H8", "H10", "H11", "H12", "HJ", "C3"])
+def test_canonicalise_groups(fixtures, name):
+    labels, coeffs = H.CONFIGS["C3"][1]() if name == "C3" else fixtures[name]
+    op = make_op(labels, coeffs)
+    terms = op.terms()
+    gx, goff, order = op.plan().groups()
+    ref_order = np.argsort(terms["x"], kind="stable")
+    assert np.array_equal(order, ref_order.astype(np.uint32))
+    sx = terms["x"][ref_order]
+    heads = np.flatnonzero(np.r_[True, sx[1:] != sx[:-1]])
+    assert np.array_equal(gx, sx[heads])
+    assert np.array_equal(goff, np.r_[heads, len(sx)].astype(np.uint32))
+
+
+# ---- full-size configs -------------------------------------------------------------------------
+def test_C2_full_matrix():
+    """BASELINE config 2 (XXZ periodic n=20, nnz = 22 020 096) compared in full."""
+    labels, coeffs = H.xxz_chain(20, 1.0, 0.7)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n, step=1000)
+    shape, data, indices, indptr = make_op(labels, coeffs).to_matrix_mode("Cuda").export()
+    assert (len(data), shape) == (22020096, (1 << 20, 1 << 20))
+    assert_same((indptr, indices, data), ref, "C2")
+    assert np.mean(data == 0) > 0.4            # XX+YY cancellation leaves explicit zeros, kept
+
+
+def _sorted_cols(rows, gx):
+    return np.sort(rows[:, None] ^ gx[None, :], axis=1).ravel()
+
+
+@pytest.mark.parametrize("cfg,win", [("C3", 1 << 10), ("C4", 1 << 12), ("C5", 1 << 12)])
+def test_big_config_windows(cfg, win):
+    """C3/C4/C5 do not fit the host (or the GPU): row windows at sampled positions, indices also
+    against the closed form sort_g(r ^ x_g)."""
+    labels, coeffs = H.CONFIGS[cfg][1]()
+    n, params = O.make_params(labels, coeffs)
+    plan = make_op(labels, coeffs).plan()
+    G = plan.n_groups
+    gx = np.unique(params["x"])
+    dim = 1 << n
+    rng = np.random.default_rng(5)
+    starts = [0, dim - win, dim // 2 - win // 2] + [int(s) for s in rng.integers(0, dim - win, 3)]
+    for lo in starts:
+        hi = lo + win
+        ip, ix, dt = device_build(plan, lo, hi, _ffi.QR_INDPTR_GLOBAL)
+        assert np.array_equal(ip, (np.arange(win + 1, dtype=np.uint64) + np.uint64(lo)) * np.uint64(G))
+        assert np.array_equal(ix, _sorted_cols(np.arange(lo, hi, dtype=np.uint64), gx)), (cfg, lo)
+        ref = O.build_csr(params, n, row_lo=lo, row_hi=hi, groups=G)
+        assert np.array_equal(ix, ref[1]) and np.array_equal(u64(dt), u64(ref[2])), (cfg, lo)
+
+
+def test_C4_full_size_properties():
+    """All 2^25 rows of C4 (872 415 232 entries, 21 GB) built in 2^21-row windows; every window's
+    indices equal the closed form, and a checksum of data is compared with the oracle on 8 windows."""
+    labels, coeffs = H.tfim_lattice(5, 5, 1.0, 3.0)
+    n, params = O.make_params(labels, coeffs)
+    plan = make_op(labels, coeffs).plan()
+    G, dim, win = plan.n_groups, 1 << n, 1 << 21
+    gx = np.unique(params["x"])
+    ip = DeviceBuffer((win + 1) * 8); ix = DeviceBuffer(win * G * 8); dt = DeviceBuffer(win * G * 16)
+    hix = np.empty(win * G, np.uint64); hdt = np.empty(win * G, np.complex128)
+    check_data = set(range(0, dim // win, 2))
+    for w in range(dim // win):
+        lo, hi = w * win, (w + 1) * win
+        _ffi.call("qr_build_rows_device", plan.handle, lo, hi, ip.ptr, ix.ptr, dt.ptr, 0, None)
+        ix.download(hix)
+        r = np.arange(lo, hi, dtype=np.uint64)
+        # columns of row r are {r ^ x_g}: XOR-sum and sum are order-free invariants; sortedness pins order
+        cols = hix.reshape(win, G)
+        assert (cols[:, 1:] > cols[:, :-1]).all()
+        assert np.array_equal(np.bitwise_xor.reduce(cols, axis=1), np.bitwise_xor.reduce(r[:, None] ^ gx[None, :], axis=1))
+        assert np.array_equal(cols.sum(axis=1, dtype=np.uint64), (r[:, None] ^ gx[None, :]).sum(axis=1, dtype=np.uint64))
+        if w in check_data:
+            dt.download(hdt)
+            sub = slice(0, 4096 * G)
+            ref = O.build_csr(params, n, row_lo=lo, row_hi=lo + 4096, groups=G)
+            assert np.array_equal(hix[sub], ref[1]) and np.array_equal(u64(hdt[sub]), u64(ref[2]))
+            # TFIM: diagonal (slot of mask 0) carries -J * sum of bond signs, off-diagonals are -h exactly
+            vals = hdt.reshape(win, G)
+            diag_slot = (cols == r[:, None])
+            assert diag_slot.sum() == win
+            assert np.all(vals[~diag_slot] == -3.0)
+
+
+# ---- H.v -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["H2", "H6", "C1", "random_n10"])
+def test_spmv_bit_exact(fixtures, name):
+    """spmat_dot_densevec on the device CSR == accel.rs:338-370 bit for bit (lib.rs:887-919)."""
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    rng = np.random.default_rng(3)
+    v = rng.uniform(0, 10, 1 << n) + 1j * rng.uniform(-5, 5, 1 << n)
+    m = make_op(labels, coeffs).to_matrix()
+    y = Q.spmat_dot_densevec(m, v)
+    assert np.array_equal(u64(y), u64(O.spmv(*ref, v)))
+    csr = Q.csr_matrix(m)
+    assert np.allclose(y, csr.dot(v))                              # test_it.py:218-230
+
+
+@pytest.mark.parametrize("name", ["H2", "H6", "C1", "random_n10", "xxz_n10"])
+def test_apply_matrix_free(fixtures, name):
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    indptr, indices, data = O.build_csr(params, n)
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    ref = O.spmv(indptr, indices, data, v)
+    bound = O.spmv(indptr, indices, np.abs(data).astype(np.complex128), np.abs(v).astype(np.complex128)).real
+    op = make_op(labels, coeffs)
+    y = op.apply(v)
+    assert np.all(np.abs(y - ref) <= 1e-12 * bound + 1e-300)
+    assert np.array_equal(op.diagonal(), np.asarray(N.csr_to_dense(indptr, indices, data, 1 << n).diagonal())) if n <= 10 else True
+    assert np.array_equal(op.to_matrix().diagonal(), op.diagonal())
+
+
+def test_apply_C2_and_linearity():
+    labels, coeffs = H.xxz_chain(20, 1.0, 0.7)
+    n, params = O.make_params(labels, coeffs)
+    op = make_op(labels, coeffs)
+    dim = 1 << n
+    v1 = H.lanczos_start_vector(0, dim, seed=25)
+    v2 = H.lanczos_start_vector(0, dim, seed=26)
+    y1, y2 = op.apply(v1), op.apply(v2)
+    rows = np.random.default_rng(6).integers(0, dim, 4096).astype(np.uint64)
+    ref = O.apply_rows(params, rows, v1)
+    assert np.all(np.abs(y1[rows.astype(np.int64)] - ref) <= 1e-12 * 64 * np.abs(v1).max())
+    a, b = 0.5 - 1.25j, -2.0 + 0.75j
+    y12 = op.apply(a * v1 + b * v2)
+    assert np.abs(y12 - (a * y1 + b * y2)).max() <= 1e-11 * np.abs(y12).max()
+    # H is Hermitian: <v2, H v1> == conj(<v1, H v2>)
+    assert abs(np.vdot(v2, y1) - np.conj(np.vdot(v1, y2))) <= 1e-9 * abs(np.vdot(v2, y1))
+
+
+# ---- accel.rs:374-393 (test_it.py:232-269, lib.rs:921-990) ------------------------------------
+def test_vector_ops_bit_exact():
+    rng = np.random.default_rng(8)
+    for rows in (4, 1 << 20):
+        x = rng.random(rows) + rng.random(rows) * 1j
+        y = rng.random(rows) + rng.random(rows) * 1j
+        a, b = 1.0 + 2.0j, 3.0 + 4.0j
+        assert np.array_equal(u64(Q.axpby(a, x, b, y)), u64(O.axpby(a, x, b, y)))
+        assert np.array_equal(u64(Q.axpy(a, x, y)), u64(O.axpy(a, x, y)))
+        assert np.array_equal(u64(Q.ax(a, x)), u64(O.ax(a, x)))
+        assert np.allclose(Q.axpby(a, x, b, y), a * x + b * y)
+        assert np.allclose(Q.axpy(1j, x, y), 1j * x + y) and np.allclose(Q.ax(1j, x), 1j * x)
+
+
+def test_dotc():
+    rng = np.random.default_rng(9)
+    n = (1 << 18) + 17
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    y = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    dx, dy, out = DeviceBuffer(n * 16), DeviceBuffer(n * 16), DeviceBuffer(16)
+    dx.upload(x); dy.upload(y)
+    _ffi.call("qr_dotc_device", n, dx.ptr, dy.ptr, out.ptr, None)
+    got = out.download(np.empty(1, np.complex128))[0]
+    assert abs(got - np.vdot(x, y)) <= 1e-10 * np.abs(x).sum()
+
+
+def test_multi_gpu_single_process(fixtures):
+    if _ffi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    labels, coeffs = fixtures["H6"]
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    shape, data, indices, indptr = make_op(labels, coeffs).to_matrix_mode("Cuda/2").export()
+    assert_same((indptr, indices, data), ref, "Cuda/2")
+
+
+def test_kernels_were_launched():
+    before = _ffi.kernel_launches()
+    make_op(*H.tfim_chain(8)).to_matrix().export()
+    assert _ffi.kernel_launches() >= before + 2
