@@ -102,10 +102,12 @@ void choose_staged(qr_plan *pl)
             pl->rw = rw; pl->gw = gw; return;
         }
     }
+    // Measured on B200 (profiles/r01_fill_sweep.jsonl): 32-row tiles with the groups split
+    // over 8 warps beat taller tiles (C2: 6.06 vs 5.99 TB/s, C4: 6.47 vs 6.11 TB/s).
     const uint64_t row_bytes = G * 24;
-    if (64 * row_bytes <= 56 * 1024)       { pl->rw = 2; pl->gw = 4; }   // >= 4 CTAs/SM of 8 warps
-    else if (32 * row_bytes <= 113 * 1024) { pl->rw = 1; pl->gw = 8; }   // 2+ CTAs/SM
-    else if (32 * row_bytes <= MAX_SMEM)   { pl->rw = 1; pl->gw = 16; }  // 1 CTA/SM
+    if (G < 8 && 32 * row_bytes <= MAX_SMEM)  { pl->rw = 1; pl->gw = 4; }
+    else if (32 * row_bytes <= 113 * 1024)    { pl->rw = 1; pl->gw = 8; }   // 2+ CTAs/SM
+    else if (32 * row_bytes <= MAX_SMEM)      { pl->rw = 1; pl->gw = 16; }  // 1 CTA/SM
 }
 
 int launch_direct(const qr_plan *pl, uint64_t lo, uint64_t hi, uint64_t out_row0, uint64_t req_hi,

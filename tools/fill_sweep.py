@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Times the fill kernel (events on the launching stream) for one workload under several
+(RW,GW) tile configurations, the direct kernel, and a row window size.  GPU box only.
+  python tools/fill_sweep.py C2 | C4 | C3 | xxz<n> | H8 ...   [--rows LOG2] [--cfgs "2,4 1,8 direct"]
+"""
+import argparse, ctypes as C, gzip, json, os, sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import qrusty_b200 as Q
+from qrusty_b200 import _ffi, hamiltonians as H
+from qrusty_b200._ffi import call
+from qrusty_b200._runtime import DeviceBuffer
+
+
+def get_workload(name):
+    if name in H.CONFIGS:
+        return H.CONFIGS[name][1]()
+    if name.startswith("xxz"):
+        return H.xxz_chain(int(name[3:]), 1.0, 0.7)
+    fx = json.load(gzip.open(ROOT / "tests/golden/h_fixtures.json.gz"))
+    return fx[name]["labels"], [complex(a, b) for a, b in fx[name]["coeffs"]]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("workload")
+    ap.add_argument("--rows", type=int, default=None, help="log2 of the row window (default: all rows that fit 8 GB)")
+    ap.add_argument("--cfgs", default="auto direct")
+    ap.add_argument("--reps", type=int, default=20)
+    a = ap.parse_args()
+    labels, coeffs = get_workload(a.workload)
+    terms = Q.SparsePauliOp([Q.Pauli(l) for l in labels], coeffs).terms()
+    n = len(labels[0])
+    stream = C.c_void_p(); call("qr_stream_create", C.byref(stream))
+    e0, e1 = C.c_void_p(), C.c_void_p(); call("qr_event_create", C.byref(e0)); call("qr_event_create", C.byref(e1))
+    bufs = None
+    for cfg in a.cfgs.split():
+        flags = 0
+        os.environ.pop("QR_FILL_CFG", None)
+        if cfg == "direct":
+            flags = _ffi.QR_FILL_DIRECT
+        elif cfg != "auto":
+            os.environ["QR_FILL_CFG"] = cfg
+        op = Q.SparsePauliOp.from_terms(n, terms)
+        plan = op.plan()
+        G, dim = plan.n_groups, plan.dim
+        rows = dim
+        if a.rows is not None:
+            rows = min(dim, 1 << a.rows)
+        while rows * G * 24 > 8e9:
+            rows //= 2
+        if bufs is None:
+            bufs = (DeviceBuffer((rows + 1) * 8), DeviceBuffer(rows * G * 8), DeviceBuffer(rows * G * 16))
+        ip, ix, dt = bufs
+        lo = (dim // 2) // rows * rows if rows < dim else 0
+        for _ in range(3):
+            call("qr_build_rows_device", plan.handle, lo, lo + rows, ip.ptr, ix.ptr, dt.ptr, flags, stream)
+        call("qr_event_record", e0, stream)
+        for _ in range(a.reps):
+            call("qr_build_rows_device", plan.handle, lo, lo + rows, ip.ptr, ix.ptr, dt.ptr, flags, stream)
+        call("qr_event_record", e1, stream)
+        ms = C.c_float(); call("qr_event_elapsed_ms", e0, e1, C.byref(ms))
+        t = ms.value / a.reps
+        nbytes = rows * G * 24 + (rows + 1) * 8
+        print(json.dumps({"workload": a.workload, "cfg": cfg, "n": n, "T": len(labels), "G": G, "rows": rows,
+                          "ms": round(t, 5), "GBps": round(nbytes / t / 1e6, 1), "Gnnz_s": round(rows * G / t / 1e6, 2)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
