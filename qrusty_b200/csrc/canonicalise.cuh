@@ -143,4 +143,36 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
     if (tid == 0) { p.meta[1] = max_group; p.meta[2] = 0; p.meta[3] = 0; }
 }
 
+// K1b: cut the sorted masks into maximal trie subtrees of at most S groups (S >= 32).
+// For group g, p_g = the largest prefix level p in [5,32] whose subtree
+// {h : gx[h] >> p == gx[g] >> p} holds <= S groups (two binary searches per level); g heads a
+// block iff it is the first group of that subtree; a CTA scan numbers the blocks.
+__global__ void __launch_bounds__(K1_THREADS, 1) partition_kernel(PlanDev p, uint32_t S)
+{
+    __shared__ uint32_t scan_scratch[33];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t G = p.meta[0];
+    uint32_t carry = 0;
+    for (uint32_t tile = 0; tile < G; tile += K1_THREADS) {
+        const uint32_t g = tile + tid;
+        uint32_t head = 0, level = 0;
+        if (g < G) {
+            const uint32_t x = p.gx[g];
+            uint32_t lo_idx = 0;
+            for (level = 32; level > 5; level--) {
+                const uint32_t low = level == 32 ? 0xffffffffu : ((1u << level) - 1u);
+                lo_idx = lower_bound_u32(p.gx, G, x & ~low);
+                if (upper_bound_u32(p.gx, G, x | low) - lo_idx <= S) break;
+            }
+            if (level == 5) lo_idx = lower_bound_u32(p.gx, G, x & ~31u);
+            head = lo_idx == g ? 1u : 0u;
+        }
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan(head, scan_scratch, &total);
+        if (head) { p.blk_start[carry + excl] = g; p.blk_p[carry + excl] = level; }
+        carry += total;
+    }
+    if (tid == 0) { p.blk_start[carry] = G; p.meta[2] = carry; p.meta[3] = S; }
+}
+
 }  // namespace qr

@@ -152,4 +152,84 @@ fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, u
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Blocked kernel (large G).  Work item = (block of <= S groups, run of `strips_per_cta`
+// 32-row strips).  The block's tables (cnt, lr5, masks, term offsets) are copied to
+// shared memory once and reused for every strip.  For a strip:
+//   base   = sum_{b >= p} cnt[g0][b] * bit_b(gx[g0] ^ rbase)      slots before the block
+//   offset = sum_{5 <= b < p} cnt[g][b] * bit_b(gx[g] ^ rbase)    (REDUX over lanes [5,p))
+//            + lr5[g][(gx[g] ^ lane) & 31]                        position inside the block
+// Each lane drops (col, value) at stage[lane][offset]; after a barrier the 32 row
+// segments [base, base + size) stream out with coalesced 16-byte / 8-byte stores.
+// ---------------------------------------------------------------------------------
+constexpr int FILL_BLOCKED_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * FILL_BLOCKED_WARPS)
+fill_blocked_kernel(PlanDev p, uint32_t G, uint32_t S, uint32_t n_blocks, uint32_t strips_per_cta,
+                    uint64_t tile_row0, uint64_t n_strips, uint64_t row_lo, uint64_t indptr_base,
+                    uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
+                    double2 *__restrict__ data, uint64_t indptr_last_row)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t pitch = S + 1;
+    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                               // [32][S+1]
+    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)32 * pitch * 16);     // [32][S+1]
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem_raw + (size_t)32 * pitch * 24);    // [S][32]
+    uint32_t *s_lr5 = s_cnt + S * 32u;                                                    // [S][32]
+    uint32_t *s_gx = s_lr5 + S * 32u;                                                     // [S]
+    uint32_t *s_goff = s_gx + S;                                                          // [S+1]
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t blk = blockIdx.x % n_blocks;
+    const uint64_t strip0 = (uint64_t)(blockIdx.x / n_blocks) * strips_per_cta;
+    const uint32_t g0 = __ldg(&p.blk_start[blk]), g1 = __ldg(&p.blk_start[blk + 1]);
+    const uint32_t size = g1 - g0, plevel = __ldg(&p.blk_p[blk]);
+
+    for (uint32_t i = threadIdx.x; i < size * 32u; i += blockDim.x) {
+        s_cnt[i] = __ldg(&p.cnt[g0 * 32u + i]);
+        s_lr5[i] = __ldg(&p.lr5[g0 * 32u + i]);
+    }
+    for (uint32_t i = threadIdx.x; i <= size; i += blockDim.x) {
+        s_goff[i] = __ldg(&p.goff[g0 + i]);
+        if (i < size) s_gx[i] = __ldg(&p.gx[g0 + i]);
+    }
+    __syncthreads();
+
+    const uint32_t in_block = (lane >= 5u && lane < plevel) ? 1u : 0u;     // bits ordering groups inside the block
+    const uint32_t above = lane >= plevel ? 1u : 0u;                        // bits ordering the block among blocks
+    const uint64_t strip_end = min(strip0 + strips_per_cta, n_strips);
+    for (uint64_t strip = strip0; strip < strip_end; strip++) {
+        const uint64_t tile_base = tile_row0 + strip * 32u;
+        const uint32_t wbase = (uint32_t)tile_base;
+        const uint32_t r = wbase + lane;
+        const uint32_t bit0 = ((s_gx[0] ^ wbase) >> lane) & 1u;
+        const uint32_t base = __reduce_add_sync(0xffffffffu, (above && bit0) ? s_cnt[lane] : 0u);
+
+        for (uint32_t gi = warp; gi < size; gi += FILL_BLOCKED_WARPS) {
+            const uint32_t x = s_gx[gi];
+            const uint32_t bit = ((x ^ wbase) >> lane) & 1u;
+            const uint32_t off = __reduce_add_sync(0xffffffffu, (in_block && bit) ? s_cnt[gi * 32u + lane] : 0u)
+                               + s_lr5[gi * 32u + ((x ^ lane) & 31u)];
+            const double2 v = group_value(p.tz, p.tc, s_goff[gi], s_goff[gi + 1], r);
+            sidx[lane * pitch + off] = (uint64_t)(r ^ x);
+            sdat[lane * pitch + off] = v;
+        }
+        if (blk == 0 && warp == 0 && indptr != nullptr) {
+            const uint64_t lr = tile_base + lane - row_lo;
+            indptr[lr] = indptr_base + lr * G;
+            if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+        }
+        __syncthreads();
+        const uint64_t out0 = (tile_base - row_lo) * G + base;
+        for (uint32_t l = warp; l < 32u; l += FILL_BLOCKED_WARPS) {
+            const uint64_t o = out0 + (uint64_t)l * G;
+            for (uint32_t k = lane; k < size; k += 32u) {
+                data[o + k] = sdat[l * pitch + k];
+                indices[o + k] = sidx[l * pitch + k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace qr

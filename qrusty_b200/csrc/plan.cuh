@@ -18,7 +18,11 @@ namespace qr {
 //   goff  u32[G+1]        group g owns sorted terms [goff[g], goff[g+1])
 //   cnt   u32[G][32]      cnt[g][b] = #{h != g : msb(gx[g]^gx[h]) == b}
 //   lr5   u32[G][32]      lr5[g][j] = sum_{b<5} cnt[g][b] * bit_b(j)
-//   meta  u32[4]          {G, max terms in a group, 0, 0}
+//   meta  u32[4]          {G, max terms in a group, B, S}
+//   blk_start u32[B+1]    large-G path: the sorted groups cut into B trie subtrees ("blocks")
+//   blk_p     u32[B]      of <= S groups; block b = groups [blk_start[b], blk_start[b+1]), all
+//                         sharing the mask bits >= blk_p[b] (>= 5).  A subtree's groups fill
+//                         one contiguous slot range in every row (XOR keeps subtrees together).
 //
 // Slot of group g in row r (columns ascending, accel.rs:188):
 //   slot(r,g) = sum_b cnt[g][b] * bit_b(gx[g] ^ r)
@@ -37,6 +41,8 @@ struct PlanDev {
     uint32_t *cnt;
     uint32_t *lr5;
     uint32_t *meta;
+    uint32_t *blk_start;
+    uint32_t *blk_p;
 };
 
 }  // namespace qr

@@ -54,8 +54,9 @@ struct qr_plan {
     int n_qubits = 0;
     uint64_t dim = 0, n_terms = 0, n_groups = 0;
     void *slab = nullptr;             // one allocation holding every table of PlanDev
-    // staged-fill configuration chosen from G
+    // fill configuration chosen from G: staged whole-row tiles (rw,gw) or subtree blocks
     int rw = 0, gw = 0;
+    uint32_t block_s = 0, n_blocks = 0;    // blocked kernel: S and the number of subtree blocks
     // lazily allocated scratch
     double2 *dot_partials = nullptr;
     void *win_buf[2] = {nullptr, nullptr};
@@ -92,10 +93,17 @@ const StagedCfg *find_staged(int rw, int gw)
 }
 
 // Pick (RW, GW) from G: as many resident warps per SM as the R*G*24-byte tile allows.
+size_t blocked_smem(uint32_t S) { return (size_t)32 * (S + 1) * 24 + (size_t)S * 256 + (size_t)(2 * S + 1) * 4; }
+
 void choose_staged(qr_plan *pl)
 {
     pl->rw = pl->gw = 0;
     const uint64_t G = pl->n_groups;
+    pl->block_s = 0;
+    if (const char *env = getenv("QR_FILL_BLOCK")) {         // "S" override: force the blocked kernel
+        int S = atoi(env);
+        if (S >= 32 && blocked_smem(S) <= MAX_SMEM) { pl->block_s = (uint32_t)S; return; }
+    }
     if (const char *env = getenv("QR_FILL_CFG")) {           // "RW,GW" override for experiments
         int rw = 0, gw = 0;
         if (sscanf(env, "%d,%d", &rw, &gw) == 2 && find_staged(rw, gw) && (uint64_t)32 * rw * G * 24 <= MAX_SMEM) {
@@ -107,7 +115,11 @@ void choose_staged(qr_plan *pl)
     const uint64_t row_bytes = G * 24;
     if (G < 8 && 32 * row_bytes <= MAX_SMEM)  { pl->rw = 1; pl->gw = 4; }
     else if (32 * row_bytes <= 113 * 1024)    { pl->rw = 1; pl->gw = 8; }   // 2+ CTAs/SM
-    else if (32 * row_bytes <= MAX_SMEM)      { pl->rw = 1; pl->gw = 16; }  // 1 CTA/SM
+    else {
+        // whole rows do not fit (twice): subtree blocks of <= 32 groups.  Measured
+        // (profiles/r01_fill_sweep_largeG.jsonl): C3 4.52 TB/s at S=32, 3.73 at 64, 2.08 at 128.
+        pl->block_s = 32;
+    }
 }
 
 int launch_direct(const qr_plan *pl, uint64_t lo, uint64_t hi, uint64_t out_row0, uint64_t req_hi,
@@ -129,6 +141,14 @@ static int run_canonicalise(qr_plan *pl, cudaStream_t st)
 {
     qr::canonicalise_kernel<<<1, qr::K1_THREADS, 0, st>>>(pl->dev);
     QR_LAUNCH_CHECK("canonicalise_kernel");
+    return QR_OK;
+}
+
+static int run_partition(qr_plan *pl, cudaStream_t st)
+{
+    if (!pl->block_s) return QR_OK;
+    qr::partition_kernel<<<1, qr::K1_THREADS, 0, st>>>(pl->dev, pl->block_s);
+    QR_LAUNCH_CHECK("partition_kernel");
     return QR_OK;
 }
 
@@ -161,6 +181,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     const size_t o_tz = carve(T * 4), o_tc = carve(T * 16), o_perm = carve(T * 4);
     const size_t o_gx = carve(T * 4), o_goff = carve((T + 1) * 4);
     const size_t o_cnt = carve(T * 128), o_lr5 = carve(T * 128), o_meta = carve(16);
+    const size_t o_bs = carve((T + 1) * 4), o_bp = carve(T * 4);
     cudaError_t e = cudaMalloc(&pl->slab, off);
     if (e != cudaSuccess) { delete pl; return fail(QR_ERR_OOM, std::string("qr_plan_create: cudaMalloc: ") + cudaGetErrorString(e)); }
     char *b = static_cast<char *>(pl->slab);
@@ -174,6 +195,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     d.gx = reinterpret_cast<uint32_t *>(b + o_gx); d.goff = reinterpret_cast<uint32_t *>(b + o_goff);
     d.cnt = reinterpret_cast<uint32_t *>(b + o_cnt); d.lr5 = reinterpret_cast<uint32_t *>(b + o_lr5);
     d.meta = reinterpret_cast<uint32_t *>(b + o_meta);
+    d.blk_start = reinterpret_cast<uint32_t *>(b + o_bs); d.blk_p = reinterpret_cast<uint32_t *>(b + o_bp);
 
     auto bail = [&](int code) { cudaFree(pl->slab); delete pl; return code; };
     e = cudaMemcpy(b + o_raw, terms, T * sizeof(qr_term), cudaMemcpyHostToDevice);
@@ -186,6 +208,14 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     pl->n_groups = meta[0];
     if (pl->n_groups == 0 || pl->n_groups > T) return bail(fail(QR_ERR_CUDA, "qr_plan_create: canonicalisation produced no groups"));
     choose_staged(pl);
+    if (pl->block_s) {
+        rc = run_partition(pl, nullptr);
+        if (rc != QR_OK) return bail(rc);
+        e = cudaMemcpy(meta, d.meta, sizeof(meta), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: partition: ") + cudaGetErrorString(e)));
+        pl->n_blocks = meta[2];
+        if (pl->n_blocks == 0) return bail(fail(QR_ERR_CUDA, "qr_plan_create: partition produced no blocks"));
+    }
     *out = pl;
     return QR_OK;
 }
@@ -231,7 +261,8 @@ extern "C" int qr_plan_canonicalise_async(qr_plan *pl, void *stream)
 {
     if (!pl) return fail(QR_ERR_INVALID, "qr_plan_canonicalise_async: NULL plan");
     QR_CUDA(cudaSetDevice(pl->device));
-    return run_canonicalise(pl, as_stream(stream));
+    int rc = run_canonicalise(pl, as_stream(stream));
+    return rc != QR_OK ? rc : run_partition(pl, as_stream(stream));
 }
 
 // =====================================================================================
@@ -260,6 +291,27 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
     const uint64_t G = pl->n_groups;
     const uint64_t indptr_base = (flags & QR_INDPTR_GLOBAL) ? row_lo * G : 0;
     uint64_t lo = row_lo, hi = row_hi;
+    if (!(flags & QR_FILL_DIRECT) && pl->block_s) {
+        const uint64_t s0 = align_up(row_lo, 32), s1 = row_hi / 32 * 32;
+        if (s1 > s0) {
+            const size_t smem = blocked_smem(pl->block_s);
+            const uint64_t strips = (s1 - s0) / 32;
+            // enough CTAs to fill the chip several times over, else as many strips per CTA as
+            // amortise the table load (17 KB at S=64 against ~35 KB of output per strip)
+            uint32_t per_cta = 8;
+            while (per_cta > 1 && (strips + per_cta - 1) / per_cta * pl->n_blocks < 148ull * 16) per_cta /= 2;
+            const uint64_t ctas = (strips + per_cta - 1) / per_cta * pl->n_blocks;
+            if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_blocked: row window too large for one launch");
+            QR_CUDA(cudaFuncSetAttribute(qr::fill_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+            if (rc != QR_OK) return rc;
+            qr::fill_blocked_kernel<<<(unsigned)ctas, 32 * qr::FILL_BLOCKED_WARPS, smem, st>>>(
+                pl->dev, (uint32_t)G, pl->block_s, pl->n_blocks, per_cta, s0, strips, row_lo, indptr_base,
+                d_indptr, d_indices, d_data, row_hi - row_lo);
+            QR_LAUNCH_CHECK("fill_blocked_kernel");
+            return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+        }
+    }
     const StagedCfg *cfg = (flags & QR_FILL_DIRECT) || pl->rw == 0 ? nullptr : find_staged(pl->rw, pl->gw);
     if (cfg) {
         const uint64_t R = 32ull * cfg->rw;

@@ -170,6 +170,25 @@ def test_direct_equals_staged(fixtures):
     assert_same(a, b, "staged vs direct")
 
 
+@pytest.mark.parametrize("S", [32, 48, 64, 128])
+@pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2"])
+def test_blocked_kernel(fixtures, monkeypatch, name, S):
+    """Large-G path (partition_kernel + fill_blocked_kernel) forced on every case: subtree blocks
+    of at most S groups, whole matrix and ragged windows."""
+    monkeypatch.setenv("QR_FILL_BLOCK", str(S))
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    G, dim = plan.n_groups, 1 << n
+    assert_same(device_build(plan, 0, dim), ref, f"{name} S={S}")
+    if dim >= 128:
+        for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 33)]:
+            ip, ix, dt = device_build(plan, lo, hi)
+            assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G])), (lo, hi)
+            assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
+
+
 def test_build_host_windows(fixtures):
     labels, coeffs = fixtures["H4"]
     n, params = O.make_params(labels, coeffs)
