@@ -67,7 +67,10 @@ class ClockSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
-    def __init__(self, local_rank):
+    def __init__(self, local_rank, interval=0.005):
+        # NVML queries contend with CUDA driver calls (a 2 ms poll slowed cudaMemcpy 4x), so poll
+        # gently and stop before the host-facing e2e loop
+        self.interval = interval
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
         self._stop = threading.Event()
         try:
@@ -97,7 +100,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.interval)
 
     def start(self):
         if self.ok:
@@ -280,30 +283,52 @@ def run_b200(args, rank, local_rank, world):
     fill_ms = float(np.mean([elapsed(a, b) for a, b in fill_ev]))
     fill_ms = max_over_ranks(fill_ms)
 
-    # ---- matrix-free H.v on the same operator (compulsory bytes: read v once, write y once) ----
+    # ---- matrix-free H.v: BASELINE config 4 (TFIM 5x5, n=25), rows sharded over the ranks.
+    # N=1: local apply.  N>1: ncclAllGather of the row-sharded v (inside the C library) + apply.
     hv = None
     if not args.no_hv:
-        d_v, d_y = DeviceBuffer(dim * 16, device), DeviceBuffer(rows * 16, device)
-        from qrusty_b200 import hamiltonians as H
+        from qrusty_b200 import hamiltonians as H, dist as qd
+        hl, hc = H.tfim_lattice(5, 5, 1.0, 3.0)
+        hop = Q.SparsePauliOp([Q.Pauli(l) for l in hl], hc)
+        hplan = hop.plan(device)
+        hdim, hG = hplan.dim, hplan.n_groups
+        hrows = hdim // world
+        hlo, hhi = qd.row_block(rank, world, hdim)
+        d_vs, d_y = DeviceBuffer(hrows * 16, device), DeviceBuffer(hrows * 16, device)
+        d_vf = DeviceBuffer(hdim * 16, device)
         chunk = 1 << 22
-        for c0 in range(0, dim, chunk):
-            v = H.lanczos_start_vector(c0, min(dim, c0 + chunk))
-            call("qr_memcpy_h2d", d_v.ptr + c0 * 16, v.ctypes.data, v.nbytes, None)
+        for c0 in range(hlo, hhi, chunk):
+            v = H.lanczos_start_vector(c0, min(hhi, c0 + chunk))
+            call("qr_memcpy_h2d", d_vs.ptr + (c0 - hlo) * 16, v.ctypes.data, v.nbytes, None)
+        comm = qd.create_comm(dist, device) if dist is not None else None
+
+        def hv_step():
+            if comm is None:
+                call("qr_apply_device", hplan.handle, hlo, hhi, d_vs.ptr, d_y.ptr, stream)
+            else:
+                call("qr_apply_distributed", hplan.handle, comm, d_vs.ptr, d_vf.ptr, d_y.ptr, stream)
         for _ in range(3):
-            call("qr_apply_device", plan.handle, lo, hi, d_v.ptr, d_y.ptr, stream)
+            hv_step()
+        call("qr_stream_synchronize", stream)
         h0, h1 = ev(), ev()
         barrier()
         reps = 20
         call("qr_event_record", h0, stream)
         for _ in range(reps):
-            call("qr_apply_device", plan.handle, lo, hi, d_v.ptr, d_y.ptr, stream)
+            hv_step()
         call("qr_event_record", h1, stream)
         call("qr_stream_synchronize", stream)
         hv_ms = max_over_ranks(elapsed(h0, h1) / reps)
-        hv = {"workload": name, "ms": hv_ms, "gbs_compulsory": 32.0 * dim / hv_ms / 1e6,
-              "gbs_gather_effective": 16.0 * (G + 1) * dim / hv_ms / 1e6,
-              "note": "local apply on a replicated v (no allgather); vector %s L2" % ("fits" if dim * 16 < 100e6 else "exceeds")}
-        del d_v, d_y
+        hv = {"workload": "tfim_5x5_n25", "n_groups": hG, "ms": hv_ms, "gbs_compulsory": 32.0 * hdim / hv_ms / 1e6,
+              "gbs_gather_effective": 16.0 * (hG + 1) * hdim / hv_ms / 1e6,
+              "nvlink_gbs_in_per_gpu": (16.0 * hdim * (world - 1) / world / hv_ms / 1e6) if world > 1 else None,
+              "note": ("ncclAllGather(v shards) + local matrix-free apply per rank" if world > 1 else
+                       "local matrix-free apply") + "; compulsory bytes = read v once + write y once (32 B/row)"}
+        if comm is not None:
+            call("qr_comm_destroy", comm)
+        del d_vs, d_vf, d_y, hplan, hop
+
+    sampler.stop()
 
     # ---- e2e: the public API with host buffers, copies inside the timed region -------------------
     e2e = None
@@ -328,7 +353,6 @@ def run_b200(args, rank, local_rank, world):
         e2e = {"value": nnz_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(len(terms) * 32),
                "d2h_bytes_per_step": int(bytes_local), "ms_per_step": t_e2e * 1e3,
                "path": "SparsePauliOp.from_terms(terms).to_matrix_mode('Cuda').export(): plan (H2D + K1), K3, D2H of the CSR into pinned host arrays (per rank: its row block)"}
-    sampler.stop()
     barrier()
 
     if rank == 0:
@@ -347,7 +371,7 @@ def run_b200(args, rank, local_rank, world):
                          "algorithmic_bytes_per_launch": bytes_local, "kernel_ms": fill_ms,
                          "bytes_per_nnz": 24 + 8.0 / G},
             "gpu_launches": int(launches),
-            "clocks": sampler.summary("timed region + H.v + e2e loops"),
+            "clocks": sampler.summary("timed region + H.v loop"),
         }
         if hv:
             line["hv"] = hv

@@ -234,9 +234,6 @@ class SparsePauliOp:
             plan = self.plan(d)
             lo, hi = dim // ngpus * d, dim // ngpus * (d + 1)
             shards.append(_Shard.build(plan, lo, hi))
-        for s in shards:
-            call("qr_set_device", s.device)
-            synchronize()
         return SpMat._from_shards((dim, dim), shards)
 
     def to_matrix_rows(self, row_lo, row_hi, device=0):
@@ -246,8 +243,6 @@ class SparsePauliOp:
         if not (0 <= row_lo < row_hi <= plan.dim):
             raise Exception("to_matrix_rows: bad row range")
         sh = _Shard.build(plan, row_lo, row_hi, local=True)
-        call("qr_set_device", device)
-        synchronize()
         return SpMat._from_shards((row_hi - row_lo, plan.dim), [sh])
 
     # -- matrix-free H.v -------------------------------------------------------------
@@ -269,24 +264,32 @@ class SparsePauliOp:
 
 
 class _Shard:
-    """Rows [lo,hi) of the CSR, resident on one device."""
+    """Rows [lo,hi) of the CSR on one device.  Plan-backed shards are LAZY: nothing is built
+    until the CSR is needed on the device (SpMV, copy) -- export() streams fill -> PCIe windows
+    straight into pinned host arrays (qr_build_host) without ever holding the shard in HBM."""
 
-    def __init__(self, plan, lo, hi, indptr, indices, data, off=None):
+    def __init__(self, plan, lo, hi, indptr=None, indices=None, data=None, off=None, local=False):
         self.plan, self.lo, self.hi = plan, lo, hi
         self.off = lo if off is None else off        # first row of this shard inside its SpMat
+        self.local = local                           # indptr relative to the shard (else global)
         self.device = plan.device if plan is not None else indptr.device
         self.indptr, self.indices, self.data = indptr, indices, data
         self.nnz = (hi - lo) * plan.n_groups if plan is not None else None
 
     @classmethod
     def build(cls, plan, lo, hi, local=False):
-        rows, G = hi - lo, plan.n_groups
-        indptr = DeviceBuffer((rows + 1) * 8, plan.device)
-        indices = DeviceBuffer(rows * G * 8, plan.device)
-        data = DeviceBuffer(rows * G * 16, plan.device)
-        call("qr_build_rows_device", plan.handle, lo, hi, indptr.ptr, indices.ptr, data.ptr,
-             _ffi.QR_INDPTR_LOCAL if local else _ffi.QR_INDPTR_GLOBAL, None)
-        return cls(plan, lo, hi, indptr, indices, data, off=0 if local else lo)
+        return cls(plan, lo, hi, off=0 if local else lo, local=local)
+
+    def materialise(self, stream=None):
+        """Build the shard in HBM (asynchronous on `stream`)."""
+        if self.data is None:
+            plan, rows, G = self.plan, self.hi - self.lo, self.plan.n_groups
+            self.indptr = DeviceBuffer((rows + 1) * 8, plan.device)
+            self.indices = DeviceBuffer(rows * G * 8, plan.device)
+            self.data = DeviceBuffer(rows * G * 16, plan.device)
+            call("qr_build_rows_device", plan.handle, self.lo, self.hi, self.indptr.ptr, self.indices.ptr,
+                 self.data.ptr, _ffi.QR_INDPTR_LOCAL if self.local else _ffi.QR_INDPTR_GLOBAL, stream)
+        return self
 
 
 class SpMat:
@@ -314,7 +317,7 @@ class SpMat:
             b = DeviceBuffer(max(a.nbytes, 16), device)
             b.upload(a)
             bufs.append(b)
-        sh = _Shard(None, 0, int(shape[0]), *bufs)
+        sh = _Shard(None, 0, int(shape[0]), *bufs, local=True)
         sh.nnz = len(data)
         return SpMat._from_shards((int(shape[0]), int(shape[1])), [sh])
 
@@ -341,6 +344,9 @@ class SpMat:
     def __copy__(self):
         shards = []
         for s in self._live("cannot copy an exported sparse matrix"):
+            if s.data is None:                       # lazy: nothing to duplicate yet
+                shards.append(_Shard(s.plan, s.lo, s.hi, off=s.off, local=s.local))
+                continue
             bufs = []
             for b in (s.indptr, s.indices, s.data):
                 nb = DeviceBuffer(b.nbytes, b.device)
@@ -348,7 +354,7 @@ class SpMat:
                 b.download(tmp)
                 nb.upload(tmp)
                 bufs.append(nb)
-            c = _Shard(s.plan, s.lo, s.hi, *bufs, off=s.off)
+            c = _Shard(s.plan, s.lo, s.hi, *bufs, off=s.off, local=s.local)
             c.nnz = s.nnz
             shards.append(c)
         return SpMat._from_shards(self._shape, shards)
@@ -366,9 +372,21 @@ class SpMat:
             d.download(out[s.off:s.off + s.hi - s.lo])
         return out
 
+    def to_device(self):
+        """Materialise every shard in HBM (needed for SpMV on the stored matrix); returns self."""
+        shards = self._live("cannot use an exported sparse matrix")
+        for s in shards:
+            s.materialise()
+        for s in shards:
+            call("qr_set_device", s.device)
+            synchronize()
+        return self
+
     def export(self):
         """-> ((rows, cols), data, indices, indptr), then the matrix is gone
-        (pyqrusty/src/lib.rs:190-214).  Arrays live in pinned host memory."""
+        (pyqrusty/src/lib.rs:190-214).  Arrays live in pinned host memory.  Shards not yet
+        built are produced by qr_build_host: row windows filled on the GPU and copied over PCIe
+        on two streams, never resident in HBM as a whole."""
         shards = self._live("cannot export from an already-exported sparse matrix")
         nnz = self.nnz()
         data = pinned_empty(nnz, np.complex128)
@@ -378,13 +396,18 @@ class SpMat:
         streams = []
         for s in shards:
             rows = s.hi - s.lo
-            call("qr_set_device", s.device)
-            st = C.c_void_p()
-            call("qr_stream_create", C.byref(st))
-            streams.append((s.device, st))
-            s.data.download(data[off:off + s.nnz], stream=st)
-            s.indices.download(indices[off:off + s.nnz], stream=st)
-            s.indptr.download(indptr[s.off:s.off + rows + 1], stream=st)
+            if s.data is None:
+                call("qr_build_host", s.plan.handle, s.lo, s.hi, indptr[s.off:].ctypes.data,
+                     indices[off:].ctypes.data, data[off:].ctypes.data,
+                     _ffi.QR_INDPTR_LOCAL if s.local else _ffi.QR_INDPTR_GLOBAL)
+            else:
+                call("qr_set_device", s.device)
+                st = C.c_void_p()
+                call("qr_stream_create", C.byref(st))
+                streams.append((s.device, st))
+                s.data.download(data[off:off + s.nnz], stream=st)
+                s.indices.download(indices[off:off + s.nnz], stream=st)
+                s.indptr.download(indptr[s.off:s.off + rows + 1], stream=st)
             off += s.nnz
         for dev, st in streams:
             call("qr_set_device", dev)
@@ -405,7 +428,7 @@ def csr_matrix(m):
 def spmat_dot_densevec(spmat, x):
     """pyqrusty spmat_dot_densevec (pyqrusty/src/lib.rs:476-491) -> accel.rs:338-370:
     CSR SpMV over the device-resident matrix, sequential per row in stored order."""
-    shards = spmat._live("cannot multiply with an exported sparse matrix")
+    shards = spmat.to_device()._live("cannot multiply with an exported sparse matrix")
     x = np.ascontiguousarray(x, dtype=np.complex128)
     y = np.empty(spmat._shape[0], np.complex128)
     for s in shards:

@@ -1,0 +1,52 @@
+"""One-process-per-GPU plumbing.  The CSR build shards by contiguous row blocks and needs no
+collective; the matrix-free H.v all-gathers the row-sharded vector with NCCL (qr_comm_*, inside
+the C library).  torch.distributed is used only as the rendezvous that carries the NCCL unique
+id and for barriers / max-over-ranks reductions; any backend works ("gloo" in the CPU tests).
+"""
+import ctypes as C
+
+
+def row_block(rank, world, dim):
+    """Rows [lo,hi) owned by `rank`: contiguous blocks = fixed top log2(world) row bits
+    (SURVEY.md 8(e)).  world must divide dim."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("row_block: bad rank/world")
+    if dim % world:
+        raise ValueError("row_block: %d ranks do not divide %d rows" % (world, dim))
+    rows = dim // world
+    return rank * rows, (rank + 1) * rows
+
+
+def owner_of_row(row, world, dim):
+    return row // (dim // world)
+
+
+def exchange_unique_id(dist, make_id, src=0):
+    """Rank `src` creates the 128-byte NCCL unique id (make_id() -> bytes); everyone gets it."""
+    box = [make_id() if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    if not isinstance(box[0], (bytes, bytearray)) or len(box[0]) != 128:
+        raise RuntimeError("exchange_unique_id: malformed id")
+    return bytes(box[0])
+
+
+def max_over_ranks(dist, value, device=None):
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def create_comm(dist, device):
+    """-> qr_comm handle (ctypes void*) spanning the default process group."""
+    from . import _ffi
+
+    def make_id():
+        buf = C.create_string_buffer(_ffi.QR_UNIQUE_ID_BYTES)
+        _ffi.call("qr_comm_unique_id", buf)
+        return buf.raw
+
+    uid = exchange_unique_id(dist, make_id)
+    comm = C.c_void_p()
+    _ffi.call("qr_comm_create", uid, dist.get_world_size(), dist.get_rank(), device, C.byref(comm))
+    return comm
