@@ -21,23 +21,203 @@ __device__ __forceinline__ double2 ld_nc_double2(const double2 *ptr)
 // v[r ^ x] is one aligned 512-byte segment with lanes permuted, so every load is
 // fully coalesced; re-use across groups is left to L1/L2.
 constexpr int APPLY_THREADS = 256;
+constexpr int APPLY_ROWS = 4;          // rows per thread: group descriptors are read once per 4 rows
+constexpr int APPLY_BATCH = 128;       // descriptors staged in shared memory at a time (4 KB)
 
+// acc += a * w, with the 2-FMA form when a is known to be real (warp-uniform flag)
+__device__ __forceinline__ void cfma(double &yr, double &yi, double ar, double ai, double2 w, bool a_real)
+{
+    if (a_real) { yr += ar * w.x; yi += ar * w.y; }
+    else { yr += ar * w.x - ai * w.y; yi += ar * w.y + ai * w.x; }
+}
+
+// Values of one row-dependent group for E rows at once: the term table is walked once, every
+// (z, c') is loaded once (warp-uniform) and applied to the E rows held in registers.
+template <int E>
+__device__ __forceinline__ void group_values(const PlanDev &p, uint32_t t0, uint32_t t1, const uint32_t (&r)[E],
+                                             double (&ar)[E], double (&ai)[E])
+{
+    double2 c = __ldg(&p.tc[t0]);
+    uint32_t z = __ldg(&p.tz[t0]);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint32_t s = (uint32_t)(__popc(r[e] & z) & 1) << 31;
+        ar[e] = flip_sign(c.x, s); ai[e] = flip_sign(c.y, s);
+    }
+    for (uint32_t t = t0 + 1; t < t1; t++) {
+        c = __ldg(&p.tc[t]);
+        z = __ldg(&p.tz[t]);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint32_t s = (uint32_t)(__popc(r[e] & z) & 1) << 31;
+            ar[e] += flip_sign(c.x, s); ai[e] += flip_sign(c.y, s);
+        }
+    }
+}
+
+// v0 (gather): thread <-> APPLY_ROWS rows (r, r+256, ...), so a warp's loads of v[r ^ x] stay one
+// permuted, fully coalesced 512-byte segment.  Group descriptors come through shared memory.
+// `diag` (optional): cached values of the mask-0 group for rows [row_lo,row_hi); when given, group 0
+// is not re-evaluated (an eigensolver applies the same operator hundreds of times).
 __global__ void __launch_bounds__(APPLY_THREADS)
 apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
-                    const double2 *__restrict__ v, double2 *__restrict__ y)
+                    const double2 *__restrict__ v, double2 *__restrict__ y,
+                    const double2 *__restrict__ diag)
 {
-    const uint64_t r64 = row_lo + (uint64_t)blockIdx.x * APPLY_THREADS + threadIdx.x;
-    if (r64 >= row_hi) return;
-    const uint32_t r = (uint32_t)r64;
-    double yr = 0.0, yi = 0.0;
-    for (uint32_t g = 0; g < G; g++) {
-        const uint32_t x = __ldg(&p.gx[g]);
-        const double2 a = group_value(p.tz, p.tc, __ldg(&p.goff[g]), __ldg(&p.goff[g + 1]), r);
-        const double2 w = ld_nc_double2(&v[r ^ x]);
-        yr += a.x * w.x - a.y * w.y;
-        yi += a.x * w.y + a.y * w.x;
+    constexpr int E = APPLY_ROWS;
+    __shared__ GroupDesc sd[APPLY_BATCH];
+    const uint64_t cta_base = row_lo + (uint64_t)blockIdx.x * (APPLY_THREADS * E);
+    uint32_t r[E];
+    bool live[E];
+    double yr[E], yi[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint64_t r64 = cta_base + (uint64_t)e * APPLY_THREADS + threadIdx.x;
+        live[e] = r64 < row_hi;
+        r[e] = (uint32_t)(live[e] ? r64 : row_hi - 1);          // clamp: dead rows recompute a live one
+        yr[e] = 0.0; yi[e] = 0.0;
     }
-    y[r64 - row_lo] = make_double2(yr, yi);
+    uint32_t g_first = 0;
+    if (diag != nullptr) {
+        g_first = 1;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const double2 d = __ldcs(&diag[(uint64_t)r[e] - row_lo]);      // evict-first: keep L2 for v
+            cfma(yr[e], yi[e], d.x, d.y, ld_nc_double2(&v[r[e]]), false);
+        }
+    }
+    for (uint32_t g0 = g_first; g0 < G; g0 += APPLY_BATCH) {
+        const uint32_t nb = min((uint32_t)APPLY_BATCH, G - g0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nb * 2u; i += APPLY_THREADS)
+            reinterpret_cast<uint4 *>(sd)[i] = __ldg(reinterpret_cast<const uint4 *>(p.gdesc + g0) + i);
+        __syncthreads();
+        for (uint32_t k = 0; k < nb; k++) {
+            const GroupDesc d = sd[k];
+            const bool real = (d.flag & 2u) != 0u;
+            if (d.flag & 1u) {
+#pragma unroll
+                for (int e = 0; e < E; e++) cfma(yr[e], yi[e], d.cre, d.cim, ld_nc_double2(&v[r[e] ^ d.x]), real);
+            } else {
+                double ar[E], ai[E];
+                group_values<E>(p, d.t0, d.t1, r, ar, ai);
+#pragma unroll
+                for (int e = 0; e < E; e++) cfma(yr[e], yi[e], ar[e], ai[e], ld_nc_double2(&v[r[e] ^ d.x]), real);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++)
+        if (live[e]) __stcs(&y[(uint64_t)r[e] - row_lo], make_double2(yr[e], yi[e]));   // streaming store
+}
+
+// ---------------------------------------------------------------------------------
+// v1: multi-pass shared-memory tiling.
+//
+// v0 moves 16*(G+1) bytes per row through L1/L2.  Here the groups are split into passes;
+// pass q owns a set S_q of K bit positions (bits 0..4 plus K-5 higher bits of the
+// LOCAL row index) and every group whose X-mask lies inside S_q.  A CTA takes one
+// tile = the 2^K elements of v whose bits outside S_q are fixed (2^(K-5) runs of 32
+// consecutive elements, 512 B each), loads it into shared memory once, and for each of
+// its rows accumulates sum_g a_g(r) * tile[idx ^ cx_g] where idx is the row's index inside
+// the tile and cx_g the mask compacted onto S_q.  Pass 0 writes y, later passes add to
+// it, so HBM/L2 traffic is 32 + 48*(passes-1) bytes per row instead of 16*(G+1).
+// Groups that fit no pass (mask wider than K-5 high bits, or touching bits above the
+// local row block in a row-sharded apply) are gathered from global memory in pass 0.
+// ---------------------------------------------------------------------------------
+struct ApplyPass {
+    const uint32_t *groups;     // group ids applied from shared memory in this pass
+    const uint32_t *cmask;      // their masks compacted onto S (tile-index space)
+    uint32_t n_groups;
+    const uint32_t *direct;     // pass 0 only: groups gathered from global memory
+    uint32_t n_direct;
+    const uint32_t *expand;     // [2^(K-5)]: tile index bits >= 5 -> row bits (S positions)
+    uint32_t free_mask;         // local row bits NOT in S (enumerated by blockIdx)
+    uint32_t first;             // 1: y = acc, 0: y += acc
+    const double2 *diag;        // pass 0 only, optional: cached mask-0 group (then not in `groups`)
+};
+
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+apply_pass_kernel(PlanDev p, ApplyPass ps, uint64_t row_lo, const double2 *__restrict__ v,
+                  double2 *__restrict__ y)
+{
+    constexpr uint32_t TILE = 1u << K, RUNS = TILE / 32u;
+    constexpr int E = APPLY_ROWS;
+    constexpr int CHUNKS = TILE / (THREADS * E);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *tile = reinterpret_cast<double2 *>(smem_raw);                               // [2^K]
+    uint32_t *s_exp = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TILE * 16);          // [2^(K-5)]
+    GroupDesc *sd = reinterpret_cast<GroupDesc *>(smem_raw + (size_t)TILE * 16 + RUNS * 4); // [APPLY_BATCH]
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // scatter blockIdx's bits onto the free (non-S) positions of the local row index
+    uint32_t fixed = 0, rest = blockIdx.x, fm = ps.free_mask;
+    while (fm) { const uint32_t b = fm & (0u - fm); if (rest & 1u) fixed |= b; rest >>= 1; fm ^= b; }
+    const uint32_t base = (uint32_t)row_lo + fixed;                      // row_lo is block-aligned
+
+    for (uint32_t j = threadIdx.x; j < RUNS; j += THREADS) s_exp[j] = __ldg(&ps.expand[j]);
+    __syncthreads();
+    for (uint32_t j = warp; j < RUNS; j += THREADS / 32)
+        tile[j * 32u + lane] = ld_nc_double2(&v[(base | s_exp[j]) + lane]);
+
+    const uint32_t n_all = ps.n_groups + ps.n_direct;
+    for (int c = 0; c < CHUNKS; c++) {
+        uint32_t idx[E], r[E];
+        double yr[E], yi[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            idx[e] = (uint32_t)(c * E + e) * THREADS + threadIdx.x;
+            yr[e] = 0.0; yi[e] = 0.0;
+        }
+        for (uint32_t g0 = 0; g0 < n_all || g0 == 0; g0 += APPLY_BATCH) {
+            const uint32_t nb = min((uint32_t)APPLY_BATCH, n_all - g0);
+            __syncthreads();                                     // tile loaded / previous batch consumed
+            for (uint32_t i = threadIdx.x; i < nb; i += THREADS) {
+                const uint32_t k = g0 + i;
+                GroupDesc d;
+                if (k < ps.n_groups) { d = p.gdesc[__ldg(&ps.groups[k])]; d.x = __ldg(&ps.cmask[k]); }
+                else { d = p.gdesc[__ldg(&ps.direct[k - ps.n_groups])]; d.flag |= 4u; }      // bit2: gather from global
+                sd[i] = d;
+            }
+            __syncthreads();
+            if (g0 == 0) {
+#pragma unroll
+                for (int e = 0; e < E; e++) r[e] = (base | s_exp[idx[e] >> 5]) + (idx[e] & 31u);
+                if (ps.diag != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        const double2 dg = ps.diag[(uint64_t)r[e] - row_lo];
+                        cfma(yr[e], yi[e], dg.x, dg.y, tile[idx[e]], false);
+                    }
+                }
+            }
+            for (uint32_t k = 0; k < nb; k++) {
+                const GroupDesc d = sd[k];
+                const bool real = (d.flag & 2u) != 0u;
+                double ar[E], ai[E];
+                if (d.flag & 1u) {
+#pragma unroll
+                    for (int e = 0; e < E; e++) { ar[e] = d.cre; ai[e] = d.cim; }
+                } else {
+                    group_values<E>(p, d.t0, d.t1, r, ar, ai);
+                }
+                if (d.flag & 4u) {
+#pragma unroll
+                    for (int e = 0; e < E; e++) cfma(yr[e], yi[e], ar[e], ai[e], ld_nc_double2(&v[r[e] ^ d.x]), real);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; e++) cfma(yr[e], yi[e], ar[e], ai[e], tile[idx[e] ^ d.x], real);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            double2 *out = &y[(uint64_t)r[e] - row_lo];
+            if (!ps.first) { const double2 o = *out; yr[e] += o.x; yi[e] += o.y; }
+            *out = make_double2(yr[e], yi[e]);
+        }
+    }
 }
 
 // diag(H): only the group with X-mask 0 (gx[0], masks are ascending) touches the diagonal.

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
     __shared__ uint16_t wcount[K1_WARPS][256];      // per-warp digit counts of the current tile
     __shared__ uint32_t woffset[K1_WARPS][256];     // per-warp digit start positions
     __shared__ uint32_t scan_scratch[33];
-    __shared__ uint32_t max_group;
+    __shared__ uint32_t max_group, n_const;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t T = p.n_terms;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
     // ---- 0. keys = X-masks, payload = original index ---------------------------------
     for (uint32_t i = tid; i < T; i += K1_THREADS) { p.key_a[i] = (uint32_t)p.raw[i].x; p.idx_a[i] = i; }
     for (uint32_t i = tid; i < K1_WARPS * 256; i += K1_THREADS) (&wcount[0][0])[i] = 0;
-    if (tid == 0) max_group = 0;
+    if (tid == 0) { max_group = 0; n_const = 0; }
     __syncthreads();
 
     // ---- 1. stable LSD radix sort -----------------------------------------------------
@@ -131,7 +131,26 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
         }
         p.cnt[q] = c;
     }
-    for (uint32_t g = tid; g < G; g += K1_THREADS) atomicMax(&max_group, p.goff[g + 1] - p.goff[g]);
+    for (uint32_t g = tid; g < G; g += K1_THREADS) {
+        const uint32_t t0 = p.goff[g], t1 = p.goff[g + 1];
+        atomicMax(&max_group, t1 - t0);
+        // row-independent groups (all z == 0: X-only strings) and real-valued groups
+        uint32_t zor = p.tz[t0];
+        double2 c = p.tc[t0];
+        double re = c.x, im = c.y;
+        bool real = c.y == 0.0;
+        for (uint32_t t = t0 + 1; t < t1; t++) {
+            zor |= p.tz[t];
+            c = p.tc[t];
+            re = __dadd_rn(re, c.x); im = __dadd_rn(im, c.y);     // same fold as the fill kernels
+            real = real && c.y == 0.0;
+        }
+        p.gflag[g] = (zor == 0u ? 1u : 0u) | (real ? 2u : 0u);
+        if (zor == 0u) atomicAdd(&n_const, 1u);
+        p.gconst[g] = make_double2(re, im);
+        GroupDesc d; d.x = p.gx[g]; d.flag = p.gflag[g]; d.t0 = t0; d.t1 = t1; d.cre = re; d.cim = im;
+        p.gdesc[g] = d;
+    }
     __syncthreads();
     for (uint32_t q = tid; q < G * 32u; q += K1_THREADS) {
         const uint32_t g = q >> 5, j = q & 31u;
@@ -140,7 +159,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
         for (uint32_t b = 0; b < 5; b++) s += ((j >> b) & 1u) ? p.cnt[g * 32u + b] : 0u;
         p.lr5[q] = s;
     }
-    if (tid == 0) { p.meta[1] = max_group; p.meta[2] = 0; p.meta[3] = 0; }
+    if (tid == 0) { p.meta[1] = max_group; p.meta[2] = 0; p.meta[3] = 0; p.meta[4] = n_const; }
 }
 
 // K1b: cut the sorted masks into maximal trie subtrees of at most S groups (S >= 32).

@@ -18,7 +18,11 @@ namespace qr {
 //   goff  u32[G+1]        group g owns sorted terms [goff[g], goff[g+1])
 //   cnt   u32[G][32]      cnt[g][b] = #{h != g : msb(gx[g]^gx[h]) == b}
 //   lr5   u32[G][32]      lr5[g][j] = sum_{b<5} cnt[g][b] * bit_b(j)
-//   meta  u32[4]          {G, max terms in a group, B, S}
+//   gflag u32[G]          bit0: every term of the group has z == 0 (value is row-independent)
+//                         bit1: every c' of the group is real (im == +-0)
+//   gconst double2[G]     the group's ordered sum of c' (its value when bit0 is set)
+//   gdesc GroupDesc[G]    {x, flag, t0, t1, gconst} packed in 32 B for the H.v kernels
+//   meta  u32[8]          {G, max terms in a group, B, S, #row-independent groups, 0, 0, 0}
 //   blk_start u32[B+1]    large-G path: the sorted groups cut into B trie subtrees ("blocks")
 //   blk_p     u32[B]      of <= S groups; block b = groups [blk_start[b], blk_start[b+1]), all
 //                         sharing the mask bits >= blk_p[b] (>= 5).  A subtree's groups fill
@@ -28,6 +32,11 @@ namespace qr {
 //   slot(r,g) = sum_b cnt[g][b] * bit_b(gx[g] ^ r)
 // because h precedes g in row r  <=>  (r^gx[h]) < (r^gx[g])  <=>  at the most
 // significant bit where gx[h] and gx[g] differ, r^gx[g] has a 1.
+struct __align__(16) GroupDesc {
+    uint32_t x, flag, t0, t1;      // mask (or tile-compacted mask), gflag, term range
+    double   cre, cim;             // gconst
+};
+
 struct PlanDev {
     int       n_qubits;
     uint32_t  n_terms;
@@ -40,6 +49,9 @@ struct PlanDev {
     uint32_t *goff;
     uint32_t *cnt;
     uint32_t *lr5;
+    uint32_t *gflag;
+    double2  *gconst;
+    GroupDesc *gdesc;
     uint32_t *meta;
     uint32_t *blk_start;
     uint32_t *blk_p;

@@ -1,11 +1,13 @@
 // qrusty_cuda.cu -- the extern "C" boundary (include/qrusty_cuda.h) over the sm_100a kernels.
 // No torch, no CPU compute path: every compute entry point launches kernels or fails.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <new>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -48,8 +50,20 @@ constexpr size_t MAX_SMEM = 227 * 1024;
 
 }  // namespace
 
+// H.v pass plan for a local row block of 2^m rows (see apply.cuh)
+struct ApplyPlan {
+    std::vector<qr::ApplyPass> passes;
+    void *slab = nullptr;
+};
+
 struct qr_plan {
     qr::PlanDev dev{};
+    std::map<int, ApplyPlan> apply_plans;       // keyed by log2(rows of the block)
+    std::vector<uint32_t> host_gx;
+    // cached values of the mask-0 group (diag(H)) for one row range, reused by every apply
+    double2 *diag_cache = nullptr;
+    uint64_t diag_lo = 0, diag_hi = 0;
+    int diag_terms = -1;                        // number of terms in group 0 if its mask is 0, else 0
     int device = 0;
     int n_qubits = 0;
     uint64_t dim = 0, n_terms = 0, n_groups = 0;
@@ -57,6 +71,7 @@ struct qr_plan {
     // fill configuration chosen from G: staged whole-row tiles (rw,gw) or subtree blocks
     int rw = 0, gw = 0;
     uint32_t block_s = 0, n_blocks = 0;    // blocked kernel: S and the number of subtree blocks
+    uint32_t n_const = 0;                  // groups whose value does not depend on the row
     // lazily allocated scratch
     double2 *dot_partials = nullptr;
     void *win_buf[2] = {nullptr, nullptr};
@@ -76,14 +91,11 @@ namespace {
 // ---------------------------------------------------------------------------------
 using StagedFn = void (*)(qr::PlanDev, uint32_t, uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *,
                           double2 *, uint64_t);
-struct StagedCfg { int rw, gw; StagedFn fn; };
+struct StagedCfg { int rw, gw; StagedFn fn, fn_const; };   // fn_const: operator has row-independent groups
+#define QR_STAGED(RW, GW) {RW, GW, qr::fill_staged_kernel<RW, GW, false>, qr::fill_staged_kernel<RW, GW, true>}
 const StagedCfg kStaged[] = {
-    {1, 4, qr::fill_staged_kernel<1, 4>},  {1, 8, qr::fill_staged_kernel<1, 8>},
-    {1, 16, qr::fill_staged_kernel<1, 16>}, {2, 2, qr::fill_staged_kernel<2, 2>},
-    {2, 4, qr::fill_staged_kernel<2, 4>},  {2, 8, qr::fill_staged_kernel<2, 8>},
-    {4, 1, qr::fill_staged_kernel<4, 1>},  {4, 2, qr::fill_staged_kernel<4, 2>},
-    {4, 4, qr::fill_staged_kernel<4, 4>},  {8, 1, qr::fill_staged_kernel<8, 1>},
-    {8, 2, qr::fill_staged_kernel<8, 2>},
+    QR_STAGED(1, 4), QR_STAGED(1, 8), QR_STAGED(1, 16), QR_STAGED(2, 2), QR_STAGED(2, 4), QR_STAGED(2, 8),
+    QR_STAGED(4, 2), QR_STAGED(4, 4),
 };
 
 const StagedCfg *find_staged(int rw, int gw)
@@ -180,8 +192,9 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     const size_t o_ka = carve(T * 4), o_kb = carve(T * 4), o_ia = carve(T * 4), o_ib = carve(T * 4);
     const size_t o_tz = carve(T * 4), o_tc = carve(T * 16), o_perm = carve(T * 4);
     const size_t o_gx = carve(T * 4), o_goff = carve((T + 1) * 4);
-    const size_t o_cnt = carve(T * 128), o_lr5 = carve(T * 128), o_meta = carve(16);
+    const size_t o_cnt = carve(T * 128), o_lr5 = carve(T * 128), o_meta = carve(32);
     const size_t o_bs = carve((T + 1) * 4), o_bp = carve(T * 4);
+    const size_t o_gf = carve(T * 4), o_gc = carve(T * 16), o_gd = carve(T * sizeof(qr::GroupDesc));
     cudaError_t e = cudaMalloc(&pl->slab, off);
     if (e != cudaSuccess) { delete pl; return fail(QR_ERR_OOM, std::string("qr_plan_create: cudaMalloc: ") + cudaGetErrorString(e)); }
     char *b = static_cast<char *>(pl->slab);
@@ -196,16 +209,19 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     d.cnt = reinterpret_cast<uint32_t *>(b + o_cnt); d.lr5 = reinterpret_cast<uint32_t *>(b + o_lr5);
     d.meta = reinterpret_cast<uint32_t *>(b + o_meta);
     d.blk_start = reinterpret_cast<uint32_t *>(b + o_bs); d.blk_p = reinterpret_cast<uint32_t *>(b + o_bp);
+    d.gflag = reinterpret_cast<uint32_t *>(b + o_gf); d.gconst = reinterpret_cast<double2 *>(b + o_gc);
+    d.gdesc = reinterpret_cast<qr::GroupDesc *>(b + o_gd);
 
     auto bail = [&](int code) { cudaFree(pl->slab); delete pl; return code; };
     e = cudaMemcpy(b + o_raw, terms, T * sizeof(qr_term), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: H2D: ") + cudaGetErrorString(e)));
     int rc = run_canonicalise(pl, nullptr);
     if (rc != QR_OK) return bail(rc);
-    uint32_t meta[4] = {0, 0, 0, 0};
+    uint32_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     e = cudaMemcpy(meta, d.meta, sizeof(meta), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: canonicalise: ") + cudaGetErrorString(e)));
     pl->n_groups = meta[0];
+    pl->n_const = meta[4];
     if (pl->n_groups == 0 || pl->n_groups > T) return bail(fail(QR_ERR_CUDA, "qr_plan_create: canonicalisation produced no groups"));
     choose_staged(pl);
     if (pl->block_s) {
@@ -228,6 +244,8 @@ extern "C" int qr_plan_destroy(qr_plan *pl)
         if (pl->win_buf[i]) cudaFree(pl->win_buf[i]);
         if (pl->win_stream[i]) cudaStreamDestroy(pl->win_stream[i]);
     }
+    for (auto &kv : pl->apply_plans) if (kv.second.slab) cudaFree(kv.second.slab);
+    if (pl->diag_cache) cudaFree(pl->diag_cache);
     if (pl->dot_partials) cudaFree(pl->dot_partials);
     if (pl->slab) cudaFree(pl->slab);
     delete pl;
@@ -322,11 +340,12 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             const size_t smem = (size_t)(R * G * 24);
             const uint64_t tiles = (s1 - s0) / R;
             if (tiles > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_staged: row window too large for one launch");
-            QR_CUDA(cudaFuncSetAttribute(cfg->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            StagedFn fn = pl->n_const ? cfg->fn_const : cfg->fn;
+            QR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // prefix / suffix rows that do not fill a tile
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
-            cfg->fn<<<(unsigned)tiles, 32 * cfg->rw * cfg->gw, smem, st>>>(
+            fn<<<(unsigned)tiles, 32 * cfg->rw * cfg->gw, smem, st>>>(
                 pl->dev, (uint32_t)G, s0, row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo);
             QR_LAUNCH_CHECK("fill_staged_kernel");
             lo = s1; hi = row_hi;
@@ -399,12 +418,172 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
 // =====================================================================================
 // H.v and friends
 // =====================================================================================
+constexpr int APPLY_THREADS_V1 = 512;
+
+static int apply_tile_bits()
+{
+    if (const char *env = getenv("QR_APPLY_K")) { int k = atoi(env); if (k >= 11 && k <= 13) return k; }
+    return 12;                                   // tile = 2^12 elements = 64 KB of shared memory
+}
+
+// diag(H) of rows [row_lo,row_hi), computed once and reused by every later apply on that range
+// (the mask-0 group is by far the most expensive one: all Z-only strings land in it).
+static int ensure_diag_cache(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, cudaStream_t st, const double2 **out)
+{
+    *out = nullptr;
+    const char *off = getenv("QR_APPLY_NO_DIAG_CACHE");
+    if (off && off[0] == '1') return QR_OK;
+    if (pl->diag_terms < 0) {
+        uint32_t x0 = 1, goff1 = 0;
+        QR_CUDA(cudaMemcpy(&x0, pl->dev.gx, 4, cudaMemcpyDeviceToHost));
+        QR_CUDA(cudaMemcpy(&goff1, pl->dev.goff + 1, 4, cudaMemcpyDeviceToHost));
+        pl->diag_terms = x0 == 0 ? (int)goff1 : 0;
+    }
+    if (pl->diag_terms < 3) return QR_OK;        // cheaper to recompute than to read 16 B/row
+    if (!pl->diag_cache || pl->diag_lo != row_lo || pl->diag_hi != row_hi) {
+        if (pl->diag_cache) { QR_CUDA(cudaFree(pl->diag_cache)); pl->diag_cache = nullptr; }
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&pl->diag_cache), (row_hi - row_lo) * 16));
+        const uint64_t ctas = (row_hi - row_lo + 255) / 256;
+        qr::diagonal_kernel<<<(unsigned)ctas, 256, 0, st>>>(pl->dev, row_lo, row_hi, pl->diag_cache);
+        QR_LAUNCH_CHECK("diagonal_kernel");
+        QR_CUDA(cudaStreamSynchronize(st));      // one-time; later applies may use any stream
+        pl->diag_lo = row_lo; pl->diag_hi = row_hi;
+    }
+    *out = pl->diag_cache;
+    return QR_OK;
+}
+
+// Greedy cover of the groups by passes (apply.cuh).  m = log2(rows of the local block).
+static int make_apply_plan(qr_plan *pl, int m, int K, ApplyPlan **out)
+{
+    auto it = pl->apply_plans.find(m * 100 + K);
+    if (it != pl->apply_plans.end()) { *out = &it->second; return QR_OK; }
+    const uint32_t G = (uint32_t)pl->n_groups;
+    if (pl->host_gx.empty()) {
+        pl->host_gx.resize(G);
+        QR_CUDA(cudaMemcpy(pl->host_gx.data(), pl->dev.gx, G * 4, cudaMemcpyDeviceToHost));
+    }
+    const std::vector<uint32_t> &gx = pl->host_gx;
+    const int HB = K - 5;
+    const uint32_t local_mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+    struct HostPass { uint32_t smask; std::vector<uint32_t> groups, direct; };
+    std::vector<HostPass> hp;
+    std::vector<char> done(G, 0);
+    std::vector<uint32_t> direct;
+    // groups that can never sit in a tile: bits outside the local block, or too many high bits
+    for (uint32_t g = 0; g < G; g++)
+        if ((gx[g] & ~local_mask) || __builtin_popcount(gx[g] & ~31u) > HB) { direct.push_back(g); done[g] = 1; }
+    auto fill_to_k = [&](uint32_t smask) {          // pad S with the lowest unused local bits
+        for (int b = 5; b < m && __builtin_popcount(smask) < K; b++) smask |= 1u << b;
+        return smask;
+    };
+    bool first = true;
+    for (;;) {
+        uint32_t smask = 31u;
+        if (first) smask = fill_to_k(31u);           // pass 0: the contiguous low tile
+        else {
+            // order the uncovered groups by their highest bit; add greedily while S has room
+            std::vector<uint32_t> order;
+            for (uint32_t g = 0; g < G; g++) if (!done[g]) order.push_back(g);
+            if (order.empty()) break;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                const int ha = 31 - __builtin_clz(gx[a] | 1u), hb = 31 - __builtin_clz(gx[b] | 1u);
+                return ha != hb ? ha < hb : gx[a] < gx[b];
+            });
+            for (uint32_t g : order) {
+                const uint32_t cand = smask | gx[g];
+                if (__builtin_popcount(cand & ~31u) <= HB) smask = cand;
+            }
+            smask = fill_to_k(smask);
+        }
+        HostPass ps; ps.smask = smask;
+        for (uint32_t g = 0; g < G; g++)
+            if (!done[g] && (gx[g] & ~smask) == 0) { ps.groups.push_back(g); done[g] = 1; }
+        if (first) ps.direct = direct;
+        if (!first && ps.groups.empty()) break;      // cannot happen: every group left fits some S
+        hp.push_back(ps);
+        first = false;
+        bool any = false;
+        for (uint32_t g = 0; g < G; g++) any |= !done[g];
+        if (!any) break;
+    }
+    // device tables
+    size_t words = 0;
+    for (auto &ps : hp) words += 2 * ps.groups.size() + ps.direct.size() + (1u << HB);
+    ApplyPlan ap;
+    std::vector<uint32_t> host(words ? words : 1);
+    QR_CUDA(cudaMalloc(&ap.slab, host.size() * 4));
+    uint32_t *dbase = static_cast<uint32_t *>(ap.slab);
+    size_t off = 0;
+    for (size_t q = 0; q < hp.size(); q++) {
+        const HostPass &ps = hp[q];
+        std::vector<int> sbits;
+        for (int b = 0; b < 32; b++) if (ps.smask >> b & 1u) sbits.push_back(b);
+        auto compact = [&](uint32_t x) { uint32_t c = 0; for (size_t j = 0; j < sbits.size(); j++) if (x >> sbits[j] & 1u) c |= 1u << j; return c; };
+        qr::ApplyPass dp{};
+        dp.groups = dbase + off; for (uint32_t g : ps.groups) host[off++] = g;
+        dp.cmask = dbase + off;  for (uint32_t g : ps.groups) host[off++] = compact(gx[g]);
+        dp.n_groups = (uint32_t)ps.groups.size();
+        dp.direct = dbase + off; for (uint32_t g : ps.direct) host[off++] = g;
+        dp.n_direct = (uint32_t)ps.direct.size();
+        dp.expand = dbase + off;
+        for (uint32_t j = 0; j < (1u << HB); j++) {            // tile index bits >= 5 -> row bits
+            uint32_t rbits = 0;
+            for (size_t t = 5; t < sbits.size(); t++) if (j >> (t - 5) & 1u) rbits |= 1u << sbits[t];
+            host[off++] = rbits;
+        }
+        dp.free_mask = local_mask & ~ps.smask;
+        dp.first = q == 0 ? 1u : 0u;
+        ap.passes.push_back(dp);
+    }
+    cudaError_t e = cudaMemcpy(ap.slab, host.data(), host.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(ap.slab); return fail(QR_ERR_CUDA, std::string("make_apply_plan: ") + cudaGetErrorString(e)); }
+    *out = &(pl->apply_plans[m * 100 + K] = ap);
+    return QR_OK;
+}
+
+template <int K>
+static int launch_apply_passes(qr_plan *pl, ApplyPlan *ap, uint64_t row_lo, uint64_t rows, const double2 *v,
+                               double2 *y, const double2 *diag, cudaStream_t st)
+{
+    auto kern = qr::apply_pass_kernel<K, APPLY_THREADS_V1>;
+    const size_t smem = ((size_t)16 << K) + ((size_t)4 << (K - 5)) + qr::APPLY_BATCH * sizeof(qr::GroupDesc);
+    QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t tiles = rows >> K;
+    for (qr::ApplyPass ps : ap->passes) {
+        if (ps.first && diag != nullptr && ps.n_groups > 0) {
+            // group 0 (mask 0) is first in pass 0's list: served from the cache instead
+            ps.groups += 1; ps.cmask += 1; ps.n_groups -= 1; ps.diag = diag;
+        }
+        kern<<<(unsigned)tiles, APPLY_THREADS_V1, smem, st>>>(pl->dev, ps, row_lo, v, y);
+        QR_LAUNCH_CHECK("apply_pass_kernel");
+    }
+    return QR_OK;
+}
+
 static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double2 *v, double2 *y, cudaStream_t st)
 {
     const uint64_t rows = row_hi - row_lo;
-    const uint64_t ctas = (rows + qr::APPLY_THREADS - 1) / qr::APPLY_THREADS;
+    const double2 *diag = nullptr;
+    int rc = ensure_diag_cache(pl, row_lo, row_hi, st, &diag);
+    if (rc != QR_OK) return rc;
+    // tiled path: the rows form an aligned power-of-two block of at least one tile
+    const bool pow2 = (rows & (rows - 1)) == 0 && (row_lo & (rows - 1)) == 0;
+    const char *mode = getenv("QR_APPLY_V0");
+    const int K = apply_tile_bits();
+    if (pow2 && rows >= (1ull << K) && mode && mode[0] == '0') {
+        const int m = 63 - __builtin_clzll(rows);
+        ApplyPlan *ap = nullptr;
+        rc = make_apply_plan(pl, m, K, &ap);
+        if (rc != QR_OK) return rc;
+        if (K == 11) return launch_apply_passes<11>(pl, ap, row_lo, rows, v, y, diag, st);
+        if (K == 13) return launch_apply_passes<13>(pl, ap, row_lo, rows, v, y, diag, st);
+        return launch_apply_passes<12>(pl, ap, row_lo, rows, v, y, diag, st);
+    }
+    const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
+    const uint64_t ctas = (rows + per_cta - 1) / per_cta;
     if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "apply: row window too large for one launch");
-    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y);
+    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag);
     QR_LAUNCH_CHECK("apply_direct_kernel");
     return QR_OK;
 }

@@ -349,6 +349,42 @@ def test_apply_C2_and_linearity():
     assert abs(np.vdot(v2, y1) - np.conj(np.vdot(v1, y2))) <= 1e-9 * abs(np.vdot(v2, y1))
 
 
+def _apply_block(plan, lo, hi, v_dev):
+    dy = DeviceBuffer((hi - lo) * 16)
+    _ffi.call("qr_memset_device", dy.ptr, 0xFF, dy.nbytes, None)
+    _ffi.call("qr_apply_device", plan.handle, lo, hi, v_dev.ptr, dy.ptr, None)
+    return dy.download(np.empty(hi - lo, np.complex128))
+
+
+@pytest.mark.parametrize("name", ["xxz16", "tfim_4x4", "H8", "random_n14", "heis_n18"])
+def test_apply_tiled_passes(fixtures, monkeypatch, name):
+    """Multi-pass shared-memory H.v (apply_pass_kernel) against the v0 gather kernel and the oracle,
+    on the whole vector and on row-sharded blocks (groups touching bits above the block go direct)."""
+    labels, coeffs = {"xxz16": lambda: H.xxz_chain(16, 1.0, 0.7), "tfim_4x4": lambda: H.tfim_lattice(4, 4, 1.0, 3.0),
+                      "H8": lambda: fixtures["H8"], "random_n14": lambda: H.random_pauli_sum(14, 300, 200, 30, 11),
+                      "heis_n18": lambda: H.heisenberg_chain(18)}[name]()
+    n, params = O.make_params(labels, coeffs)
+    op = make_op(labels, coeffs)
+    plan = op.plan()
+    dim = 1 << n
+    v = H.lanczos_start_vector(0, dim, seed=31)
+    dv = DeviceBuffer(dim * 16); dv.upload(v)
+    monkeypatch.setenv("QR_APPLY_V0", "1")
+    y0 = _apply_block(plan, 0, dim, dv)
+    monkeypatch.setenv("QR_APPLY_V0", "0")
+    y1 = _apply_block(plan, 0, dim, dv)
+    absH = np.abs(params["re"] + 1j * params["im"]).sum()
+    tol = 1e-12 * absH * np.abs(v).max()
+    assert np.abs(y1 - y0).max() <= tol
+    rows = np.random.default_rng(12).integers(0, dim, 512).astype(np.uint64)
+    ref = O.apply_rows(params, rows, v)
+    assert np.abs(y1[rows.astype(np.int64)] - ref).max() <= tol
+    for parts in (2, 4):
+        blk = dim // parts
+        ys = np.concatenate([_apply_block(plan, p * blk, (p + 1) * blk, dv) for p in range(parts)])
+        assert np.abs(ys - y0).max() <= tol, parts
+
+
 # ---- accel.rs:374-393 (test_it.py:232-269, lib.rs:921-990) ------------------------------------
 def test_vector_ops_bit_exact():
     rng = np.random.default_rng(8)
