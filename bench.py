@@ -67,12 +67,15 @@ class ClockSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
-    def __init__(self, local_rank, interval=0.005):
+    def __init__(self, local_rank, interval=0.01, enabled=True):
         # NVML queries contend with CUDA driver calls (a 2 ms poll slowed cudaMemcpy 4x), so poll
         # gently and stop before the host-facing e2e loop
         self.interval = interval
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
         self._stop = threading.Event()
+        if not enabled:
+            self.err = "disabled on this rank"
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -263,7 +266,7 @@ def run_b200(args, rank, local_rank, world):
             call("qr_event_record", e_fill1, stream)
 
     K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))     # 8 processes polling NVML stall launches
     for _ in range(W):
         step()
     call("qr_stream_synchronize", stream)

@@ -130,7 +130,7 @@ class _Plan:
         return x, off, order
 
     def __del__(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and lib is not None:      # lib is None at interpreter exit
             lib.qr_plan_destroy(self.handle)
             self.handle = None
 

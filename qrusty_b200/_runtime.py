@@ -20,7 +20,7 @@ class DeviceBuffer:
         self.ptr = p.value
 
     def free(self):
-        if getattr(self, "ptr", None):
+        if getattr(self, "ptr", None) and lib is not None:
             lib.qr_set_device(self.device)
             lib.qr_free_device(self.ptr)
             self.ptr = None
@@ -102,7 +102,7 @@ class HostBuffer:
         return np.asarray(self)
 
     def __del__(self):
-        if getattr(self, "ptr", None):
+        if getattr(self, "ptr", None) and PINNED is not None and lib is not None:
             PINNED.give(self.ptr, self.nbytes)
             self.ptr = None
 

@@ -113,6 +113,19 @@ def splitmix64(x):
     return x ^ (x >> np.uint64(31))
 
 
+def lanczos_start_at(indices, seed=25):
+    """The same start vector evaluated at arbitrary row indices."""
+    i = np.asarray(indices, dtype=np.uint64)
+    base = np.uint64(seed) << np.uint64(40)
+    with np.errstate(over="ignore"):
+        a = splitmix64(i * np.uint64(2) + base)
+        b = splitmix64(i * np.uint64(2) + np.uint64(1) + base)
+    scale = 1.0 / float(1 << 53)
+    u1 = (a >> np.uint64(11)).astype(np.float64) * scale * 2.0 - 1.0
+    u2 = (b >> np.uint64(11)).astype(np.float64) * scale * 2.0 - 1.0
+    return u1 + 1j * u2
+
+
 def lanczos_start_vector(lo, hi, seed=25):
     """Elements [lo,hi) of the (un-normalised) start vector of SURVEY.md 8(d) C4:
     v[i] = u1 + i*u2 with u1,u2 uniform(-1,1) from splitmix64(2i + {0,1} + seed*2^40), so any
