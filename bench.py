@@ -305,28 +305,37 @@ def run_b200(args, rank, local_rank, world):
             call("qr_memcpy_h2d", d_vs.ptr + (c0 - hlo) * 16, v.ctypes.data, v.nbytes, None)
         comm = qd.create_comm(dist, device) if dist is not None else None
 
-        def hv_step():
-            if comm is None:
-                call("qr_apply_device", hplan.handle, hlo, hhi, d_vs.ptr, d_y.ptr, stream)
-            else:
-                call("qr_apply_distributed", hplan.handle, comm, d_vs.ptr, d_vf.ptr, d_y.ptr, stream)
-        for _ in range(3):
-            hv_step()
-        call("qr_stream_synchronize", stream)
-        h0, h1 = ev(), ev()
-        barrier()
-        reps = 20
-        call("qr_event_record", h0, stream)
-        for _ in range(reps):
-            hv_step()
-        call("qr_event_record", h1, stream)
-        call("qr_stream_synchronize", stream)
-        hv_ms = max_over_ranks(elapsed(h0, h1) / reps)
+        def time_hv(fn, reps=20):
+            for _ in range(3):
+                fn()
+            call("qr_stream_synchronize", stream)
+            h0, h1 = ev(), ev()
+            barrier()
+            call("qr_event_record", h0, stream)
+            for _ in range(reps):
+                fn()
+            call("qr_event_record", h1, stream)
+            call("qr_stream_synchronize", stream)
+            return max_over_ranks(elapsed(h0, h1) / reps)
+
+        hv_allgather_ms = None
+        if comm is None:
+            hv_ms = time_hv(lambda: call("qr_apply_device", hplan.handle, hlo, hhi, d_vs.ptr, d_y.ptr, stream))
+        else:
+            # baseline: ncclAllGather into a full local copy, then the local apply
+            hv_allgather_ms = time_hv(lambda: call("qr_apply_distributed", hplan.handle, comm, d_vs.ptr, d_vf.ptr, d_y.ptr, stream))
+            # product: peers' shards read in place over NVLink inside the apply kernel
+            ptrs, opened = qd.share_shards(dist, d_vs.ptr)
+            parr = qd.pointer_array(ptrs)
+            hv_ms = time_hv(lambda: call("qr_apply_p2p", hplan.handle, comm, parr, d_y.ptr, stream))
+            barrier()
+            qd.close_shards(opened)
         hv = {"workload": "tfim_5x5_n25", "n_groups": hG, "ms": hv_ms, "gbs_compulsory": 32.0 * hdim / hv_ms / 1e6,
               "gbs_gather_effective": 16.0 * (hG + 1) * hdim / hv_ms / 1e6,
-              "nvlink_gbs_in_per_gpu": (16.0 * hdim * (world - 1) / world / hv_ms / 1e6) if world > 1 else None,
-              "note": ("ncclAllGather(v shards) + local matrix-free apply per rank" if world > 1 else
-                       "local matrix-free apply") + "; compulsory bytes = read v once + write y once (32 B/row)"}
+              "allgather_variant_ms": hv_allgather_ms,
+              "note": ("fused peer-memory apply (qr_apply_p2p): remote v shards read in place over NVLink, two NCCL "
+                       "barriers; allgather_variant_ms = ncclAllGather + local apply" if world > 1 else
+                       "local matrix-free apply, diag(H) cached") + "; compulsory bytes = read v once + write y once (32 B/row)"}
         if comm is not None:
             call("qr_comm_destroy", comm)
         del d_vs, d_vf, d_y, hplan, hop

@@ -150,6 +150,19 @@ QR_API int qr_apply_distributed(qr_plan *plan, qr_comm *comm, const double *d_v_
                          double *d_v_full, double *d_y_shard, void *stream);
 QR_API int qr_allreduce_sum_f64(qr_comm *comm, double *d_buf, size_t count, void *stream);
 
+/* Fused distributed H.v over peer memory: no all-gather and no full copy of v.  Every rank
+ * passes the device pointers of ALL ranks' v shards (its own at [rank]; the others opened from
+ * CUDA IPC handles, below).  The apply kernel reads v[r ^ x_g] straight from the owning GPU
+ * over NVLink: the owner is rank ^ (x_g >> log2(rows per rank)), the same for every row of the
+ * caller, so only groups whose mask touches the sharded (top) row bits cross the link.  Two
+ * stream-ordered NCCL barriers bracket the kernel (shards ready / shards no longer read). */
+QR_API int qr_apply_p2p(qr_plan *plan, qr_comm *comm, const double *const *v_shards,
+                 double *d_y_shard, void *stream);
+#define QR_IPC_HANDLE_BYTES 64
+QR_API int qr_ipc_get_handle(void *d_ptr, void *handle_out /* QR_IPC_HANDLE_BYTES */);
+QR_API int qr_ipc_open_handle(const void *handle, void **d_ptr_out);
+QR_API int qr_ipc_close_handle(void *d_ptr);
+
 /* ---- runtime helpers for hosts without a CUDA binding of their own ---- */
 QR_API int qr_device_count(int *count);
 QR_API int qr_device_name(int device, char *buf, size_t buf_len);

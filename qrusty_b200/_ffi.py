@@ -13,6 +13,7 @@ LIB_PATH = Path(os.environ.get("QRUSTY_CUDA_LIB", _PKG / "lib" / "libqrusty_cuda
 QR_OK, QR_ERR_INVALID, QR_ERR_CUDA, QR_ERR_NCCL, QR_ERR_OOM, QR_ERR_UNSUPPORTED = range(6)
 QR_INDPTR_LOCAL, QR_INDPTR_GLOBAL, QR_FILL_DIRECT = 0, 1, 2
 QR_UNIQUE_ID_BYTES = 128
+QR_IPC_HANDLE_BYTES = 64
 
 
 class QrustyCudaError(Exception):
@@ -66,6 +67,10 @@ SIGNATURES = {
     "qr_comm_destroy": [_vp],
     "qr_apply_distributed": [_vp, _vp, _vp, _vp, _vp, _vp],
     "qr_allreduce_sum_f64": [_vp, _vp, _sz, _vp],
+    "qr_apply_p2p": [_vp, _vp, _vp, _vp, _vp],
+    "qr_ipc_get_handle": [_vp, _vp],
+    "qr_ipc_open_handle": [_vp, C.POINTER(_vp)],
+    "qr_ipc_close_handle": [_vp],
     "qr_device_count": [C.POINTER(_int)],
     "qr_device_name": [_int, C.c_char_p, _sz],
     "qr_set_device": [_int],

@@ -59,14 +59,23 @@ __device__ __forceinline__ void group_values(const PlanDev &p, uint32_t t0, uint
 // permuted, fully coalesced 512-byte segment.  Group descriptors come through shared memory.
 // `diag` (optional): cached values of the mask-0 group for rows [row_lo,row_hi); when given, group 0
 // is not re-evaluated (an eigensolver applies the same operator hundreds of times).
+// Row-sharded form: `peers` (optional) holds one pointer per rank, each pre-offset so that it can
+// be indexed with the GLOBAL row id; the shard that owns v[r ^ x] is rank ^ (x >> shard_bits) for
+// every row of this rank, so the base pointer is a per-group constant (staged beside the
+// descriptor) and remote shards are read in place over NVLink -- the collective is fused into
+// the apply.  Without `peers`, v is the full vector in local memory.
 __global__ void __launch_bounds__(APPLY_THREADS)
 apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
                     const double2 *__restrict__ v, double2 *__restrict__ y,
-                    const double2 *__restrict__ diag)
+                    const double2 *__restrict__ diag,
+                    const double2 *const *__restrict__ peers, uint32_t shard_bits)
 {
     constexpr int E = APPLY_ROWS;
     __shared__ GroupDesc sd[APPLY_BATCH];
+    __shared__ const double2 *sv[APPLY_BATCH];
     const uint64_t cta_base = row_lo + (uint64_t)blockIdx.x * (APPLY_THREADS * E);
+    const uint32_t my_rank = peers ? (uint32_t)(row_lo >> shard_bits) : 0u;
+    const double2 *v_own = peers ? peers[my_rank] : v;
     uint32_t r[E];
     bool live[E];
     double yr[E], yi[E];
@@ -83,26 +92,30 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
 #pragma unroll
         for (int e = 0; e < E; e++) {
             const double2 d = __ldcs(&diag[(uint64_t)r[e] - row_lo]);      // evict-first: keep L2 for v
-            cfma(yr[e], yi[e], d.x, d.y, ld_nc_double2(&v[r[e]]), false);
+            cfma(yr[e], yi[e], d.x, d.y, ld_nc_double2(&v_own[r[e]]), false);
         }
     }
     for (uint32_t g0 = g_first; g0 < G; g0 += APPLY_BATCH) {
         const uint32_t nb = min((uint32_t)APPLY_BATCH, G - g0);
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nb * 2u; i += APPLY_THREADS)
-            reinterpret_cast<uint4 *>(sd)[i] = __ldg(reinterpret_cast<const uint4 *>(p.gdesc + g0) + i);
+        for (uint32_t i = threadIdx.x; i < nb; i += APPLY_THREADS) {
+            const GroupDesc d = p.gdesc[g0 + i];
+            sd[i] = d;
+            sv[i] = peers ? peers[my_rank ^ (d.x >> shard_bits)] : v;
+        }
         __syncthreads();
         for (uint32_t k = 0; k < nb; k++) {
             const GroupDesc d = sd[k];
+            const double2 *vb = sv[k];
             const bool real = (d.flag & 2u) != 0u;
             if (d.flag & 1u) {
 #pragma unroll
-                for (int e = 0; e < E; e++) cfma(yr[e], yi[e], d.cre, d.cim, ld_nc_double2(&v[r[e] ^ d.x]), real);
+                for (int e = 0; e < E; e++) cfma(yr[e], yi[e], d.cre, d.cim, ld_nc_double2(&vb[r[e] ^ d.x]), real);
             } else {
                 double ar[E], ai[E];
                 group_values<E>(p, d.t0, d.t1, r, ar, ai);
 #pragma unroll
-                for (int e = 0; e < E; e++) cfma(yr[e], yi[e], ar[e], ai[e], ld_nc_double2(&v[r[e] ^ d.x]), real);
+                for (int e = 0; e < E; e++) cfma(yr[e], yi[e], ar[e], ai[e], ld_nc_double2(&vb[r[e] ^ d.x]), real);
             }
         }
     }

@@ -82,6 +82,10 @@ struct qr_plan {
 struct qr_comm {
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0, device = 0;
+    // qr_apply_p2p: device table of pre-offset peer shard pointers, barrier scratch
+    const double2 **d_peers = nullptr;
+    std::vector<const void *> host_peers;
+    double *d_scratch = nullptr;
 };
 
 namespace {
@@ -583,7 +587,7 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
     const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
     const uint64_t ctas = (rows + per_cta - 1) / per_cta;
     if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "apply: row window too large for one launch");
-    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag);
+    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, nullptr, 0u);
     QR_LAUNCH_CHECK("apply_direct_kernel");
     return QR_OK;
 }
@@ -779,6 +783,9 @@ extern "C" int qr_comm_create(const void *id, int n_ranks, int rank, int device,
 extern "C" int qr_comm_destroy(qr_comm *cm)
 {
     if (!cm) return QR_OK;
+    cudaSetDevice(cm->device);
+    if (cm->d_peers) cudaFree(cm->d_peers);
+    if (cm->d_scratch) cudaFree(cm->d_scratch);
     if (cm->comm && nccl().ok) nccl().CommDestroy(cm->comm);
     delete cm;
     return QR_OK;
@@ -797,6 +804,72 @@ extern "C" int qr_apply_distributed(qr_plan *pl, qr_comm *cm, const double *d_v_
     QR_NCCL(nccl().AllGather(d_v_shard, d_v_full, 2 * shard, ncclDouble, cm->comm, as_stream(stream)));
     return apply_rows(pl, shard * cm->rank, shard * (cm->rank + 1), reinterpret_cast<const double2 *>(d_v_full),
                       reinterpret_cast<double2 *>(d_y_shard), as_stream(stream));
+}
+
+extern "C" int qr_apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_shards, double *d_y_shard, void *stream)
+{
+    if (!pl || !cm || !v_shards || !d_y_shard) return fail(QR_ERR_INVALID, "qr_apply_p2p: NULL argument");
+    const uint64_t P = (uint64_t)cm->n_ranks;
+    if ((P & (P - 1)) || pl->dim % P) return fail(QR_ERR_INVALID, "qr_apply_p2p: n_ranks must be a power of two dividing dim");
+    const uint64_t shard = pl->dim / P;
+    const uint32_t m = (uint32_t)(63 - __builtin_clzll(shard));
+    for (uint64_t o = 0; o < P; o++)
+        if (!v_shards[o] || ((uintptr_t)v_shards[o] & 15)) return fail(QR_ERR_INVALID, "qr_apply_p2p: bad shard pointer");
+    QR_CUDA(cudaSetDevice(pl->device));
+    cudaStream_t st = as_stream(stream);
+    if (!cm->d_peers) {
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&cm->d_peers), P * sizeof(void *)));
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&cm->d_scratch), 16));
+        QR_CUDA(cudaMemset(cm->d_scratch, 0, 16));
+    }
+    bool same = cm->host_peers.size() == P;
+    for (uint64_t o = 0; same && o < P; o++) same = cm->host_peers[o] == v_shards[o];
+    if (!same) {
+        cm->host_peers.assign(v_shards, v_shards + P);
+        std::vector<const double2 *> adj(P);                      // indexable with the GLOBAL row id
+        for (uint64_t o = 0; o < P; o++) adj[o] = reinterpret_cast<const double2 *>(v_shards[o]) - (o << m);
+        QR_CUDA(cudaStreamSynchronize(st));
+        QR_CUDA(cudaMemcpy(cm->d_peers, adj.data(), P * sizeof(void *), cudaMemcpyHostToDevice));
+    }
+    const uint64_t row_lo = shard * cm->rank, row_hi = row_lo + shard;
+    const double2 *diag = nullptr;
+    int rc = ensure_diag_cache(pl, row_lo, row_hi, st, &diag);
+    if (rc != QR_OK) return rc;
+    // every rank's shard is complete before anyone reads it ...
+    QR_NCCL(nccl().AllReduce(cm->d_scratch, cm->d_scratch, 1, ncclDouble, ncclSum, cm->comm, st));
+    const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
+    const uint64_t ctas = (shard + per_cta - 1) / per_cta;
+    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(
+        pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag,
+        cm->d_peers, m);
+    QR_LAUNCH_CHECK("apply_direct_kernel(p2p)");
+    // ... and nobody overwrites a shard while a peer may still be reading it
+    QR_NCCL(nccl().AllReduce(cm->d_scratch, cm->d_scratch, 1, ncclDouble, ncclSum, cm->comm, st));
+    return QR_OK;
+}
+
+extern "C" int qr_ipc_get_handle(void *d_ptr, void *handle_out)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == QR_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    if (!d_ptr || !handle_out) return fail(QR_ERR_INVALID, "qr_ipc_get_handle: NULL argument");
+    cudaIpcMemHandle_t h;
+    QR_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle_out, &h, sizeof(h));
+    return QR_OK;
+}
+extern "C" int qr_ipc_open_handle(const void *handle, void **d_ptr_out)
+{
+    if (!handle || !d_ptr_out) return fail(QR_ERR_INVALID, "qr_ipc_open_handle: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    *d_ptr_out = nullptr;
+    QR_CUDA(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return QR_OK;
+}
+extern "C" int qr_ipc_close_handle(void *d_ptr)
+{
+    if (d_ptr) QR_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return QR_OK;
 }
 
 extern "C" int qr_allreduce_sum_f64(qr_comm *cm, double *d_buf, size_t count, void *stream)

@@ -50,3 +50,34 @@ def create_comm(dist, device):
     comm = C.c_void_p()
     _ffi.call("qr_comm_create", uid, dist.get_world_size(), dist.get_rank(), device, C.byref(comm))
     return comm
+
+
+def share_shards(dist, local_ptr):
+    """CUDA-IPC exchange of one device buffer per rank (e.g. the v shards of a row-sharded H.v):
+    returns (pointers[world], opened) where pointers[rank] is local_ptr and the others are peer
+    mappings usable in kernels; pass `opened` to close_shards when done."""
+    from . import _ffi
+    buf = C.create_string_buffer(_ffi.QR_IPC_HANDLE_BYTES)
+    _ffi.call("qr_ipc_get_handle", local_ptr, buf)
+    handles = [None] * dist.get_world_size()
+    dist.all_gather_object(handles, buf.raw)
+    ptrs, opened = [], []
+    for r, h in enumerate(handles):
+        if r == dist.get_rank():
+            ptrs.append(local_ptr)
+        else:
+            p = C.c_void_p()
+            _ffi.call("qr_ipc_open_handle", h, C.byref(p))
+            ptrs.append(p.value)
+            opened.append(p.value)
+    return ptrs, opened
+
+
+def close_shards(opened):
+    from . import _ffi
+    for p in opened:
+        _ffi.call("qr_ipc_close_handle", p)
+
+
+def pointer_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*ptrs)

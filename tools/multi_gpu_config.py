@@ -31,7 +31,9 @@ def barrier():
 def maxr(x):
     return qd.max_over_ranks(dist, x, "cuda") if world > 1 else x
 
-labels, coeffs = H.CONFIGS[cfg][1]()
+sys.path.insert(0, str(ROOT / "tools"))
+from fill_sweep import get_workload
+labels, coeffs = get_workload(cfg)
 n, params = O.make_params(labels, coeffs)
 op = Q.SparsePauliOp([Q.Pauli(l) for l in labels], coeffs)
 plan = op.plan(local)
@@ -44,7 +46,7 @@ def ev():
 def elapsed(a, b):
     ms = C.c_float(); call("qr_event_elapsed_ms", a, b, C.byref(ms)); return ms.value
 
-out = {"config": cfg, "workload": H.CONFIGS[cfg][0], "n_gpus": world, "n_qubits": n, "n_terms": len(labels), "n_groups": G,
+out = {"config": cfg, "workload": H.CONFIGS[cfg][0] if cfg in H.CONFIGS else cfg, "n_gpus": world, "n_qubits": n, "n_terms": len(labels), "n_groups": G,
        "nnz": G * dim, "rows_per_gpu": rows, "csr_bytes_per_gpu": rows * G * 24 + (rows + 1) * 8}
 # ---- build the shard in HBM ----
 d_ip, d_ix, d_dt = DeviceBuffer((rows + 1) * 8, local), DeviceBuffer(rows * G * 8, local), DeviceBuffer(rows * G * 16, local)
@@ -62,7 +64,7 @@ out.update(build_ms=t_build, build_nnz_per_s=G * dim / (t_build * 1e-3),
            build_GBps_per_gpu=(rows * G * 24 + (rows + 1) * 8) / t_build / 1e6)
 # verify 1024 sampled rows of this shard against the oracle
 rng = np.random.default_rng(100 + rank)
-sample = np.unique(np.r_[lo, hi - 1, rng.integers(lo, hi, 1022)])
+sample = np.unique(np.r_[lo, hi - 1, rng.integers(lo, hi, min(1022, rows))])
 bad = 0
 row_ix, row_dt, ipv = np.empty(G, np.uint64), np.empty(G, np.complex128), np.empty(2, np.uint64)
 for r in sample:
@@ -92,6 +94,24 @@ call("qr_event_record", e1, st); call("qr_stream_synchronize", st)
 t_hv = maxr(elapsed(e0, e1) / reps)
 out.update(hv_ms=t_hv, hv_GBps_compulsory=32.0 * dim / t_hv / 1e6,
            hv_nvlink_GBps_in_per_gpu=(16.0 * dim * (world - 1) / world / t_hv / 1e6) if world > 1 else None)
+# fused variant: peers' shards read in place over NVLink (no all-gather, no v_full)
+if comm is not None:
+    ptrs, opened = qd.share_shards(dist, d_vs.ptr)
+    parr = qd.pointer_array(ptrs)
+    d_y2 = DeviceBuffer(rows * 16, local)
+    for _ in range(3): call("qr_apply_p2p", plan.handle, comm, parr, d_y2.ptr, st)
+    call("qr_stream_synchronize", st)
+    barrier()
+    call("qr_event_record", e0, st)
+    for _ in range(reps): call("qr_apply_p2p", plan.handle, comm, parr, d_y2.ptr, st)
+    call("qr_event_record", e1, st); call("qr_stream_synchronize", st)
+    t_p2p = maxr(elapsed(e0, e1) / reps)
+    ya, yb = np.empty(min(rows, 1 << 16), np.complex128), np.empty(min(rows, 1 << 16), np.complex128)
+    d_y.download(ya); d_y2.download(yb)
+    out.update(hv_p2p_ms=t_p2p, hv_p2p_GBps_compulsory=32.0 * dim / t_p2p / 1e6,
+               hv_p2p_equals_allgather=bool(maxr(0.0 if np.array_equal(ya.view(np.uint64), yb.view(np.uint64)) else 1.0) == 0.0))
+    barrier()
+    qd.close_shards(opened)
 ys = rng.integers(lo, hi, 4096)
 yv = np.empty(1, np.complex128); worst = 0.0
 absH = float(np.abs(params["re"] + 1j * params["im"]).sum())
