@@ -129,6 +129,18 @@ QR_API int qr_diagonal_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi, d
 QR_API int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const uint64_t *d_indices,
                    const double *d_data, const double *d_v, double *d_y, void *stream);
 
+/* ---- zero elimination on a device-resident shard with uniform row length G (every plan-built
+ * shard): util::csmatrix_nz / csmatrix_eliminate_zeroes (qrusty/src/util.rs:144-171; Python
+ * SpMat.count_zeros / eliminate_zeros, pyqrusty/src/lib.rs:170-183).  An entry is kept iff
+ * hypot(re, im) > tol.  qr_count_kept_device writes the compacted CSR's indptr (local, starting
+ * at 0: per-row counts + prefix scan) and returns its nnz (synchronises); qr_compact_rows_device
+ * then writes indices/data of the kept entries, row-major order preserved. */
+QR_API int qr_count_kept_device(uint64_t n_rows, uint64_t n_groups, const double *d_data, double tol,
+                         uint64_t *d_indptr_out, uint64_t *nnz_out, void *stream);
+QR_API int qr_compact_rows_device(uint64_t n_rows, uint64_t n_groups, const uint64_t *d_indices,
+                           const double *d_data, double tol, const uint64_t *d_indptr,
+                           uint64_t *d_indices_out, double *d_data_out, void *stream);
+
 /* Lanczos/Davidson vector kernels (accel.rs:374-393): z = a*x + b*y, a*x + y, a*x. */
 QR_API int qr_axpby_device(uint64_t n, const double a[2], const double *d_x, const double b[2],
                     const double *d_y, double *d_z, void *stream);

@@ -184,3 +184,18 @@ def ax(a, x):
     x = _cv(x); z = np.empty_like(x); a = complex(a)
     lib().oracle_ax(a.real, a.imag, _p(x), _p(z), len(x))
     return z
+
+
+def eliminate_zeros(indptr, indices, data, tolerance=1e-7):
+    """util::csmatrix_eliminate_zeroes (qrusty/src/util.rs:154-171): keep entries with
+    norm() > tolerance (norm = hypot), row-major order preserved; -> (indptr, indices, data)."""
+    keep = np.hypot(data.real, data.imag) > tolerance
+    rows = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr.astype(np.int64)))
+    counts = np.bincount(rows[keep], minlength=len(indptr) - 1).astype(np.uint64)
+    new_indptr = np.concatenate([[np.uint64(0)], np.cumsum(counts, dtype=np.uint64)])
+    return new_indptr, indices[keep].copy(), data[keep].copy()
+
+
+def count_zeros(data, tolerance=1e-7):
+    """util::csmatrix_nz (util.rs:144-152)."""
+    return int(np.count_nonzero(np.hypot(data.real, data.imag) <= tolerance))

@@ -11,8 +11,7 @@ csrc/ through the C ABI of include/qrusty_cuda.h; there is no CPU implementation
 here, so the reference's CPU-strategy mode strings ("", "Rowwise", "RowwiseUnsafeChunked/n",
 ...) are accepted and executed by the same CUDA build -- they all denote the same matrix.
 
-Out of scope: MatrixMarket I/O, SpMat +/-/scale, a_spmat_p_b_spmat,
-count_zeros/eliminate_zeros, precond.
+Out of scope: MatrixMarket I/O, SpMat +/-/scale, a_spmat_p_b_spmat, precond.
 """
 import ctypes as C
 import re
@@ -372,6 +371,55 @@ class SpMat:
             d.download(out[s.off:s.off + s.hi - s.lo])
         return out
 
+    # -- zero elimination (pyqrusty/src/lib.rs:170-183 -> util.rs:144-171) ------------------------
+    def _kept(self, tolerance, compact):
+        """Per shard: count + scan (and optionally compact) on the device.  -> (kept, new shards)."""
+        shards = self.to_device()._live("cannot %s zeroes of an exported sparse matrix"
+                                        % ("eliminate" if compact else "count"))
+        kept_total, out = 0, []
+        for s in shards:
+            if s.plan is None or getattr(s, "compacted", False):
+                raise Exception("zero elimination is implemented for matrices built from a SparsePauliOp")
+            rows, G = s.hi - s.lo, s.plan.n_groups
+            call("qr_set_device", s.device)
+            indptr = DeviceBuffer((rows + 1) * 8, s.device)
+            kept = C.c_uint64()
+            call("qr_count_kept_device", rows, G, s.data.ptr, float(tolerance), indptr.ptr, C.byref(kept), None)
+            kept_total += kept.value
+            if compact:
+                indices = DeviceBuffer(max(kept.value * 8, 16), s.device)
+                data = DeviceBuffer(max(kept.value * 16, 16), s.device)
+                call("qr_compact_rows_device", rows, G, s.indices.ptr, s.data.ptr, float(tolerance), indptr.ptr,
+                     indices.ptr, data.ptr, None)
+                c = _Shard(s.plan, s.lo, s.hi, indptr, indices, data, off=s.off, local=True)
+                c.nnz, c.compacted = kept.value, True
+                out.append(c)
+        return kept_total, out
+
+    def count_zeros(self, tolerance=1e-7):
+        """Entries with norm <= tolerance (util.rs:144-152)."""
+        shards = self._live("cannot count zeroes of an exported sparse matrix")
+        if all(getattr(s, "compacted", False) for s in shards):
+            return self._count_zeros_compacted(tolerance)
+        kept, _ = self._kept(tolerance, compact=False)
+        return self.nnz() - kept
+
+    def _count_zeros_compacted(self, tolerance):
+        # an already compacted matrix: count on the stored values (generic sparse algebra, off the path)
+        n = 0
+        for s in self._shards:
+            d = s.data.download(np.empty(s.nnz, np.complex128)) if s.nnz else np.empty(0, np.complex128)
+            n += int(np.count_nonzero(np.hypot(d.real, d.imag) <= tolerance))
+        return n
+
+    def eliminate_zeros(self, tolerance=1e-7):
+        """New SpMat holding only entries with norm > tolerance (util.rs:154-171)."""
+        _, shards = self._kept(tolerance, compact=True)
+        for s in shards:
+            call("qr_set_device", s.device)
+            synchronize()
+        return SpMat._from_shards(self._shape, shards)
+
     def to_device(self):
         """Materialise every shard in HBM (needed for SpMV on the stored matrix); returns self."""
         shards = self._live("cannot use an exported sparse matrix")
@@ -413,6 +461,12 @@ class SpMat:
             call("qr_set_device", dev)
             call("qr_stream_synchronize", st)
             call("qr_stream_destroy", st)
+        base = 0
+        for s in shards:                             # compacted shards carry shard-local indptr
+            if getattr(s, "compacted", False) and base:
+                indptr[s.off + 1:s.off + (s.hi - s.lo) + 1] += np.uint64(base)
+                indptr[s.off] = base                 # overwritten by this shard's local 0
+            base += s.nnz
         shape = self._shape
         self._shards = None
         return shape, data, indices, indptr

@@ -17,6 +17,7 @@
 #include "../../include/qrusty_cuda.h"
 #include "apply.cuh"
 #include "canonicalise.cuh"
+#include "compact.cuh"
 #include "fill.cuh"
 #include "plan.cuh"
 
@@ -643,6 +644,55 @@ extern "C" int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const u
         n_rows, d_indptr, d_indices, reinterpret_cast<const double2 *>(d_data),
         reinterpret_cast<const double2 *>(d_v), reinterpret_cast<double2 *>(d_y));
     QR_LAUNCH_CHECK("spmv_csr_kernel");
+    return QR_OK;
+}
+
+// =====================================================================================
+// K2: count + scan + compaction (eliminate_zeros)
+// =====================================================================================
+extern "C" int qr_count_kept_device(uint64_t n_rows, uint64_t G, const double *d_data, double tol,
+                                    uint64_t *d_indptr_out, uint64_t *nnz_out, void *stream)
+{
+    if (!d_data || !d_indptr_out || !nnz_out) return fail(QR_ERR_INVALID, "qr_count_kept_device: NULL argument");
+    if (n_rows == 0 || G == 0 || G > 0xffffffffull) return fail(QR_ERR_INVALID, "qr_count_kept_device: bad shape");
+    cudaStream_t st = as_stream(stream);
+    // rows per CTA: about 8192 entries, at most 2048 rows (8 KB of counters)
+    uint32_t R = (uint32_t)std::min<uint64_t>(2048, std::max<uint64_t>(1, 8192 / G));
+    const uint64_t ctas = (n_rows + R - 1) / R;
+    if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "qr_count_kept_device: shard too large for one launch");
+    qr::count_kept_kernel<<<(unsigned)ctas, qr::K2_THREADS, R * 4, st>>>(
+        n_rows, (uint32_t)G, R, reinterpret_cast<const double2 *>(d_data), tol, d_indptr_out);
+    QR_LAUNCH_CHECK("count_kept_kernel");
+    const uint64_t n_tiles = (n_rows + qr::SCAN_TILE - 1) / qr::SCAN_TILE;
+    uint64_t *d_tiles = nullptr;
+    QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_tiles), (n_tiles + 1) * 8));
+    qr::scan_tile_sums_kernel<<<(unsigned)n_tiles, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr_out, d_tiles);
+    g_launches.fetch_add(1);
+    qr::scan_tile_offsets_kernel<<<1, qr::K2_THREADS, 0, st>>>(n_tiles, d_tiles, d_tiles + n_tiles);
+    g_launches.fetch_add(1);
+    qr::scan_apply_kernel<<<(unsigned)n_tiles, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr_out, d_tiles);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nnz_out, d_tiles + n_tiles, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_tiles);
+    if (e != cudaSuccess) return fail(QR_ERR_CUDA, std::string("qr_count_kept_device: ") + cudaGetErrorString(e));
+    return QR_OK;
+}
+
+extern "C" int qr_compact_rows_device(uint64_t n_rows, uint64_t G, const uint64_t *d_indices, const double *d_data,
+                                      double tol, const uint64_t *d_indptr, uint64_t *d_indices_out,
+                                      double *d_data_out, void *stream)
+{
+    if (!d_indices || !d_data || !d_indptr || !d_indices_out || !d_data_out)
+        return fail(QR_ERR_INVALID, "qr_compact_rows_device: NULL argument");
+    if (n_rows == 0 || G == 0 || G > 0xffffffffull) return fail(QR_ERR_INVALID, "qr_compact_rows_device: bad shape");
+    const uint64_t per_cta = qr::K2_THREADS / 32;
+    const uint64_t ctas = std::min<uint64_t>((n_rows + per_cta - 1) / per_cta, 148ull * 64);
+    qr::compact_rows_kernel<<<(unsigned)ctas, qr::K2_THREADS, 0, as_stream(stream)>>>(
+        n_rows, (uint32_t)G, d_indices, reinterpret_cast<const double2 *>(d_data), tol, d_indptr, d_indices_out,
+        reinterpret_cast<double2 *>(d_data_out));
+    QR_LAUNCH_CHECK("compact_rows_kernel");
     return QR_OK;
 }
 

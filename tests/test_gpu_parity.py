@@ -411,6 +411,46 @@ def test_dotc():
     assert abs(got - np.vdot(x, y)) <= 1e-10 * np.abs(x).sum()
 
 
+# ---- K2: count + scan + compaction (test_it.py:141-148, util.rs:144-171) -----------------------
+@pytest.mark.parametrize("name", ["H2", "H4", "H6", "C1", "random_n10", "xxz_n10"])
+def test_eliminate_zeros(fixtures, name):
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    for tol in (1e-7, 0.0, 0.05):
+        want = O.eliminate_zeros(*ref, tolerance=tol)
+        m = make_op(labels, coeffs).to_matrix()
+        assert m.count_zeros(tol) == O.count_zeros(ref[2], tol)
+        m2 = m.eliminate_zeros(tol)
+        assert m2.nnz() == len(want[2]) and m2.shape() == (1 << n, 1 << n)
+        assert m2.count_zeros(tol) == 0
+        v = H.lanczos_start_vector(0, 1 << n, seed=3)
+        y2 = Q.spmat_dot_densevec(m2, v)
+        assert np.array_equal(u64(y2), u64(O.spmv(*want, v)))
+        shape, data, indices, indptr = m2.export()
+        assert_same((indptr, indices, data), want, f"{name} tol={tol}")
+        assert m.nnz() == len(ref[2])                      # the original is untouched
+
+
+def test_eliminate_zeros_tiny_values():
+    """test_it.py:141-148: a matrix of 1e-8 entries has 2 'zeros'; eliminating them leaves nothing."""
+    m = Q.SparsePauliOp([Q.Pauli("I")], [1e-8 + 0j]).to_matrix()
+    assert m.count_zeros() == 2
+    m2 = m.eliminate_zeros()
+    assert m2.count_zeros() == 0 and m2.nnz() == 0
+    shape, data, indices, indptr = m2.export()
+    assert len(data) == 0 and np.array_equal(indptr, [0, 0, 0])
+
+
+def test_eliminate_zeros_C2_full():
+    labels, coeffs = H.xxz_chain(20, 1.0, 0.7)
+    n, params = O.make_params(labels, coeffs)
+    want = O.eliminate_zeros(*O.build_csr(params, n))
+    shape, data, indices, indptr = make_op(labels, coeffs).to_matrix().eliminate_zeros().export()
+    assert_same((indptr, indices, data), want, "C2 compacted")
+    assert len(data) < 22020096 * 0.6
+
+
 def test_multi_gpu_single_process(fixtures):
     if _ffi.device_count() < 2:
         pytest.skip("needs 2 GPUs")
