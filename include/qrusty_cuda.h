@@ -62,7 +62,7 @@ typedef struct qr_plan_info_t {
     int32_t  n_qubits;
     int32_t  device;
     uint64_t dim;        /* 2^n_qubits rows and columns                                   */
-    uint64_t n_terms;    /* T                                                             */
+    uint64_t n_terms;    /* T as supplied (after QR_PLAN_MERGE_DUPLICATES: see qr_plan_groups)   */
     uint64_t n_groups;   /* G = distinct X-masks = stored entries per row                 */
     uint64_t nnz;        /* G * dim: explicit zeros are kept, as accel.rs:171-210 does    */
 } qr_plan_info_t;
@@ -72,6 +72,10 @@ typedef struct qr_plan_info_t {
  * canonicalisation kernel (stable radix sort by X-mask, head-flag scan -> groups,
  * rank tables) on `device`, and waits for it.  n_qubits in [1, 32], n_terms >= 1
  * (SparsePauliOp::new, lib.rs:354-376), every x and z < 2^n_qubits. */
+#define QR_PLAN_MERGE_DUPLICATES 1u  /* merge terms with identical (x, z): segmented reduce after a
+                                      (x, z)-keyed sort.  Changes the summation order inside a
+                                      group: data then matches the reference to 1e-12, not bit
+                                      for bit.  Off by default. */
 QR_API int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms, int device,
                    uint32_t flags, qr_plan **out);
 QR_API int qr_plan_destroy(qr_plan *plan);
@@ -83,6 +87,10 @@ QR_API int qr_plan_info(const qr_plan *plan, qr_plan_info_t *info);
  * inside a group).  Any pointer may be NULL.  Synchronous. */
 QR_API int qr_plan_groups(const qr_plan *plan, uint64_t *xmask, uint32_t *group_offsets,
                    uint32_t *term_order);
+/* Number of terms the kernels iterate over: n_terms, or fewer after QR_PLAN_MERGE_DUPLICATES
+ * (group_offsets then index the merged list and term_order[i] is the first original index of
+ * merged term i, for i < the returned count). */
+QR_API int qr_plan_canonical_terms(const qr_plan *plan, uint64_t *count);
 
 /* Re-runs the canonicalisation kernel from the raw term table already in HBM,
  * asynchronously on `stream` (a cudaStream_t, NULL = default stream).  Lets a

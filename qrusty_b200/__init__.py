@@ -111,15 +111,18 @@ def _parse_mode(mode):
 class _Plan:
     """Owns a qr_plan handle."""
 
-    def __init__(self, n_qubits, terms, device):
+    def __init__(self, n_qubits, terms, device, flags=0):
         self.terms = np.ascontiguousarray(terms, dtype=TERM_DTYPE)
         h = C.c_void_p()
-        call("qr_plan_create", n_qubits, self.terms.ctypes.data, len(self.terms), device, 0, C.byref(h))
+        call("qr_plan_create", n_qubits, self.terms.ctypes.data, len(self.terms), device, flags, C.byref(h))
         self.handle = h.value
         info = _ffi.PlanInfo()
         call("qr_plan_info", self.handle, C.byref(info))
         self.n_qubits, self.device = info.n_qubits, info.device
         self.dim, self.n_terms, self.n_groups, self.nnz = info.dim, info.n_terms, info.n_groups, info.nnz
+        c = C.c_uint64()
+        call("qr_plan_canonical_terms", self.handle, C.byref(c))
+        self.n_terms_canonical = c.value
 
     def groups(self):
         x = np.zeros(self.n_groups, np.uint64)
@@ -209,12 +212,15 @@ class SparsePauliOp:
             self._terms = t
         return self._terms
 
+    merge_duplicates = False     # opt-in: merge identical (x, z) terms on the GPU (data to 1e-12, not bit-exact)
+
     def plan(self, device=0):
         if device not in self._plans:
             n = self.num_qubits()
             if n > 32:
                 raise QrustyCudaError(_ffi.QR_ERR_UNSUPPORTED, "n_qubits > 32 is not supported")
-            self._plans[device] = _Plan(n, self.terms(), device)
+            flags = _ffi.QR_PLAN_MERGE_DUPLICATES if self.merge_duplicates else 0
+            self._plans[device] = _Plan(n, self.terms(), device, flags)
         return self._plans[device]
 
     # -- matrix build ----------------------------------------------------------------

@@ -12,6 +12,7 @@ LIB_PATH = Path(os.environ.get("QRUSTY_CUDA_LIB", _PKG / "lib" / "libqrusty_cuda
 
 QR_OK, QR_ERR_INVALID, QR_ERR_CUDA, QR_ERR_NCCL, QR_ERR_OOM, QR_ERR_UNSUPPORTED = range(6)
 QR_INDPTR_LOCAL, QR_INDPTR_GLOBAL, QR_FILL_DIRECT = 0, 1, 2
+QR_PLAN_MERGE_DUPLICATES = 1
 QR_UNIQUE_ID_BYTES = 128
 QR_IPC_HANDLE_BYTES = 64
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     "qr_plan_destroy": [_vp],
     "qr_plan_info": [_vp, C.POINTER(PlanInfo)],
     "qr_plan_groups": [_vp, _vp, _vp, _vp],
+    "qr_plan_canonical_terms": [_vp, C.POINTER(_u64)],
     "qr_plan_canonicalise_async": [_vp, _vp],
     "qr_build_rows_device": [_vp, _u64, _u64, _vp, _vp, _vp, _u32, _vp],
     "qr_build_host": [_vp, _u64, _u64, _vp, _vp, _vp, _u32],

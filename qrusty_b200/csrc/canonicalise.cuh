@@ -8,10 +8,12 @@
 //
 // One CTA of 512 threads; T is at most tens of thousands (a Hamiltonian's term
 // list), the output of this kernel is what 2^n rows then share.
-//   1. stable LSD radix sort of (x, original index), 8-bit digits, ceil(n/8) passes:
+//   1. stable LSD radix sort of (x, original index), 8-bit digits, ceil(n/8) passes
+//      (preceded by a z-keyed sort when duplicate merging is requested):
 //      histogram (shared atomics) -> bin scan -> per-tile stable ranking with
 //      __match_any_sync + per-warp digit counts -> scatter.
 //   2. head flags + CTA scan (scan.cuh) -> group ids, gx[], goff[], G.
+//   2b. (opt-in) runs of identical (x, z) merged by a segmented reduce.
 //   3. rank tables cnt[g][b] by two binary searches on the sorted masks, lr5[g][j].
 #pragma once
 #include "plan.cuh"
@@ -35,38 +37,29 @@ __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *a, uint32_t 
     return lo;
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
+// One stable LSD radix sort of (key, payload) over `bits` key bits; returns with the sorted
+// arrays in (kin, iin) (the pointers are swapped per pass).  All threads of the CTA call it.
+struct RadixSmem {
+    uint32_t hist[256];                  // digit histogram, then running bin base
+    uint16_t wcount[K1_WARPS][256];      // per-warp digit counts of the current tile
+    uint32_t woffset[K1_WARPS][256];     // per-warp digit start positions
+    uint32_t scan_scratch[33];
+};
+
+__device__ __forceinline__ void radix_sort_cta(RadixSmem &sm, uint32_t T, int bits, uint32_t *&kin, uint32_t *&kout,
+                                               uint32_t *&iin, uint32_t *&iout)
 {
-    __shared__ uint32_t hist[256];                  // digit histogram, then running bin base
-    __shared__ uint16_t wcount[K1_WARPS][256];      // per-warp digit counts of the current tile
-    __shared__ uint32_t woffset[K1_WARPS][256];     // per-warp digit start positions
-    __shared__ uint32_t scan_scratch[33];
-    __shared__ uint32_t max_group, n_const;
-
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t T = p.n_terms;
-
-    // ---- 0. keys = X-masks, payload = original index ---------------------------------
-    for (uint32_t i = tid; i < T; i += K1_THREADS) { p.key_a[i] = (uint32_t)p.raw[i].x; p.idx_a[i] = i; }
-    for (uint32_t i = tid; i < K1_WARPS * 256; i += K1_THREADS) (&wcount[0][0])[i] = 0;
-    if (tid == 0) { max_group = 0; n_const = 0; }
-    __syncthreads();
-
-    // ---- 1. stable LSD radix sort -----------------------------------------------------
-    uint32_t *kin = p.key_a, *kout = p.key_b, *iin = p.idx_a, *iout = p.idx_b;
-    const int passes = (p.n_qubits + 7) / 8;
-    for (int pass = 0; pass < passes; pass++) {
-        const int shift = 8 * pass;
-        if (tid < 256) hist[tid] = 0;
+    for (int shift = 0; shift < bits; shift += 8) {
+        if (tid < 256) sm.hist[tid] = 0;
         __syncthreads();
-        for (uint32_t i = tid; i < T; i += K1_THREADS) atomicAdd(&hist[(kin[i] >> shift) & 255u], 1u);
+        for (uint32_t i = tid; i < T; i += K1_THREADS) atomicAdd(&sm.hist[(kin[i] >> shift) & 255u], 1u);
         __syncthreads();
         uint32_t total;
-        uint32_t h = tid < 256 ? hist[tid] : 0u;
-        uint32_t excl = block_exclusive_scan(h, scan_scratch, &total);
-        if (tid < 256) hist[tid] = excl;            // hist[d] = next free output position of digit d
+        const uint32_t h = tid < 256 ? sm.hist[tid] : 0u;
+        const uint32_t excl = block_exclusive_scan(h, sm.scan_scratch, &total);
+        if (tid < 256) sm.hist[tid] = excl;         // hist[d] = next free output position of digit d
         __syncthreads();
-
         for (uint32_t tile = 0; tile < T; tile += K1_THREADS) {
             const uint32_t i = tile + tid;
             const bool valid = i < T;
@@ -74,41 +67,71 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
             if (valid) { key = kin[i]; idx = iin[i]; d = (key >> shift) & 255u; }
             const unsigned peers = __match_any_sync(FULL_MASK, d);
             const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-            if (valid && rank_in_warp == 0) wcount[warp][d] = (uint16_t)__popc(peers);
+            if (valid && rank_in_warp == 0) sm.wcount[warp][d] = (uint16_t)__popc(peers);
             __syncthreads();
             if (tid < 256) {                        // digit tid: prefix over warps, in element order
-                uint32_t run = hist[tid];
+                uint32_t run = sm.hist[tid];
 #pragma unroll 4
                 for (int w = 0; w < K1_WARPS; w++) {
-                    uint32_t c = wcount[w][tid];
-                    wcount[w][tid] = 0;
-                    woffset[w][tid] = run;
+                    const uint32_t c = sm.wcount[w][tid];
+                    sm.wcount[w][tid] = 0;
+                    sm.woffset[w][tid] = run;
                     run += c;
                 }
-                hist[tid] = run;
+                sm.hist[tid] = run;
             }
             __syncthreads();
-            if (valid) { uint32_t pos = woffset[warp][d] + rank_in_warp; kout[pos] = key; iout[pos] = idx; }
+            if (valid) { const uint32_t pos = sm.woffset[warp][d] + rank_in_warp; kout[pos] = key; iout[pos] = idx; }
             __syncthreads();
         }
         uint32_t *t = kin; kin = kout; kout = t;
         t = iin; iin = iout; iout = t;
     }
-    // sorted (key, idx) now in (kin, iin)
+}
 
-    // ---- 2. head flags -> groups; gather the sorted term table ------------------------
+// merge_dups = 0: terms keep their original order inside a group (bit-exact data).
+// merge_dups = 1: terms are ordered by (x, z) -- a z-keyed sort followed by the stable x-keyed
+// sort -- and every run of identical (x, z) is replaced by one term whose coefficient is the
+// run's sum in original order (segmented reduce).  This changes the summation order inside a
+// group, so data then agrees with the reference to rounding (1e-12), not bit for bit.
+__global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, uint32_t merge_dups)
+{
+    __shared__ RadixSmem sm;
+    __shared__ uint32_t max_group, n_const;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t T = p.n_terms;
+
+    // ---- 0. payload = original index ------------------------------------------------------
+    for (uint32_t i = tid; i < T; i += K1_THREADS) p.idx_a[i] = i;
+    for (uint32_t i = tid; i < K1_WARPS * 256; i += K1_THREADS) (&sm.wcount[0][0])[i] = 0;
+    if (tid == 0) { max_group = 0; n_const = 0; }
+    __syncthreads();
+
+    // ---- 1. stable LSD radix sort(s) --------------------------------------------------------
+    uint32_t *kin = p.key_a, *kout = p.key_b, *iin = p.idx_a, *iout = p.idx_b;
+    if (merge_dups) {
+        for (uint32_t i = tid; i < T; i += K1_THREADS) kin[i] = (uint32_t)p.raw[i].z;
+        __syncthreads();
+        radix_sort_cta(sm, T, p.n_qubits, kin, kout, iin, iout);
+    }
+    for (uint32_t i = tid; i < T; i += K1_THREADS) kin[i] = (uint32_t)p.raw[iin[i]].x;
+    __syncthreads();
+    radix_sort_cta(sm, T, p.n_qubits, kin, kout, iin, iout);
+    // sorted (x, idx) now in (kin, iin)
+
+    // ---- 2. head flags -> groups; gather the sorted term table ------------------------------
     uint32_t carry = 0;
     for (uint32_t tile = 0; tile < T; tile += K1_THREADS) {
         const uint32_t i = tile + tid;
         const bool valid = i < T;
-        uint32_t key = valid ? kin[i] : 0u;
-        uint32_t head = (valid && (i == 0 || kin[i - 1] != key)) ? 1u : 0u;
+        const uint32_t key = valid ? kin[i] : 0u;
+        const uint32_t head = (valid && (i == 0 || kin[i - 1] != key)) ? 1u : 0u;
         uint32_t total;
-        uint32_t excl = block_exclusive_scan(head, scan_scratch, &total);
+        const uint32_t excl = block_exclusive_scan(head, sm.scan_scratch, &total);
         if (valid) {
-            uint32_t gid = carry + excl;            // index of the group that starts at or before i ...
-            if (head) { p.gx[gid] = key; p.goff[gid] = i; }
-            uint32_t src = iin[i];
+            if (head) { p.gx[carry + excl] = key; p.goff[carry + excl] = i; }
+            const uint32_t src = iin[i];
             p.perm[i] = src;
             p.tz[i] = (uint32_t)p.raw[src].z;
             p.tc[i] = make_double2(p.raw[src].re, p.raw[src].im);
@@ -119,7 +142,50 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
     if (tid == 0) { p.goff[G] = T; p.meta[0] = G; }
     __syncthreads();
 
-    // ---- 3. rank tables ---------------------------------------------------------------
+    // ---- 2b. optional: merge runs of identical (x, z) (segmented reduce) ----------------------
+    uint32_t T2 = T;
+    if (merge_dups) {
+        // kout/iout are free now: kout[i] = compact position of term i, iout[] = merged perm
+        uint32_t c2 = 0;
+        for (uint32_t tile = 0; tile < T; tile += K1_THREADS) {
+            const uint32_t i = tile + tid;
+            const bool valid = i < T;
+            const uint32_t head = (valid && (i == 0 || kin[i - 1] != kin[i] || p.tz[i - 1] != p.tz[i])) ? 1u : 0u;
+            uint32_t total;
+            const uint32_t excl = block_exclusive_scan(head, sm.scan_scratch, &total);
+            if (valid) kout[i] = head ? (c2 + excl) : 0xffffffffu;
+            c2 += total;
+        }
+        T2 = c2;
+        __syncthreads();
+        // run heads sum their run in original order and write the compact term; double2 staging
+        // goes through p.gconst (G <= T entries are not enough) -> reuse raw-order scratch in cnt
+        double2 *tc2 = reinterpret_cast<double2 *>(p.cnt);         // >= T*128 B, free until step 3
+        uint32_t *tz2 = p.lr5;                                      // >= T*128 B, free until step 3
+        for (uint32_t i = tid; i < T; i += K1_THREADS) {
+            const uint32_t pos = kout[i];
+            if (pos == 0xffffffffu) continue;
+            double2 c = p.tc[i];
+            double re = c.x, im = c.y;
+            for (uint32_t j = i + 1; j < T && kout[j] == 0xffffffffu; j++) {
+                c = p.tc[j];
+                re = __dadd_rn(re, c.x); im = __dadd_rn(im, c.y);
+            }
+            tc2[pos] = make_double2(re, im);
+            tz2[pos] = p.tz[i];
+            iout[pos] = p.perm[i];
+        }
+        __syncthreads();
+        for (uint32_t g = tid; g <= G; g += K1_THREADS) {            // group offsets in the merged list
+            const uint32_t o = p.goff[g];
+            p.goff[g] = o < T ? kout[o] : T2;                        // a group's first term heads a run
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < T2; i += K1_THREADS) { p.tc[i] = tc2[i]; p.tz[i] = tz2[i]; p.perm[i] = iout[i]; }
+        __syncthreads();
+    }
+
+    // ---- 3. rank tables -----------------------------------------------------------------------
     const uint32_t nq = (uint32_t)p.n_qubits;
     for (uint32_t q = tid; q < G * 32u; q += K1_THREADS) {
         const uint32_t g = q >> 5, b = q & 31u;
@@ -159,7 +225,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p)
         for (uint32_t b = 0; b < 5; b++) s += ((j >> b) & 1u) ? p.cnt[g * 32u + b] : 0u;
         p.lr5[q] = s;
     }
-    if (tid == 0) { p.meta[1] = max_group; p.meta[2] = 0; p.meta[3] = 0; p.meta[4] = n_const; }
+    if (tid == 0) { p.meta[1] = max_group; p.meta[2] = 0; p.meta[3] = 0; p.meta[4] = n_const; p.meta[5] = T2; }
 }
 
 // K1b: cut the sorted masks into maximal trie subtrees of at most S groups (S >= 32).

@@ -22,7 +22,7 @@ namespace qr {
 //                         bit1: every c' of the group is real (im == +-0)
 //   gconst double2[G]     the group's ordered sum of c' (its value when bit0 is set)
 //   gdesc GroupDesc[G]    {x, flag, t0, t1, gconst} packed in 32 B for the H.v kernels
-//   meta  u32[8]          {G, max terms in a group, B, S, #row-independent groups, 0, 0, 0}
+//   meta  u32[8]          {G, max terms in a group, B, S, #row-independent groups, #terms after merging, 0, 0}
 //   blk_start u32[B+1]    large-G path: the sorted groups cut into B trie subtrees ("blocks")
 //   blk_p     u32[B]      of <= S groups; block b = groups [blk_start[b], blk_start[b+1]), all
 //                         sharing the mask bits >= blk_p[b] (>= 5).  A subtree's groups fill

@@ -73,6 +73,8 @@ struct qr_plan {
     int rw = 0, gw = 0;
     uint32_t block_s = 0, n_blocks = 0;    // blocked kernel: S and the number of subtree blocks
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
+    uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
+    uint64_t n_terms_canonical = 0;
     // lazily allocated scratch
     double2 *dot_partials = nullptr;
     void *win_buf[2] = {nullptr, nullptr};
@@ -156,7 +158,7 @@ extern "C" uint64_t qr_kernel_launches(void) { return g_launches.load(); }
 // =====================================================================================
 static int run_canonicalise(qr_plan *pl, cudaStream_t st)
 {
-    qr::canonicalise_kernel<<<1, qr::K1_THREADS, 0, st>>>(pl->dev);
+    qr::canonicalise_kernel<<<1, qr::K1_THREADS, 0, st>>>(pl->dev, pl->merge_dups);
     QR_LAUNCH_CHECK("canonicalise_kernel");
     return QR_OK;
 }
@@ -172,7 +174,6 @@ static int run_partition(qr_plan *pl, cudaStream_t st)
 extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms, int device,
                               uint32_t flags, qr_plan **out)
 {
-    (void)flags;
     if (!out) return fail(QR_ERR_INVALID, "qr_plan_create: out is NULL");
     *out = nullptr;
     if (!terms || n_terms == 0)
@@ -189,6 +190,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     qr_plan *pl = new (std::nothrow) qr_plan();
     if (!pl) return fail(QR_ERR_OOM, "qr_plan_create: host allocation failed");
     pl->device = device; pl->n_qubits = n_qubits; pl->dim = dim; pl->n_terms = n_terms;
+    pl->merge_dups = (flags & QR_PLAN_MERGE_DUPLICATES) ? 1u : 0u;
 
     const size_t T = n_terms;
     size_t off = 0;
@@ -227,6 +229,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: canonicalise: ") + cudaGetErrorString(e)));
     pl->n_groups = meta[0];
     pl->n_const = meta[4];
+    pl->n_terms_canonical = meta[5];
     if (pl->n_groups == 0 || pl->n_groups > T) return bail(fail(QR_ERR_CUDA, "qr_plan_create: canonicalisation produced no groups"));
     choose_staged(pl);
     if (pl->block_s) {
@@ -277,6 +280,13 @@ extern "C" int qr_plan_groups(const qr_plan *pl, uint64_t *xmask, uint32_t *grou
     }
     if (group_offsets) QR_CUDA(cudaMemcpy(group_offsets, pl->dev.goff, (G + 1) * 4, cudaMemcpyDeviceToHost));
     if (term_order) QR_CUDA(cudaMemcpy(term_order, pl->dev.perm, T * 4, cudaMemcpyDeviceToHost));
+    return QR_OK;
+}
+
+extern "C" int qr_plan_canonical_terms(const qr_plan *pl, uint64_t *count)
+{
+    if (!pl || !count) return fail(QR_ERR_INVALID, "qr_plan_canonical_terms: NULL argument");
+    *count = pl->n_terms_canonical;
     return QR_OK;
 }
 

@@ -229,6 +229,28 @@ def test_canonicalise_groups(fixtures, name):
     assert np.array_equal(goff, np.r_[heads, len(sx)].astype(np.uint32))
 
 
+def test_merge_duplicates_opt_in(fixtures):
+    """QR_PLAN_MERGE_DUPLICATES: identical (x, z) terms are merged by the (x,z)-keyed sort +
+    segmented reduce; structure stays bit-exact, data agrees to 1e-12 (summation order changes)."""
+    for labels, coeffs in (H.random_pauli_sum(10, 300, 200, 30, 7), H.random_pauli_sum(12, 900, 120, 400, 3),
+                           fixtures["H4"], H.xxz_chain(10, 1.0, 0.7)):
+        n, params = O.make_params(labels, coeffs)
+        ref = O.build_csr(params, n)
+        op = make_op(labels, coeffs)
+        op.merge_duplicates = True
+        plan = op.plan()
+        keys = np.unique(np.stack([params["x"], params["z"]], axis=1), axis=0)
+        assert plan.n_terms_canonical == len(keys) <= plan.n_terms
+        gx, goff, order = plan.groups()
+        assert np.array_equal(gx, np.unique(params["x"])) and goff[-1] == len(keys)
+        shape, data, indices, indptr = op.to_matrix().export()
+        assert np.array_equal(indptr, ref[0]) and np.array_equal(indices, ref[1])
+        scale = np.abs(params["re"] + 1j * params["im"]).sum()
+        assert np.abs(data - ref[2]).max() <= 1e-12 * scale
+        v = H.lanczos_start_vector(0, 1 << n, seed=9)
+        assert np.abs(op.apply(v) - O.spmv(*ref, v)).max() <= 1e-12 * scale * 2
+
+
 # ---- full-size configs -------------------------------------------------------------------------
 def test_C2_full_matrix():
     """BASELINE config 2 (XXZ periodic n=20, nnz = 22 020 096) compared in full."""
