@@ -31,30 +31,6 @@ __device__ __forceinline__ void cfma(double &yr, double &yi, double ar, double a
     else { yr += ar * w.x - ai * w.y; yi += ar * w.y + ai * w.x; }
 }
 
-// Values of one row-dependent group for E rows at once: the term table is walked once, every
-// (z, c') is loaded once (warp-uniform) and applied to the E rows held in registers.
-template <int E>
-__device__ __forceinline__ void group_values(const PlanDev &p, uint32_t t0, uint32_t t1, const uint32_t (&r)[E],
-                                             double (&ar)[E], double (&ai)[E])
-{
-    double2 c = __ldg(&p.tc[t0]);
-    uint32_t z = __ldg(&p.tz[t0]);
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const uint32_t s = (uint32_t)(__popc(r[e] & z) & 1) << 31;
-        ar[e] = flip_sign(c.x, s); ai[e] = flip_sign(c.y, s);
-    }
-    for (uint32_t t = t0 + 1; t < t1; t++) {
-        c = __ldg(&p.tc[t]);
-        z = __ldg(&p.tz[t]);
-#pragma unroll
-        for (int e = 0; e < E; e++) {
-            const uint32_t s = (uint32_t)(__popc(r[e] & z) & 1) << 31;
-            ar[e] += flip_sign(c.x, s); ai[e] += flip_sign(c.y, s);
-        }
-    }
-}
-
 // v0 (gather): thread <-> APPLY_ROWS rows (r, r+256, ...), so a warp's loads of v[r ^ x] stay one
 // permuted, fully coalesced 512-byte segment.  Group descriptors come through shared memory.
 // `diag` (optional): cached values of the mask-0 group for rows [row_lo,row_hi); when given, group 0

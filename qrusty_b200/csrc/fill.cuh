@@ -46,6 +46,30 @@ __device__ __forceinline__ double2 group_value(const uint32_t *__restrict__ tz,
     return make_double2(re, im);
 }
 
+// Values of one group for E rows at once: the term table is walked once, every (z, c') is loaded
+// once (warp-uniform) and applied to the E rows held in registers.  Same fold as group_value.
+template <int E>
+__device__ __forceinline__ void group_values(const PlanDev &p, uint32_t t0, uint32_t t1, const uint32_t (&r)[E],
+                                             double (&ar)[E], double (&ai)[E])
+{
+    double2 c = __ldg(&p.tc[t0]);
+    uint32_t z = __ldg(&p.tz[t0]);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint32_t s = (uint32_t)(__popc(r[e] & z) & 1) << 31;
+        ar[e] = flip_sign(c.x, s); ai[e] = flip_sign(c.y, s);
+    }
+    for (uint32_t t = t0 + 1; t < t1; t++) {
+        c = __ldg(&p.tc[t]);
+        z = __ldg(&p.tz[t]);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint32_t s = (uint32_t)(__popc(r[e] & z) & 1) << 31;
+            ar[e] = __dadd_rn(ar[e], flip_sign(c.x, s)); ai[e] = __dadd_rn(ai[e], flip_sign(c.y, s));
+        }
+    }
+}
+
 // Value of group g in row r: row-independent groups (gflag bit0: every z == 0, e.g. all
 // X-only strings) skip the term loop -- gconst holds the same ordered fold, bit for bit.
 __device__ __forceinline__ double2 group_value_g(const PlanDev &p, uint32_t g, uint32_t r)
@@ -104,13 +128,13 @@ fill_direct_kernel(PlanDev p, uint32_t G, uint64_t lo, uint64_t hi, uint64_t out
 }
 
 // ---------------------------------------------------------------------------------
-// Staged kernel: a CTA owns a tile of R = 32*RW whole rows (aligned to R).  The
+// Staged kernel: a CTA owns a tile of R = 32*E whole rows (aligned to R).  The
 // tile's R*G entries are contiguous in BOTH output arrays, so the CTA assembles
 // them in shared memory in final order and one thread hands each array to the
 // TMA as a single bulk copy (cp.async.bulk.global.shared::cta): HBM sees only
 // full-line, perfectly sequential writes and no LSU instruction is spent on them.
-// The GW warps of a row strip split the groups (g = gw, gw+GW, ...).
-// Requires R*G*24 B of shared memory; the host picks (RW, GW) from G.
+// The GW warps split the groups (g = gw, gw+GW, ...); each handles E row strips per visit.
+// Requires R*G*24 B of shared memory; the host picks (E, GW) from G.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void bulk_store_smem_to_global(void *gdst, const void *ssrc, uint32_t bytes)
 {
@@ -118,38 +142,53 @@ __device__ __forceinline__ void bulk_store_smem_to_global(void *gdst, const void
                  :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
 
-template <int RW, int GW, bool HAS_CONST>
-__global__ void __launch_bounds__(32 * RW * GW)
+template <int E, int GW>
+__global__ void __launch_bounds__(32 * GW)
 fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
                    uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
                    double2 *__restrict__ data, uint64_t indptr_last_row)
 {
-    constexpr uint32_t R = 32u * RW;
+    // tile = E strips of 32 rows; each of the GW warps visits its share of the groups and handles
+    // all E strips per visit: descriptor, rank-table row and every term are read once per 32*E entries
+    constexpr uint32_t R = 32u * E;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                         // R*G * 16 B
     uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)R * G * 16u);  // R*G *  8 B
 
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t rw = warp % RW, gw = warp / RW;
+    const uint32_t lane = threadIdx.x & 31u, gw = threadIdx.x >> 5;
     const uint64_t tile_base = tile_row0 + (uint64_t)blockIdx.x * R;
-    const uint32_t wbase = (uint32_t)tile_base + 32u * rw;
-    const uint32_t r = wbase + lane;
-    const uint32_t srow = (32u * rw + lane) * G;
+    const uint32_t tbase = (uint32_t)tile_base;
+    uint32_t r[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) r[e] = tbase + 32u * e + lane;
 
     for (uint32_t g = gw; g < G; g += GW) {
-        const uint32_t x = __ldg(&p.gx[g]);
-        const uint32_t slot = group_slot(p, g, x, wbase, lane);
-        // HAS_CONST is false when no group of the operator is row-independent: the flag load
-        // costs 10 % on C2 (measured), so it is compiled out there
-        const double2 v = HAS_CONST ? group_value_g(p, g, r)
-                                    : group_value(p.tz, p.tc, __ldg(&p.goff[g]), __ldg(&p.goff[g + 1]), r);
-        sidx[srow + slot] = (uint64_t)(r ^ x);
-        sdat[srow + slot] = v;
+        const GroupDesc d = p.gdesc[g];                                          // warp-uniform, 2 x 16 B
+        const uint32_t c = __ldg(&p.cnt[g * 32u + lane]);
+        const uint32_t lo = __ldg(&p.lr5[g * 32u + ((d.x ^ lane) & 31u)]);
+        double ar[E], ai[E];
+        if (d.flag & 1u) {
+#pragma unroll
+            for (int e = 0; e < E; e++) { ar[e] = d.cre; ai[e] = d.cim; }
+        } else {
+            group_values<E>(p, d.t0, d.t1, r, ar, ai);
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint32_t bit = ((d.x ^ (tbase + 32u * e)) >> lane) & 1u;
+            const uint32_t slot = __reduce_add_sync(0xffffffffu, (lane >= 5u && bit) ? c : 0u) + lo;
+            const uint32_t o = (32u * e + lane) * G + slot;
+            sidx[o] = (uint64_t)(r[e] ^ d.x);
+            sdat[o] = make_double2(ar[e], ai[e]);
+        }
     }
     if (gw == 0 && indptr != nullptr) {
-        const uint64_t lr = tile_base + 32u * rw + lane - row_lo;
-        indptr[lr] = indptr_base + lr * G;
-        if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint64_t lr = tile_base + 32u * e + lane - row_lo;
+            indptr[lr] = indptr_base + lr * G;
+            if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+        }
     }
     // generic-proxy writes -> visible to the async proxy, then one thread issues the copies
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -174,7 +213,32 @@ fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, u
 // segments [base, base + size) stream out with coalesced 16-byte / 8-byte stores.
 // ---------------------------------------------------------------------------------
 constexpr int FILL_BLOCKED_WARPS = 8;
+constexpr int FILL_BLOCKED_TCAP = 512;      // terms of a block staged in shared memory (10 KB)
 
+// group_values with the term table behind generic pointers (shared or global memory)
+template <int E>
+__device__ __forceinline__ void group_values_ptr(const uint32_t *tz, const double2 *tc, uint32_t t0, uint32_t t1,
+                                                 const uint32_t (&r)[E], double (&ar)[E], double (&ai)[E])
+{
+    double2 c = tc[t0];
+    uint32_t z = tz[t0];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint32_t s = (uint32_t)(__popc(r[e] & z) & 1) << 31;
+        ar[e] = flip_sign(c.x, s); ai[e] = flip_sign(c.y, s);
+    }
+    for (uint32_t t = t0 + 1; t < t1; t++) {
+        c = tc[t];
+        z = tz[t];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint32_t s = (uint32_t)(__popc(r[e] & z) & 1) << 31;
+            ar[e] = __dadd_rn(ar[e], flip_sign(c.x, s)); ai[e] = __dadd_rn(ai[e], flip_sign(c.y, s));
+        }
+    }
+}
+
+template <int E>
 __global__ void __launch_bounds__(32 * FILL_BLOCKED_WARPS)
 fill_blocked_kernel(PlanDev p, uint32_t G, uint32_t S, uint32_t n_blocks, uint32_t strips_per_cta,
                     uint64_t tile_row0, uint64_t n_strips, uint64_t row_lo, uint64_t indptr_base,
@@ -183,61 +247,88 @@ fill_blocked_kernel(PlanDev p, uint32_t G, uint32_t S, uint32_t n_blocks, uint32
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t pitch = S + 1;
-    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                               // [32][S+1]
-    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)32 * pitch * 16);     // [32][S+1]
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem_raw + (size_t)32 * pitch * 24);    // [S][32]
+    constexpr uint32_t ROWS = 32u * E;
+    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                                // [32E][S+1]
+    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ROWS * pitch * 16);    // [32E][S+1]
+    unsigned char *tab = smem_raw + (size_t)ROWS * pitch * 24;
+    GroupDesc *s_desc = reinterpret_cast<GroupDesc *>(tab);                               // [S]
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(tab + (size_t)S * sizeof(GroupDesc));   // [S][32]
     uint32_t *s_lr5 = s_cnt + S * 32u;                                                    // [S][32]
-    uint32_t *s_gx = s_lr5 + S * 32u;                                                     // [S]
-    uint32_t *s_goff = s_gx + S;                                                          // [S+1]
+    double2 *s_tc = reinterpret_cast<double2 *>(s_lr5 + S * 32u);                         // [TCAP]
+    uint32_t *s_tz = reinterpret_cast<uint32_t *>(s_tc + FILL_BLOCKED_TCAP);               // [TCAP]
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t blk = blockIdx.x % n_blocks;
     const uint64_t strip0 = (uint64_t)(blockIdx.x / n_blocks) * strips_per_cta;
     const uint32_t g0 = __ldg(&p.blk_start[blk]), g1 = __ldg(&p.blk_start[blk + 1]);
     const uint32_t size = g1 - g0, plevel = __ldg(&p.blk_p[blk]);
+    const uint32_t term0 = __ldg(&p.goff[g0]), n_terms = __ldg(&p.goff[g1]) - term0;
+    const bool terms_in_smem = n_terms <= (uint32_t)FILL_BLOCKED_TCAP;
 
     for (uint32_t i = threadIdx.x; i < size * 32u; i += blockDim.x) {
         s_cnt[i] = __ldg(&p.cnt[g0 * 32u + i]);
         s_lr5[i] = __ldg(&p.lr5[g0 * 32u + i]);
     }
-    for (uint32_t i = threadIdx.x; i <= size; i += blockDim.x) {
-        s_goff[i] = __ldg(&p.goff[g0 + i]);
-        if (i < size) s_gx[i] = __ldg(&p.gx[g0 + i]);
-    }
+    for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) s_desc[i] = p.gdesc[g0 + i];
+    if (terms_in_smem)
+        for (uint32_t i = threadIdx.x; i < n_terms; i += blockDim.x) { s_tc[i] = __ldg(&p.tc[term0 + i]); s_tz[i] = __ldg(&p.tz[term0 + i]); }
     __syncthreads();
+    // term table of this block: shared copy (indices relative to term0) or the global one
+    const uint32_t *tzp = terms_in_smem ? s_tz - term0 : p.tz;
+    const double2 *tcp = terms_in_smem ? s_tc - term0 : p.tc;
 
     const uint32_t in_block = (lane >= 5u && lane < plevel) ? 1u : 0u;     // bits ordering groups inside the block
     const uint32_t above = lane >= plevel ? 1u : 0u;                        // bits ordering the block among blocks
     const uint64_t strip_end = min(strip0 + strips_per_cta, n_strips);
-    for (uint64_t strip = strip0; strip < strip_end; strip++) {
+    for (uint64_t strip = strip0; strip < strip_end; strip += E) {
         const uint64_t tile_base = tile_row0 + strip * 32u;
-        const uint32_t wbase = (uint32_t)tile_base;
-        const uint32_t r = wbase + lane;
-        const uint32_t bit0 = ((s_gx[0] ^ wbase) >> lane) & 1u;
-        const uint32_t base = __reduce_add_sync(0xffffffffu, (above && bit0) ? s_cnt[lane] : 0u);
-
+        const uint32_t tbase = (uint32_t)tile_base;
+        const uint32_t ne = (uint32_t)min((uint64_t)E, strip_end - strip);   // strips in this visit (tail: 1)
+        uint32_t r[E], base[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            r[e] = tbase + 32u * e + lane;
+            const uint32_t bit0 = ((s_desc[0].x ^ (tbase + 32u * e)) >> lane) & 1u;
+            base[e] = __reduce_add_sync(0xffffffffu, (above && bit0) ? s_cnt[lane] : 0u);
+        }
         for (uint32_t gi = warp; gi < size; gi += FILL_BLOCKED_WARPS) {
-            const uint32_t x = s_gx[gi];
-            const uint32_t bit = ((x ^ wbase) >> lane) & 1u;
-            const uint32_t off = __reduce_add_sync(0xffffffffu, (in_block && bit) ? s_cnt[gi * 32u + lane] : 0u)
-                               + s_lr5[gi * 32u + ((x ^ lane) & 31u)];
-            const double2 v = (__ldg(&p.gflag[g0 + gi]) & 1u) ? __ldg(&p.gconst[g0 + gi])
-                                                             : group_value(p.tz, p.tc, s_goff[gi], s_goff[gi + 1], r);
-            sidx[lane * pitch + off] = (uint64_t)(r ^ x);
-            sdat[lane * pitch + off] = v;
+            const GroupDesc d = s_desc[gi];
+            const uint32_t c = s_cnt[gi * 32u + lane];
+            const uint32_t lo = s_lr5[gi * 32u + ((d.x ^ lane) & 31u)];
+            double ar[E], ai[E];
+            if (d.flag & 1u) {
+#pragma unroll
+                for (int e = 0; e < E; e++) { ar[e] = d.cre; ai[e] = d.cim; }
+            } else {
+                group_values_ptr<E>(tzp, tcp, d.t0, d.t1, r, ar, ai);
+            }
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const uint32_t bit = ((d.x ^ (tbase + 32u * e)) >> lane) & 1u;
+                const uint32_t off = __reduce_add_sync(0xffffffffu, (in_block && bit) ? c : 0u) + lo;
+                const uint32_t o = (32u * e + lane) * pitch + off;
+                sidx[o] = (uint64_t)(r[e] ^ d.x);
+                sdat[o] = make_double2(ar[e], ai[e]);
+            }
         }
         if (blk == 0 && warp == 0 && indptr != nullptr) {
-            const uint64_t lr = tile_base + lane - row_lo;
-            indptr[lr] = indptr_base + lr * G;
-            if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if ((uint32_t)e < ne) {
+                    const uint64_t lr = tile_base + 32u * e + lane - row_lo;
+                    indptr[lr] = indptr_base + lr * G;
+                    if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+                }
+            }
         }
         __syncthreads();
-        const uint64_t out0 = (tile_base - row_lo) * G + base;
-        for (uint32_t l = warp; l < 32u; l += FILL_BLOCKED_WARPS) {
-            const uint64_t o = out0 + (uint64_t)l * G;
+        for (uint32_t l = warp; l < 32u * ne; l += FILL_BLOCKED_WARPS) {
+            const uint64_t o = (tile_base + l - row_lo) * G + base[0];
+            // base differs per strip: rows of strip e use base[e]
+            const uint64_t oo = o - base[0] + (l < 32u ? base[0] : base[E - 1]);
             for (uint32_t k = lane; k < size; k += 32u) {
-                data[o + k] = sdat[l * pitch + k];
-                indices[o + k] = sidx[l * pitch + k];
+                data[oo + k] = sdat[l * pitch + k];
+                indices[oo + k] = sidx[l * pitch + k];
             }
         }
         __syncthreads();

@@ -73,6 +73,7 @@ struct qr_plan {
     int rw = 0, gw = 0;
     uint32_t block_s = 0, n_blocks = 0;    // blocked kernel: S and the number of subtree blocks
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
+    uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
     uint64_t n_terms_canonical = 0;
     // lazily allocated scratch
@@ -98,11 +99,11 @@ namespace {
 // ---------------------------------------------------------------------------------
 using StagedFn = void (*)(qr::PlanDev, uint32_t, uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *,
                           double2 *, uint64_t);
-struct StagedCfg { int rw, gw; StagedFn fn, fn_const; };   // fn_const: operator has row-independent groups
-#define QR_STAGED(RW, GW) {RW, GW, qr::fill_staged_kernel<RW, GW, false>, qr::fill_staged_kernel<RW, GW, true>}
+struct StagedCfg { int rw, gw; StagedFn fn; };             // rw = E (row strips per warp visit), gw = warps
+#define QR_STAGED(E, GW) {E, GW, qr::fill_staged_kernel<E, GW>}
 const StagedCfg kStaged[] = {
-    QR_STAGED(1, 4), QR_STAGED(1, 8), QR_STAGED(1, 16), QR_STAGED(2, 2), QR_STAGED(2, 4), QR_STAGED(2, 8),
-    QR_STAGED(4, 2), QR_STAGED(4, 4),
+    QR_STAGED(1, 4), QR_STAGED(1, 8), QR_STAGED(1, 16), QR_STAGED(2, 4), QR_STAGED(2, 8), QR_STAGED(2, 16),
+    QR_STAGED(4, 4), QR_STAGED(4, 8), QR_STAGED(4, 16),
 };
 
 const StagedCfg *find_staged(int rw, int gw)
@@ -112,7 +113,17 @@ const StagedCfg *find_staged(int rw, int gw)
 }
 
 // Pick (RW, GW) from G: as many resident warps per SM as the R*G*24-byte tile allows.
-size_t blocked_smem(uint32_t S) { return (size_t)32 * (S + 1) * 24 + (size_t)S * 256 + (size_t)(2 * S + 1) * 4; }
+size_t blocked_smem(uint32_t S, int E)
+{
+    return (size_t)32 * E * (S + 1) * 24 + (size_t)S * (256 + sizeof(qr::GroupDesc)) + qr::FILL_BLOCKED_TCAP * 20;
+}
+// strips per group visit: 2 amortises the term loads of long groups (H8 2.33 vs 2.14 TB/s), 1 keeps
+// occupancy for short ones (C3 4.26 vs 3.98 TB/s); profiles/r01_fill_sweep_largeG.jsonl
+int blocked_strips(const qr_plan *pl)
+{
+    if (const char *e = getenv("QR_FILL_BLOCK_E")) return atoi(e) == 1 ? 1 : 2;
+    return pl->n_terms >= 3 * pl->n_groups ? 2 : 1;
+}
 
 void choose_staged(qr_plan *pl)
 {
@@ -121,7 +132,7 @@ void choose_staged(qr_plan *pl)
     pl->block_s = 0;
     if (const char *env = getenv("QR_FILL_BLOCK")) {         // "S" override: force the blocked kernel
         int S = atoi(env);
-        if (S >= 32 && blocked_smem(S) <= MAX_SMEM) { pl->block_s = (uint32_t)S; return; }
+        if (S >= 32 && blocked_smem(S, 2) <= MAX_SMEM) { pl->block_s = (uint32_t)S; return; }
     }
     if (const char *env = getenv("QR_FILL_CFG")) {           // "RW,GW" override for experiments
         int rw = 0, gw = 0;
@@ -129,11 +140,12 @@ void choose_staged(qr_plan *pl)
             pl->rw = rw; pl->gw = gw; return;
         }
     }
-    // Measured on B200 (profiles/r01_fill_sweep.jsonl): 32-row tiles with the groups split
-    // over 8 warps beat taller tiles (C2: 6.06 vs 5.99 TB/s, C4: 6.47 vs 6.11 TB/s).
+    // Measured on B200 (profiles/r01_fill_sweep.jsonl): 8 warps splitting the groups, each visiting
+    // two 32-row strips per group: C2 6.56 TB/s, C4 6.72 TB/s (one strip: 5.45 / 6.39; four: 5.95 / 4.48).
     const uint64_t row_bytes = G * 24;
-    if (G < 8 && 32 * row_bytes <= MAX_SMEM)  { pl->rw = 1; pl->gw = 4; }
-    else if (32 * row_bytes <= 113 * 1024)    { pl->rw = 1; pl->gw = 8; }   // 2+ CTAs/SM
+    if (G < 8 && 64 * row_bytes <= MAX_SMEM)  { pl->rw = 2; pl->gw = 4; }
+    else if (64 * row_bytes <= 113 * 1024)    { pl->rw = 2; pl->gw = 8; }   // 2+ CTAs/SM
+    else if (32 * row_bytes <= 113 * 1024)    { pl->rw = 1; pl->gw = 8; }
     else {
         // whole rows do not fit (twice): subtree blocks of <= 32 groups.  Measured
         // (profiles/r01_fill_sweep_largeG.jsonl): C3 4.52 TB/s at S=32, 3.73 at 64, 2.08 at 128.
@@ -229,6 +241,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: canonicalise: ") + cudaGetErrorString(e)));
     pl->n_groups = meta[0];
     pl->n_const = meta[4];
+    pl->max_group_terms = meta[1];
     pl->n_terms_canonical = meta[5];
     if (pl->n_groups == 0 || pl->n_groups > T) return bail(fail(QR_ERR_CUDA, "qr_plan_create: canonicalisation produced no groups"));
     choose_staged(pl);
@@ -327,18 +340,20 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
     if (!(flags & QR_FILL_DIRECT) && pl->block_s) {
         const uint64_t s0 = align_up(row_lo, 32), s1 = row_hi / 32 * 32;
         if (s1 > s0) {
-            const size_t smem = blocked_smem(pl->block_s);
             const uint64_t strips = (s1 - s0) / 32;
+            const int E = blocked_strips(pl);
+            const size_t smem = blocked_smem(pl->block_s, E);
             // enough CTAs to fill the chip several times over, else as many strips per CTA as
-            // amortise the table load (17 KB at S=64 against ~35 KB of output per strip)
+            // amortise the table load (10 KB at S=32 against ~17 KB of output per strip)
             uint32_t per_cta = 8;
-            while (per_cta > 1 && (strips + per_cta - 1) / per_cta * pl->n_blocks < 148ull * 16) per_cta /= 2;
+            while (per_cta > (uint32_t)E && (strips + per_cta - 1) / per_cta * pl->n_blocks < 148ull * 16) per_cta /= 2;
             const uint64_t ctas = (strips + per_cta - 1) / per_cta * pl->n_blocks;
             if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_blocked: row window too large for one launch");
-            QR_CUDA(cudaFuncSetAttribute(qr::fill_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            auto kern = E == 2 ? qr::fill_blocked_kernel<2> : qr::fill_blocked_kernel<1>;
+            QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
-            qr::fill_blocked_kernel<<<(unsigned)ctas, 32 * qr::FILL_BLOCKED_WARPS, smem, st>>>(
+            kern<<<(unsigned)ctas, 32 * qr::FILL_BLOCKED_WARPS, smem, st>>>(
                 pl->dev, (uint32_t)G, pl->block_s, pl->n_blocks, per_cta, s0, strips, row_lo, indptr_base,
                 d_indptr, d_indices, d_data, row_hi - row_lo);
             QR_LAUNCH_CHECK("fill_blocked_kernel");
@@ -355,12 +370,12 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             const size_t smem = (size_t)(R * G * 24);
             const uint64_t tiles = (s1 - s0) / R;
             if (tiles > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_staged: row window too large for one launch");
-            StagedFn fn = pl->n_const ? cfg->fn_const : cfg->fn;
+            StagedFn fn = cfg->fn;
             QR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // prefix / suffix rows that do not fill a tile
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
-            fn<<<(unsigned)tiles, 32 * cfg->rw * cfg->gw, smem, st>>>(
+            fn<<<(unsigned)tiles, 32 * cfg->gw, smem, st>>>(
                 pl->dev, (uint32_t)G, s0, row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo);
             QR_LAUNCH_CHECK("fill_staged_kernel");
             lo = s1; hi = row_hi;

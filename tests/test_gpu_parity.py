@@ -170,12 +170,14 @@ def test_direct_equals_staged(fixtures):
     assert_same(a, b, "staged vs direct")
 
 
+@pytest.mark.parametrize("E", [1, 2])
 @pytest.mark.parametrize("S", [32, 48, 64, 128])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2"])
-def test_blocked_kernel(fixtures, monkeypatch, name, S):
+def test_blocked_kernel(fixtures, monkeypatch, name, S, E):
     """Large-G path (partition_kernel + fill_blocked_kernel) forced on every case: subtree blocks
     of at most S groups, whole matrix and ragged windows."""
     monkeypatch.setenv("QR_FILL_BLOCK", str(S))
+    monkeypatch.setenv("QR_FILL_BLOCK_E", str(E))
     labels, coeffs = SMALL[name](fixtures)
     n, params = O.make_params(labels, coeffs)
     ref = O.build_csr(params, n)
