@@ -158,6 +158,13 @@ QR_API int qr_ax_device(uint64_t n, const double a[2], const double *d_x, double
 /* <x,y> = sum conj(x_i) y_i  -> d_out[2] (numpy.vdot; the reference leaves this to numpy). */
 QR_API int qr_dotc_device(uint64_t n, const double *d_x, const double *d_y, double *d_out, void *stream);
 
+/* Lanczos three-term recurrence fused with the norm (the vector work either side of H.v in an
+ * eigensolver iteration): d_w_out = d_w - alpha*d_v - beta*d_v_prev (d_v_prev may be NULL),
+ * d_norm2_out[0] = sum |w_out|^2 (one double).  d_w_out may alias d_w. */
+QR_API int qr_lanczos_update_device(uint64_t n, const double alpha[2], const double beta[2], const double *d_w,
+                             const double *d_v, const double *d_v_prev, double *d_w_out,
+                             double *d_norm2_out, void *stream);
+
 /* ---- multi-GPU, one process per GPU.  NCCL is dlopen'ed on first use.  The
  * CSR build needs no communication; H.v all-gathers the row-sharded vector. */
 #define QR_UNIQUE_ID_BYTES 128

@@ -66,6 +66,7 @@ SIGNATURES = {
     "qr_axpy_device": [_u64, _dp, _vp, _vp, _vp, _vp],
     "qr_ax_device": [_u64, _dp, _vp, _vp, _vp],
     "qr_dotc_device": [_u64, _vp, _vp, _vp, _vp],
+    "qr_lanczos_update_device": [_u64, _dp, _dp, _vp, _vp, _vp, _vp, _vp, _vp],
     "qr_comm_unique_id": [_vp],
     "qr_comm_create": [_vp, _int, _int, _int, C.POINTER(_vp)],
     "qr_comm_destroy": [_vp],

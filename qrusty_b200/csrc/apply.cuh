@@ -40,6 +40,7 @@ __device__ __forceinline__ void cfma(double &yr, double &yi, double ar, double a
 // every row of this rank, so the base pointer is a per-group constant (staged beside the
 // descriptor) and remote shards are read in place over NVLink -- the collective is fused into
 // the apply.  Without `peers`, v is the full vector in local memory.
+template <bool PEERS>
 __global__ void __launch_bounds__(APPLY_THREADS)
 apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
                     const double2 *__restrict__ v, double2 *__restrict__ y,
@@ -48,10 +49,10 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
 {
     constexpr int E = APPLY_ROWS;
     __shared__ GroupDesc sd[APPLY_BATCH];
-    __shared__ const double2 *sv[APPLY_BATCH];
+    __shared__ const double2 *sv[PEERS ? APPLY_BATCH : 1];
     const uint64_t cta_base = row_lo + (uint64_t)blockIdx.x * (APPLY_THREADS * E);
-    const uint32_t my_rank = peers ? (uint32_t)(row_lo >> shard_bits) : 0u;
-    const double2 *v_own = peers ? peers[my_rank] : v;
+    const uint32_t my_rank = PEERS ? (uint32_t)(row_lo >> shard_bits) : 0u;
+    const double2 *v_own = PEERS ? peers[my_rank] : v;
     uint32_t r[E];
     bool live[E];
     double yr[E], yi[E];
@@ -77,12 +78,12 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
         for (uint32_t i = threadIdx.x; i < nb; i += APPLY_THREADS) {
             const GroupDesc d = p.gdesc[g0 + i];
             sd[i] = d;
-            sv[i] = peers ? peers[my_rank ^ (d.x >> shard_bits)] : v;
+            if (PEERS) sv[i] = peers[my_rank ^ (d.x >> shard_bits)];
         }
         __syncthreads();
         for (uint32_t k = 0; k < nb; k++) {
             const GroupDesc d = sd[k];
-            const double2 *vb = sv[k];
+            const double2 *vb = PEERS ? sv[k] : v;
             const bool real = (d.flag & 2u) != 0u;
             if (d.flag & 1u) {
 #pragma unroll
@@ -260,6 +261,33 @@ vec_axpby_kernel(uint64_t n, double2 a, const double2 *__restrict__ x, double2 b
         if (MODE == 0) { double2 u = cmul_rn(b, y[i]); t = make_double2(__dadd_rn(t.x, u.x), __dadd_rn(t.y, u.y)); }
         if (MODE == 1) { double2 u = y[i]; t = make_double2(__dadd_rn(t.x, u.x), __dadd_rn(t.y, u.y)); }
         z[i] = t;
+    }
+}
+
+// Lanczos three-term update fused with the norm: w_out = w - alpha*v - beta*v_prev and
+// partial[b] = (sum |w_out|^2, 0) per CTA (folded by dotc_final_kernel).  One pass over three
+// vectors instead of two axpy passes and a dot product.
+__global__ void __launch_bounds__(256)
+lanczos_update_kernel(uint64_t n, double2 alpha, double2 beta, const double2 *w,      // w_out may alias w
+                      const double2 *__restrict__ v, const double2 *__restrict__ v_prev,
+                      double2 *w_out, double2 *__restrict__ partial)
+{
+    __shared__ double sre[8];
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        const double2 a = v[i], b = v_prev ? v_prev[i] : make_double2(0.0, 0.0), c = w[i];
+        const double re = c.x - (alpha.x * a.x - alpha.y * a.y) - (beta.x * b.x - beta.y * b.y);
+        const double im = c.y - (alpha.x * a.y + alpha.y * a.x) - (beta.x * b.y + beta.y * b.x);
+        w_out[i] = make_double2(re, im);
+        acc += re * re + im * im;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) sre[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) acc += sre[k];
+        partial[blockIdx.x] = make_double2(acc, 0.0);
     }
 }
 

@@ -98,18 +98,22 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
 {
     __shared__ RadixSmem sm;
     __shared__ uint32_t max_group, n_const;
+    // small operators (the usual case: tens of terms) sort entirely in shared memory
+    constexpr uint32_t SMALL_T = 1024;
+    __shared__ uint32_t s_sort[4][SMALL_T];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t T = p.n_terms;
 
     // ---- 0. payload = original index ------------------------------------------------------
-    for (uint32_t i = tid; i < T; i += K1_THREADS) p.idx_a[i] = i;
     for (uint32_t i = tid; i < K1_WARPS * 256; i += K1_THREADS) (&sm.wcount[0][0])[i] = 0;
     if (tid == 0) { max_group = 0; n_const = 0; }
     __syncthreads();
 
     // ---- 1. stable LSD radix sort(s) --------------------------------------------------------
     uint32_t *kin = p.key_a, *kout = p.key_b, *iin = p.idx_a, *iout = p.idx_b;
+    if (T <= SMALL_T) { kin = s_sort[0]; kout = s_sort[1]; iin = s_sort[2]; iout = s_sort[3]; }
+    for (uint32_t i = tid; i < T; i += K1_THREADS) iin[i] = i;
     if (merge_dups) {
         for (uint32_t i = tid; i < T; i += K1_THREADS) kin[i] = (uint32_t)p.raw[i].z;
         __syncthreads();

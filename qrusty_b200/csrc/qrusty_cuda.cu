@@ -613,7 +613,7 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
     const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
     const uint64_t ctas = (rows + per_cta - 1) / per_cta;
     if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "apply: row window too large for one launch");
-    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, nullptr, 0u);
+    qr::apply_direct_kernel<false><<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, nullptr, 0u);
     QR_LAUNCH_CHECK("apply_direct_kernel");
     return QR_OK;
 }
@@ -760,18 +760,52 @@ extern "C" int qr_ax_device(uint64_t n, const double a[2], const double *x, doub
     return QR_OK;
 }
 
-extern "C" int qr_dotc_device(uint64_t n, const double *x, const double *y, double *d_out, void *stream)
+constexpr unsigned kReduceGrid = 148 * 8;
+static int reduce_scratch(double2 **out)                 // one scratch per host thread (and its device)
 {
-    if (!x || !y || !d_out) return fail(QR_ERR_INVALID, "qr_dotc_device: NULL argument");
-    static thread_local double2 *partials = nullptr;     // one scratch per host thread (and its device)
+    static thread_local double2 *partials = nullptr;
     static thread_local int partials_dev = -1;
     int dev = 0;
     QR_CUDA(cudaGetDevice(&dev));
-    const unsigned grid = 148 * 8;
     if (!partials || partials_dev != dev) {
-        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&partials), grid * sizeof(double2)));
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&partials), kReduceGrid * sizeof(double2)));
         partials_dev = dev;
     }
+    *out = partials;
+    return QR_OK;
+}
+
+extern "C" int qr_lanczos_update_device(uint64_t n, const double alpha[2], const double beta[2], const double *w,
+                                        const double *v, const double *v_prev, double *w_out, double *d_norm2_out,
+                                        void *stream)
+{
+    if (!alpha || !beta || !w || !v || !w_out || !d_norm2_out) return fail(QR_ERR_INVALID, "qr_lanczos_update_device: NULL argument");
+    double2 *partials = nullptr;
+    int rc = reduce_scratch(&partials);
+    if (rc != QR_OK) return rc;
+    qr::lanczos_update_kernel<<<kReduceGrid, 256, 0, as_stream(stream)>>>(
+        n, make_double2(alpha[0], alpha[1]), make_double2(beta[0], beta[1]), reinterpret_cast<const double2 *>(w),
+        reinterpret_cast<const double2 *>(v), reinterpret_cast<const double2 *>(v_prev),
+        reinterpret_cast<double2 *>(w_out), partials);
+    QR_LAUNCH_CHECK("lanczos_update_kernel");
+    // fold the partials; the result is (norm2, 0): only the first double is the caller's
+    static thread_local double2 *tmp = nullptr;
+    static thread_local int tmp_dev = -1;
+    int dev = 0;
+    QR_CUDA(cudaGetDevice(&dev));
+    if (!tmp || tmp_dev != dev) { QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&tmp), sizeof(double2))); tmp_dev = dev; }
+    qr::dotc_final_kernel<<<1, qr::DOT_THREADS, 0, as_stream(stream)>>>(kReduceGrid, partials, tmp);
+    QR_LAUNCH_CHECK("dotc_final_kernel");
+    QR_CUDA(cudaMemcpyAsync(d_norm2_out, tmp, sizeof(double), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return QR_OK;
+}
+
+extern "C" int qr_dotc_device(uint64_t n, const double *x, const double *y, double *d_out, void *stream)
+{
+    if (!x || !y || !d_out) return fail(QR_ERR_INVALID, "qr_dotc_device: NULL argument");
+    const unsigned grid = kReduceGrid;
+    double2 *partials = nullptr;
+    { int rc = reduce_scratch(&partials); if (rc != QR_OK) return rc; }
     qr::dotc_partial_kernel<<<grid, qr::DOT_THREADS, 0, as_stream(stream)>>>(
         n, reinterpret_cast<const double2 *>(x), reinterpret_cast<const double2 *>(y), partials);
     QR_LAUNCH_CHECK("dotc_partial_kernel");
@@ -914,7 +948,7 @@ extern "C" int qr_apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_sha
     QR_NCCL(nccl().AllReduce(cm->d_scratch, cm->d_scratch, 1, ncclDouble, ncclSum, cm->comm, st));
     const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
     const uint64_t ctas = (shard + per_cta - 1) / per_cta;
-    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(
+    qr::apply_direct_kernel<true><<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(
         pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag,
         cm->d_peers, m);
     QR_LAUNCH_CHECK("apply_direct_kernel(p2p)");

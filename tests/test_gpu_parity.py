@@ -423,6 +423,30 @@ def test_vector_ops_bit_exact():
         assert np.allclose(Q.axpy(1j, x, y), 1j * x + y) and np.allclose(Q.ax(1j, x), 1j * x)
 
 
+def test_lanczos_matches_numpy(fixtures):
+    """The device Lanczos loop (BASELINE config 4's measurement loop) against numpy on the oracle's CSR."""
+    import scipy.sparse as sps
+    from qrusty_b200 import lanczos as L
+    labels, coeffs = H.tfim_lattice(3, 4, 1.0, 3.0)                  # 12 qubits, Hermitian
+    n, params = O.make_params(labels, coeffs)
+    indptr, indices, data = O.build_csr(params, n)
+    A = sps.csr_matrix((data, indices.astype(np.int64), indptr.astype(np.int64)), shape=(1 << n, 1 << n))
+    res = L.lanczos(make_op(labels, coeffs), n_iter=30)
+    v = H.lanczos_start_vector(0, 1 << n); v /= np.linalg.norm(v)
+    v_prev, beta, al, be = np.zeros_like(v), 0.0, [], []
+    for _ in range(30):
+        w = A @ v
+        a = np.vdot(v, w).real
+        w = w - a * v - beta * v_prev
+        beta = np.linalg.norm(w)
+        al.append(a); be.append(beta)
+        v_prev, v = v, w / beta
+    assert np.allclose(res["alphas"], al, rtol=1e-9, atol=1e-9) and np.allclose(res["betas"], be, rtol=1e-9, atol=1e-9)
+    exact = np.linalg.eigvalsh(A.toarray())[0]
+    assert L.ritz_values(res["alphas"], res["betas"])[0] >= exact - 1e-9
+    assert res["hv_ms"] > 0 and res["iterations"] == 30
+
+
 def test_dotc():
     rng = np.random.default_rng(9)
     n = (1 << 18) + 17
