@@ -120,6 +120,11 @@ QR_API int qr_build_rows_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
 QR_API int qr_build_host(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
                   uint64_t *indptr, uint64_t *indices, double *data, uint32_t flags);
 
+/* rawio::write (qrusty/src/rawio.rs:128-148) of rows [row_lo,row_hi) as a (row_hi-row_lo) x 2^n CSR,
+ * streamed from the GPU in row windows (fill -> pinned staging -> pwrite at the section offsets): the
+ * matrix is never resident as a whole in HBM or in host memory.  Synchronous. */
+QR_API int qr_write_rawio(qr_plan *plan, uint64_t row_lo, uint64_t row_hi, const char *path);
+
 /* ---- matrix-free H.v: replaces build + rowwise::spmat_dot_densevec
  * (accel.rs:338-370) without reading a matrix.  d_v is the FULL vector
  * (complex128[dim]); d_y receives rows [row_lo,row_hi) (complex128[row_hi-row_lo]).
@@ -149,12 +154,28 @@ QR_API int qr_compact_rows_device(uint64_t n_rows, uint64_t n_groups, const uint
                            const double *d_data, double tol, const uint64_t *d_indptr,
                            uint64_t *d_indices_out, double *d_data_out, void *stream);
 
+/* Fused drop-zeros build: the CSR that csmatrix_eliminate_zeroes (util.rs:154-171) produces from
+ * rows [row_lo,row_hi) of the reference's build, without writing the explicit zeros first.
+ * qr_build_compact_count evaluates every (row, group) value in registers, counts the kept ones per
+ * row, prefix-scans the counts into d_indptr (u64[row_hi-row_lo+1], local, d_indptr[0] = 0) and
+ * returns the shard's nnz (synchronises).  qr_build_compact_fill then writes indices/data of the
+ * kept entries (u64[nnz], complex128[nnz]; global column ids, ascending inside a row). */
+QR_API int qr_build_compact_count(qr_plan *plan, uint64_t row_lo, uint64_t row_hi, double tol,
+                           uint64_t *d_indptr, uint64_t *nnz_out, void *stream);
+QR_API int qr_build_compact_fill(qr_plan *plan, uint64_t row_lo, uint64_t row_hi, double tol,
+                          const uint64_t *d_indptr, uint64_t *d_indices, double *d_data, void *stream);
+
 /* Lanczos/Davidson vector kernels (accel.rs:374-393): z = a*x + b*y, a*x + y, a*x. */
 QR_API int qr_axpby_device(uint64_t n, const double a[2], const double *d_x, const double b[2],
                     const double *d_y, double *d_z, void *stream);
 QR_API int qr_axpy_device(uint64_t n, const double a[2], const double *d_x, const double *d_y,
                    double *d_z, void *stream);
 QR_API int qr_ax_device(uint64_t n, const double a[2], const double *d_x, double *d_z, void *stream);
+/* Davidson preconditioner precond2 (pyqrusty/src/lib.rs:457-468, reg() at :436-440):
+ * d_out[i] = d_dx[i] / reg(d_diag[i] - e), reg(x) = (tol, 0) if |x| < tol else x.  precond
+ * (lib.rs:442-455) is the same on qr_diagonal_device's output. */
+QR_API int qr_precond2_device(uint64_t n, const double *d_diag, const double *d_dx, const double e[2],
+                       double tol, double *d_out, void *stream);
 /* <x,y> = sum conj(x_i) y_i  -> d_out[2] (numpy.vdot; the reference leaves this to numpy). */
 QR_API int qr_dotc_device(uint64_t n, const double *d_x, const double *d_y, double *d_out, void *stream);
 

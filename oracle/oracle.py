@@ -53,6 +53,8 @@ def lib():
         L.oracle_axpby.argtypes = [d, d, vp, d, d, vp, vp, C.c_size_t]
         L.oracle_axpy.argtypes = [d, d, vp, vp, vp, C.c_size_t]
         L.oracle_ax.argtypes = [d, d, vp, vp, C.c_size_t]
+        L.oracle_precond2.argtypes = [vp, vp, d, d, d, vp, C.c_size_t]
+        L.oracle_precond2.restype = None
         for f in (L.oracle_axpby, L.oracle_axpy, L.oracle_ax):
             f.restype = None
         _lib = L
@@ -186,6 +188,13 @@ def ax(a, x):
     return z
 
 
+def precond2(diag, dx, e, tol):
+    """pyqrusty/src/lib.rs:436-468: dx / reg(diag - e, tol)."""
+    diag, dx = _cv(diag), _cv(dx); out = np.empty_like(dx); e = complex(e)
+    lib().oracle_precond2(_p(diag), _p(dx), e.real, e.imag, float(tol), _p(out), len(dx))
+    return out
+
+
 def eliminate_zeros(indptr, indices, data, tolerance=1e-7):
     """util::csmatrix_eliminate_zeroes (qrusty/src/util.rs:154-171): keep entries with
     norm() > tolerance (norm = hypot), row-major order preserved; -> (indptr, indices, data)."""
@@ -199,3 +208,19 @@ def eliminate_zeros(indptr, indices, data, tolerance=1e-7):
 def count_zeros(data, tolerance=1e-7):
     """util::csmatrix_nz (util.rs:144-152)."""
     return int(np.count_nonzero(np.hypot(data.real, data.imag) <= tolerance))
+
+
+def rawio_bytes(shape, indptr, indices, data, byteorder="="):
+    """qrusty::rawio::write (rawio.rs:128-148) as bytes: native-endian "MI" mark (rawio.rs:59-68), u64
+    storage tag (0 = CSR), rows, cols, then indptr / indices / data each prefixed by its u64 length.
+    byteorder ">" / "<" forces the producer's endianness (to exercise the reader's swab path)."""
+    import sys
+    little = sys.byteorder == "little" if byteorder == "=" else byteorder == "<"
+    u8 = np.dtype("<u8" if little else ">u8")
+    c16 = np.dtype("<c16" if little else ">c16")
+    out = [b"MI" if little else b"IM"]              # u16::from_ne_bytes(['M','I']) written with to_ne_bytes
+    out.append(np.array([0, shape[0], shape[1], len(indptr)], u8).tobytes())
+    out.append(np.asarray(indptr).astype(u8).tobytes())
+    out.append(np.array([len(indices)], u8).tobytes()); out.append(np.asarray(indices).astype(u8).tobytes())
+    out.append(np.array([len(data)], u8).tobytes()); out.append(np.asarray(data).astype(c16).tobytes())
+    return b"".join(out)

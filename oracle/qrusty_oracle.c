@@ -30,6 +30,7 @@
  */
 #include <pthread.h>
 #include <stdatomic.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -380,6 +381,22 @@ void oracle_axpy(double ar, double ai, const c128 *x, const c128 *y, c128 *z, si
 { c128 a = { ar, ai }; for (size_t i = 0; i < n; i++) z[i] = cadd(cmul(a, x[i]), y[i]); }
 void oracle_ax(double ar, double ai, const c128 *x, c128 *z, size_t n)
 { c128 a = { ar, ai }; for (size_t i = 0; i < n; i++) z[i] = cmul(a, x[i]); }
+
+/* Davidson preconditioner, pyqrusty/src/lib.rs:436-468: reg() replaces |x| < tol (norm = hypot)
+ * by (tol, 0); precond2 returns dx / reg(diag - e).  Complex division as num-complex 0.4.1
+ * (Cargo.lock) spells it: re = (a.re*b.re + a.im*b.im) / |b|^2, im = (a.im*b.re - a.re*b.im) / |b|^2,
+ * |b|^2 = b.re*b.re + b.im*b.im. */
+void oracle_precond2(const c128 *diag, const c128 *dx, double er, double ei, double tol, c128 *out, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        c128 x = { diag[i].re - er, diag[i].im - ei };
+        if (hypot(x.re, x.im) < tol) { x.re = tol; x.im = 0.0; }
+        const double norm_sqr = x.re * x.re + x.im * x.im;
+        const double re = dx[i].re * x.re + dx[i].im * x.im;
+        const double im = dx[i].im * x.re - dx[i].re * x.im;
+        out[i].re = re / norm_sqr; out[i].im = im / norm_sqr;
+    }
+}
 
 int oracle_hardware_threads(void)
 {

@@ -3,7 +3,7 @@
 Same names, argument meaning and error behaviour as the reference's Python module
 (pyqrusty/src/lib.rs, pyqrusty/python/pyqrusty/__init__.py) for the hot path:
 
-    Pauli, SparsePauliOp, SpMat, csr_matrix, spmat_dot_densevec, axpby, axpy, ax
+    Pauli, SparsePauliOp, SpMat, csr_matrix, spmat_dot_densevec, axpby, axpy, ax, precond, precond2
 
 plus what the CUDA path adds: to_matrix_mode("Cuda") / ("Cuda/<ngpus>"), and the
 matrix-free SparsePauliOp.apply(v).  Every matrix is built by the CUDA kernels in
@@ -11,10 +11,11 @@ csrc/ through the C ABI of include/qrusty_cuda.h; there is no CPU implementation
 here, so the reference's CPU-strategy mode strings ("", "Rowwise", "RowwiseUnsafeChunked/n",
 ...) are accepted and executed by the same CUDA build -- they all denote the same matrix.
 
-Out of scope: MatrixMarket I/O, SpMat +/-/scale, a_spmat_p_b_spmat, precond.
+Out of scope: SpMat +/-/scale, a_spmat_p_b_spmat, the CPU build strategies.
 """
 import ctypes as C
 import re
+import sys
 
 import numpy as np
 
@@ -23,7 +24,7 @@ from ._ffi import QrustyCudaError, call, lib
 from ._runtime import DeviceBuffer, HostBuffer, PINNED, device_name, pinned_empty, synchronize
 
 __all__ = ["Pauli", "SparsePauliOp", "SpMat", "csr_matrix", "spmat_dot_densevec",
-           "axpby", "axpy", "ax", "QrustyCudaError"]
+           "axpby", "axpy", "ax", "precond", "precond2", "QrustyCudaError"]
 
 TERM_DTYPE = np.dtype([("z", "<u8"), ("x", "<u8"), ("re", "<f8"), ("im", "<f8")])   # == qr_term
 
@@ -361,6 +362,8 @@ class SpMat:
                 bufs.append(nb)
             c = _Shard(s.plan, s.lo, s.hi, *bufs, off=s.off, local=s.local)
             c.nnz = s.nnz
+            if getattr(s, "compacted", False):
+                c.compacted = True
             shards.append(c)
         return SpMat._from_shards(self._shape, shards)
 
@@ -379,9 +382,12 @@ class SpMat:
 
     # -- zero elimination (pyqrusty/src/lib.rs:170-183 -> util.rs:144-171) ------------------------
     def _kept(self, tolerance, compact):
-        """Per shard: count + scan (and optionally compact) on the device.  -> (kept, new shards)."""
-        shards = self.to_device()._live("cannot %s zeroes of an exported sparse matrix"
-                                        % ("eliminate" if compact else "count"))
+        """Per shard: count + scan (and optionally compact) on the device.  -> (kept, new shards).
+        A shard that has not been built yet takes the fused path (qr_build_compact_*): its values
+        are counted in registers and only the kept entries are ever written; a shard already
+        resident in HBM is counted and compacted in place (qr_count_kept / qr_compact_rows)."""
+        shards = self._live("cannot %s zeroes of an exported sparse matrix"
+                            % ("eliminate" if compact else "count"))
         kept_total, out = 0, []
         for s in shards:
             if s.plan is None or getattr(s, "compacted", False):
@@ -390,13 +396,21 @@ class SpMat:
             call("qr_set_device", s.device)
             indptr = DeviceBuffer((rows + 1) * 8, s.device)
             kept = C.c_uint64()
-            call("qr_count_kept_device", rows, G, s.data.ptr, float(tolerance), indptr.ptr, C.byref(kept), None)
+            fused = s.data is None
+            if fused:
+                call("qr_build_compact_count", s.plan.handle, s.lo, s.hi, float(tolerance), indptr.ptr, C.byref(kept), None)
+            else:
+                call("qr_count_kept_device", rows, G, s.data.ptr, float(tolerance), indptr.ptr, C.byref(kept), None)
             kept_total += kept.value
             if compact:
                 indices = DeviceBuffer(max(kept.value * 8, 16), s.device)
                 data = DeviceBuffer(max(kept.value * 16, 16), s.device)
-                call("qr_compact_rows_device", rows, G, s.indices.ptr, s.data.ptr, float(tolerance), indptr.ptr,
-                     indices.ptr, data.ptr, None)
+                if fused:
+                    call("qr_build_compact_fill", s.plan.handle, s.lo, s.hi, float(tolerance), indptr.ptr,
+                         indices.ptr, data.ptr, None)
+                else:
+                    call("qr_compact_rows_device", rows, G, s.indices.ptr, s.data.ptr, float(tolerance), indptr.ptr,
+                         indices.ptr, data.ptr, None)
                 c = _Shard(s.plan, s.lo, s.hi, indptr, indices, data, off=s.off, local=True)
                 c.nnz, c.compacted = kept.value, True
                 out.append(c)
@@ -425,6 +439,63 @@ class SpMat:
             call("qr_set_device", s.device)
             synchronize()
         return SpMat._from_shards(self._shape, shards)
+
+    # -- on-disk formats (rawio.rs:128-179; pyqrusty/src/lib.rs:216-259) -----------------------------
+    def rawio_write(self, path):
+        """qrusty::rawio::write (rawio.rs:128-148): "MI" mark, storage tag, shape, then the three
+        length-prefixed arrays.  A single plan-backed shard that was never built is streamed from the
+        GPU in row windows (qr_write_rawio); anything else is exported to the host first."""
+        shards = self._live("cannot write an already-destroyed sparse matrix")
+        if len(shards) == 1 and shards[0].data is None and shards[0].plan is not None:
+            s = shards[0]
+            call("qr_write_rawio", s.plan.handle, s.lo, s.hi, str(path).encode())
+            return
+        shape, data, indices, indptr = self.__copy__().export()
+        with open(path, "wb") as f:
+            f.write(b"MI" if sys.byteorder == "little" else b"IM")
+            np.array([0, shape[0], shape[1], len(indptr)], np.uint64).tofile(f)
+            indptr.tofile(f)
+            np.array([len(indices)], np.uint64).tofile(f); indices.tofile(f)
+            np.array([len(data)], np.uint64).tofile(f); data.tofile(f)
+
+    @staticmethod
+    def rawio_read(path, device=0):
+        """qrusty::rawio::read (rawio.rs:150-179), byte-swapping when the mark says so."""
+        with open(path, "rb") as f:
+            mark = f.read(2)
+            native = b"MI" if sys.byteorder == "little" else b"IM"
+            if mark not in (b"MI", b"IM"):
+                raise Exception("rawio_read: bad endian mark")
+            u8 = np.dtype(np.uint64) if mark == native else np.dtype(np.uint64).newbyteorder()
+            c16 = np.dtype(np.complex128) if mark == native else np.dtype(np.complex128).newbyteorder()
+            storage, rows, cols, n_ptr = (int(v) for v in np.fromfile(f, u8, 4))
+            if storage != 0:
+                raise Exception("rawio_read: only CSR storage is supported")      # rawio.rs:153-157 also has CSC
+            indptr = np.fromfile(f, u8, n_ptr).astype(np.uint64)
+            indices = np.fromfile(f, u8, int(np.fromfile(f, u8, 1)[0])).astype(np.uint64)
+            data = np.fromfile(f, c16, int(np.fromfile(f, u8, 1)[0])).astype(np.complex128)
+        return SpMat.new_unchecked((rows, cols), data, indices, indptr, device)
+
+    def matrixmarket_write(self, path):
+        """pyqrusty/src/lib.rs:216-230 (sprs::io::write_matrix_market): coordinate / complex / general,
+        one-based "row col re im" lines in storage order.  Text formatting is host work."""
+        shape, data, indices, indptr = self.__copy__().export()
+        rows = np.repeat(np.arange(shape[0], dtype=np.uint64), np.diff(indptr.astype(np.int64)))
+        with open(path, "w") as f:
+            f.write("%%MatrixMarket matrix coordinate complex general\n")
+            f.write("% written by qrusty_b200\n")
+            f.write("%d %d %d\n" % (shape[0], shape[1], len(data)))
+            for r, c, v in zip(rows.tolist(), indices.tolist(), data.tolist()):
+                f.write("%d %d %r %r\n" % (r + 1, c + 1, v.real, v.imag))
+
+    @staticmethod
+    def matrixmarket_read(path, device=0):
+        """pyqrusty/src/lib.rs:232-247: triplets -> CSR (duplicates summed, as TriMat::to_csr)."""
+        import scipy.io
+        import scipy.sparse
+        m = scipy.sparse.csr_matrix(scipy.io.mmread(str(path)), dtype=np.complex128)
+        m.sum_duplicates(); m.sort_indices()
+        return SpMat.new_unchecked(m.shape, m.data, m.indices.astype(np.uint64), m.indptr.astype(np.uint64), device)
 
     def to_device(self):
         """Materialise every shard in HBM (needed for SpMV on the stored matrix); returns self."""
@@ -541,3 +612,22 @@ def ax(a, x):
     """z = a*x (accel.rs:388-393)."""
     x = _vec(x)
     return _vec_op("qr_ax_device", len(x), [_c2(a)], [x])
+
+
+def precond2(diag, dx, e, tol):
+    """dx / reg(diag - e, tol) (pyqrusty/src/lib.rs:457-468, 579-591)."""
+    diag, dx = _vec(diag), _vec(dx)
+    if len(diag) != len(dx):
+        raise ValueError("precond2: diag and dx differ in length")
+    n = len(dx)
+    bd, bx, bz = DeviceBuffer(max(n * 16, 16)), DeviceBuffer(max(n * 16, 16)), DeviceBuffer(max(n * 16, 16))
+    bd.upload(diag); bx.upload(dx)
+    call("qr_precond2_device", n, bd.ptr, bx.ptr, _c2(e), float(tol), bz.ptr, None)
+    return bz.download(np.empty(n, np.complex128))
+
+
+def precond(spmat, dx, e, tol):
+    """dx / reg(spmat.diagonal() - e, tol) (pyqrusty/src/lib.rs:442-455, 564-577)."""
+    if spmat._shards is None:
+        raise Exception("cannot call precond with an exported sparse matrix")
+    return precond2(spmat.diagonal(), dx, e, tol)

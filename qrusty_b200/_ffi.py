@@ -56,15 +56,19 @@ SIGNATURES = {
     "qr_plan_canonicalise_async": [_vp, _vp],
     "qr_build_rows_device": [_vp, _u64, _u64, _vp, _vp, _vp, _u32, _vp],
     "qr_build_host": [_vp, _u64, _u64, _vp, _vp, _vp, _u32],
+    "qr_write_rawio": [_vp, _u64, _u64, C.c_char_p],
     "qr_apply_device": [_vp, _u64, _u64, _vp, _vp, _vp],
     "qr_apply_host": [_vp, _vp, _vp],
     "qr_diagonal_device": [_vp, _u64, _u64, _vp, _vp],
     "qr_spmv_device": [_u64, _vp, _vp, _vp, _vp, _vp, _vp],
     "qr_count_kept_device": [_u64, _u64, _vp, C.c_double, _vp, C.POINTER(_u64), _vp],
     "qr_compact_rows_device": [_u64, _u64, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp],
+    "qr_build_compact_count": [_vp, _u64, _u64, C.c_double, _vp, C.POINTER(_u64), _vp],
+    "qr_build_compact_fill": [_vp, _u64, _u64, C.c_double, _vp, _vp, _vp, _vp],
     "qr_axpby_device": [_u64, _dp, _vp, _dp, _vp, _vp, _vp],
     "qr_axpy_device": [_u64, _dp, _vp, _vp, _vp, _vp],
     "qr_ax_device": [_u64, _dp, _vp, _vp, _vp],
+    "qr_precond2_device": [_u64, _vp, _vp, _dp, C.c_double, _vp, _vp],
     "qr_dotc_device": [_u64, _vp, _vp, _vp, _vp],
     "qr_lanczos_update_device": [_u64, _dp, _dp, _vp, _vp, _vp, _vp, _vp, _vp],
     "qr_comm_unique_id": [_vp],

@@ -264,6 +264,25 @@ vec_axpby_kernel(uint64_t n, double2 a, const double2 *__restrict__ x, double2 b
     }
 }
 
+// Davidson preconditioner (pyqrusty/src/lib.rs:436-468): out = dx / reg(diag - e, tol), where reg()
+// replaces a denominator with norm() < tol by (tol, 0).  Division spelled as num-complex's (no FMA
+// contraction), so the result is bit-identical to the CPU for every element whose |diag - e| is not
+// within an ulp of tol.  32 B read + 16 B written per element.
+__global__ void __launch_bounds__(256)
+precond2_kernel(uint64_t n, const double2 *__restrict__ diag, const double2 *__restrict__ dx, double2 e, double tol,
+                double2 *__restrict__ out)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        const double2 d = diag[i], a = dx[i];
+        double xr = __dsub_rn(d.x, e.x), xi = __dsub_rn(d.y, e.y);
+        if (hypot(xr, xi) < tol) { xr = tol; xi = 0.0; }
+        const double norm_sqr = __dadd_rn(__dmul_rn(xr, xr), __dmul_rn(xi, xi));
+        const double re = __dadd_rn(__dmul_rn(a.x, xr), __dmul_rn(a.y, xi));
+        const double im = __dsub_rn(__dmul_rn(a.y, xr), __dmul_rn(a.x, xi));
+        out[i] = make_double2(__ddiv_rn(re, norm_sqr), __ddiv_rn(im, norm_sqr));
+    }
+}
+
 // Lanczos three-term update fused with the norm: w_out = w - alpha*v - beta*v_prev and
 // partial[b] = (sum |w_out|^2, 0) per CTA (folded by dotc_final_kernel).  One pass over three
 // vectors instead of two axpy passes and a dot product.

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
             c = upper_bound_u32(p.gx, G, lo | low) - lower_bound_u32(p.gx, G, lo);
         }
         p.cnt[q] = c;
+        p.cnt_t[b * T + g] = c;
     }
     for (uint32_t g = tid; g < G; g += K1_THREADS) {
         const uint32_t t0 = p.goff[g], t1 = p.goff[g + 1];

@@ -10,6 +10,7 @@
 //                        of scan.cuh: tile sums -> one CTA scans the sums -> tiles re-scanned
 //   compact_rows_kernel  warp per row: ballot + popc rank, entries written at indptr[row] + rank
 #pragma once
+#include "fill.cuh"
 #include "scan.cuh"
 #include <cuda_runtime.h>
 
@@ -19,7 +20,15 @@ constexpr int K2_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;                                // per thread
 constexpr int SCAN_TILE = K2_THREADS * SCAN_ITEMS;
 
-__device__ __forceinline__ bool keep_entry(double2 d, double tol) { return hypot(d.x, d.y) > tol; }
+// norm() > tol with norm = hypot(re, im) (util.rs:159).  max(|re|,|im|) <= hypot <= |re| + |im| decides
+// almost every entry (exact zeros, values far above tol) without evaluating hypot.
+__device__ __forceinline__ bool keep_entry(double2 d, double tol)
+{
+    const double a = fabs(d.x), b = fabs(d.y);
+    if (fmax(a, b) > tol) return true;
+    if (a + b <= tol) return false;
+    return hypot(d.x, d.y) > tol;
+}
 
 // counts[r + 1] = #{entries of row r with norm > tol}; counts[0] = 0.  CTA b owns rows [b*R, (b+1)*R).
 __global__ void __launch_bounds__(K2_THREADS)
@@ -105,6 +114,100 @@ compact_rows_kernel(uint64_t n_rows, uint32_t G, const uint64_t *__restrict__ in
                 const uint64_t pos = out + __popc(mask & ((1u << lane) - 1u));
                 data_out[pos] = d;
                 indices_out[pos] = indices_in[in0 + j];
+            }
+            out += __popc(mask);
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------
+// Fused drop-zeros build: the CSR util::csmatrix_eliminate_zeroes (util.rs:154-171) would
+// produce from the reference's build, without ever writing the explicit zeros.
+//   count_rows_kernel    evaluates every (row, group) value in registers, counts the kept
+//                        ones per row (no matrix traffic: 8 B written per row)
+//   scan_*               counts -> indptr (above)
+//   fill_compact_kernel  assembles a 32-row tile in shared memory in column order exactly as
+//                        fill_staged_kernel does, then each warp compacts whole rows:
+//                        ballot + popc rank, kept entries stored at indptr[row] + rank.
+//                        24 B written per KEPT entry.
+// ---------------------------------------------------------------------------------
+constexpr int COUNT_ROWS_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * COUNT_ROWS_WARPS)
+count_rows_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi, double tol, uint64_t *__restrict__ counts)
+{
+    constexpr int E = 2;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t base = row_lo + ((uint64_t)blockIdx.x * COUNT_ROWS_WARPS + warp) * (32u * E);
+    if (base >= row_hi) return;
+    uint32_t r[E], cnt[E];
+    bool live[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint64_t r64 = base + 32u * e + lane;
+        live[e] = r64 < row_hi;
+        r[e] = (uint32_t)(live[e] ? r64 : row_hi - 1);
+        cnt[e] = 0;
+    }
+    for (uint32_t g = 0; g < G; g++) {
+        const GroupDesc d = p.gdesc[g];
+        double ar[E], ai[E];
+        if (d.flag & 1u) {
+#pragma unroll
+            for (int e = 0; e < E; e++) { ar[e] = d.cre; ai[e] = d.cim; }
+        } else {
+            group_values<E>(p, d.t0, d.t1, r, ar, ai);
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) cnt[e] += keep_entry(make_double2(ar[e], ai[e]), tol) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++)
+        if (live[e]) counts[base + 32u * e + lane - row_lo + 1] = cnt[e];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
+}
+
+template <int GW>
+__global__ void __launch_bounds__(32 * GW)
+fill_compact_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, uint64_t row_hi, double tol,
+                    const uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices, double2 *__restrict__ data)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                          // 32*G * 16 B
+    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)32u * G * 16u);  // 32*G *  8 B
+    const uint32_t lane = threadIdx.x & 31u, gw = threadIdx.x >> 5;
+    const uint64_t tile_base = tile_row0 + (uint64_t)blockIdx.x * 32u;              // multiple of 32
+    const uint32_t tbase = (uint32_t)tile_base;
+    const uint32_t r[1] = {tbase + lane};
+    for (uint32_t g = gw; g < G; g += GW) {
+        const GroupDesc d = p.gdesc[g];
+        const uint32_t c = __ldg(&p.cnt[g * 32u + lane]);
+        const uint32_t lo = __ldg(&p.lr5[g * 32u + ((d.x ^ lane) & 31u)]);
+        double ar[1], ai[1];
+        if (d.flag & 1u) { ar[0] = d.cre; ai[0] = d.cim; }
+        else group_values<1>(p, d.t0, d.t1, r, ar, ai);
+        const uint32_t bit = ((d.x ^ tbase) >> lane) & 1u;
+        const uint32_t slot = __reduce_add_sync(0xffffffffu, (lane >= 5u && bit) ? c : 0u) + lo;
+        const uint32_t o = lane * G + slot;
+        sidx[o] = (uint64_t)(r[0] ^ d.x);
+        sdat[o] = make_double2(ar[0], ai[0]);
+    }
+    __syncthreads();
+    for (uint32_t l = gw; l < 32u; l += GW) {
+        const uint64_t row = tile_base + l;
+        if (row < row_lo || row >= row_hi) continue;                               // ragged first / last tile
+        uint64_t out = indptr[row - row_lo];
+        for (uint32_t j0 = 0; j0 < G; j0 += 32u) {
+            const uint32_t j = j0 + lane;
+            double2 d = make_double2(0.0, 0.0);
+            if (j < G) d = sdat[l * G + j];
+            const bool keep = j < G && keep_entry(d, tol);
+            const unsigned mask = __ballot_sync(FULL_MASK, keep);
+            if (keep) {
+                const uint64_t pos = out + __popc(mask & ((1u << lane) - 1u));
+                data[pos] = d;
+                indices[pos] = sidx[l * G + j];
             }
             out += __popc(mask);
         }

@@ -21,6 +21,7 @@
 //           bits < 5 come from lr5[g][(gx[g]^lane)&31].
 #pragma once
 #include "plan.cuh"
+#include "scan.cuh"
 
 namespace qr {
 
@@ -333,6 +334,196 @@ fill_blocked_kernel(PlanDev p, uint32_t G, uint32_t S, uint32_t n_blocks, uint32
         }
         __syncthreads();
     }
+}
+
+
+// ---------------------------------------------------------------------------------
+// Lanes kernel (large G, the default when whole rows do not fit in shared memory).
+//
+// lane <-> group: a warp owns 32 consecutive sorted groups and walks a run of R = 2^k
+// aligned rows in GRAY-CODE order.  Everything that depends only on the group -- mask,
+// up to NT (z, c') terms, the rank-table row -- lives in the lane's registers for the
+// whole run, and moving to the next row flips exactly one row bit b, so
+//     slot(r ^ 2^b, g) = slot(r, g) +- cnt[g][b]        (one IADD; the sign alternates)
+// and a row costs ~13 + 7*terms thread instructions per entry with no shared-memory
+// staging and no barrier.  The 32 entries a warp stores per row are the block's slots of
+// that row: consecutive sorted masks are a union of a few trie subtrees, each of which
+// fills one contiguous slot range in every row (XOR never splits a subtree), so one
+// STG.128 + one STG.64 per row cover a few contiguous segments (<= 512 B + 256 B).
+// All warps of a CTA -- and the sibling CTAs that own the other groups of the same rows,
+// adjacent in blockIdx -- walk the same row sequence, so the sectors shared by two
+// segments are completed in L2 within the warps' drift, long before they are evicted.
+//
+// Groups with more than NT terms ("heavy": the Z-only group of a molecular Hamiltonian,
+// a few dozen others) are left to heavy CTAs in the same grid: lane <-> row, one
+// (heavy group, 32-row strip) item per warp visit, warp-uniform term loop.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void st_global_f64x2(uintptr_t addr, double a, double b)
+{
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" :: "l"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_global_u64(uintptr_t addr, uint64_t v)
+{
+    asm volatile("st.global.u64 [%0], %1;" :: "l"(addr), "l"(v) : "memory");
+}
+
+constexpr int FILL_LANES_NT = 6;
+constexpr int FILL_LANES_MAXLOG2R = 12;
+
+template <int NT, int LW>
+__global__ void __launch_bounds__(32 * LW, 32 / LW)
+fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t n_heavy_ctas, uint32_t log2R, uint32_t resync,
+                  uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
+                  uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
+                  double2 *__restrict__ data, uint64_t indptr_last_row)
+{
+    __shared__ int32_t s_delta[LW][FILL_LANES_MAXLOG2R - 3][32];   // +-cnt[g][b] for the row bits b >= 3
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t per_range = n_light + n_heavy_ctas;
+    const uint32_t rho = blockIdx.x / per_range, beta = blockIdx.x % per_range;
+    const uint32_t R = 1u << log2R;
+    const uint64_t r0_64 = tile_row0 + (uint64_t)rho * R;          // first row of the run (aligned to R)
+    const uint32_t r0 = (uint32_t)r0_64;
+    double2 *const dbase = data + (r0_64 - row_lo) * G;
+    uint64_t *const ibase = indices + (r0_64 - row_lo) * G;
+
+    if (beta >= n_light) {
+        // ---- heavy CTA: items (heavy group h, strip s), lane <-> row ---------------------------
+        const uint32_t nh = __ldg(&p.meta[6]);
+        const uint32_t strips = R >> 5;
+        const uint32_t n_items = nh * strips;
+        for (uint32_t q = (beta - n_light) * LW + warp; q < n_items; q += n_heavy_ctas * LW) {
+            const uint32_t g = __ldg(&p.heavy[q / strips]), s = q % strips;
+            const GroupDesc d = p.gdesc[g];
+            const uint32_t wbase = r0 + 32u * s, r = wbase + lane;
+            const uint32_t slot = group_slot(p, g, d.x, wbase, lane);
+            const double2 v = (d.flag & 1u) ? make_double2(d.cre, d.cim) : group_value(p.tz, p.tc, d.t0, d.t1, r);
+            const uint32_t off = (32u * s + lane) * G + slot;
+            dbase[off] = v;
+            ibase[off] = (uint64_t)(r ^ d.x);
+        }
+        return;
+    }
+
+    if (beta == 0 && indptr != nullptr) {
+        for (uint32_t i = threadIdx.x; i < R; i += 32 * LW) {
+            const uint64_t lr = r0_64 + i - row_lo;
+            indptr[lr] = indptr_base + lr * G;
+            if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+        }
+    }
+
+    // ---- light CTA: warp <-> block of 32 groups, lane <-> group ---------------------------------
+    const uint32_t g = (beta * LW + warp) * 32u + lane;
+    if ((beta * LW + warp) * 32u >= G) {                          // warp-uniform: no groups left for this warp
+        if (resync) for (uint32_t i = 32u; i < R; i += 32u) __syncthreads();
+        return;
+    }
+    uint32_t x = 0, nt = 0, t0 = 0;
+    if (g < G) { const GroupDesc d = p.gdesc[g]; x = d.x; nt = d.t1 - d.t0; t0 = d.t0; }
+    const bool active = g < G && nt <= (uint32_t)NT;
+    if (!active) nt = 0;
+    // terms beyond the lane's own are padded with (z = 0, c' = -0.0): x + (-0.0) == x for every x,
+    // signed zeros included, so padding never needs a predicate
+    uint32_t z[NT];
+    double cr[NT], ci[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        z[t] = 0u; cr[t] = -0.0; ci[t] = -0.0;
+        if ((uint32_t)t < nt) { z[t] = __ldg(&p.tz[t0 + t]); const double2 c = __ldg(&p.tc[t0 + t]); cr[t] = c.x; ci[t] = c.y; }
+    }
+    const uint32_t nt_max = __reduce_max_sync(0xffffffffu, nt);
+    // entry offset (in entries, relative to the run's first row) at the first row of the run, and
+    // the signed step for every row bit of the run.  Flipping row bit b moves the row by +-2^b (the
+    // offset by +-G*2^b) and the slot by +-cnt[g][b]; both signs alternate with every flip of b, so
+    // one signed step per (lane, bit) carries both.  R*G*16 < 2^32 (host-checked): 32-bit byte offsets.
+    uint32_t off = 0;
+    int32_t d0 = 0, d1 = 0, d2 = 0;
+    {
+        const uint32_t nq = (uint32_t)p.n_qubits, T = p.n_terms, gg = g < G ? g : G - 1u;
+#pragma unroll
+        for (uint32_t b0 = 0; b0 < 32u; b0 += 8u) {
+            if (b0 >= nq) break;
+            uint32_t c[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; j++) c[j] = b0 + j < nq ? __ldg(&p.cnt_t[(b0 + j) * T + gg]) : 0u;   // coalesced, independent
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; j++) {
+                const uint32_t b = b0 + j;
+                const bool one = ((x ^ r0) >> b) & 1u;
+                if (one) off += c[j];
+                // r0 is aligned to R: its bits < log2R are 0, the first flip of b moves the row up
+                const int32_t step = (one ? -(int32_t)c[j] : (int32_t)c[j]) + (int32_t)(G << b);
+                if (b == 0) d0 = step; else if (b == 1) d1 = step; else if (b == 2) d2 = step;
+                else if (b < (uint32_t)FILL_LANES_MAXLOG2R && b < log2R) s_delta[warp][b - 3][lane] = step;
+            }
+        }
+    }
+    __syncwarp();
+    const uintptr_t dptr = reinterpret_cast<uintptr_t>(dbase), iptr = reinterpret_cast<uintptr_t>(ibase);
+
+    uint32_t r = r0;                                               // warp-uniform current row
+    // +-1.0 from the parity of r & z: (+-1.0) * c' and fma(+-1.0, c', acc) are exactly the sign flip
+    // and the __dadd_rn of the reference fold (accel.rs:191-205), signed zeros included
+    auto sign_of = [](uint32_t m) { return __hiloint2double((int)(0x3ff00000u | ((uint32_t)__popc(m) << 31)), 0); };
+    auto emit = [&]() {
+        const double s0 = sign_of(r & z[0]);
+        double re = __dmul_rn(s0, cr[0]), im = __dmul_rn(s0, ci[0]);
+#pragma unroll
+        for (int t = 1; t < NT; t++) {
+            if ((uint32_t)t < nt_max) {                            // warp-uniform
+                const double sg = sign_of(r & z[t]);
+                re = __fma_rn(sg, cr[t], re); im = __fma_rn(sg, ci[t], im);
+            }
+        }
+        if (active) {
+            st_global_f64x2(dptr + ((size_t)off << 4), re, im);
+            st_global_u64(iptr + ((size_t)off << 3), (uint64_t)(r ^ x));
+        }
+    };
+    for (uint32_t i = 0; i < R; i += 8u) {
+        if (i != 0u) {                                             // Gray code: step i flips bit ctz(i) >= 3
+            if (resync && (i & 31u) == 0u) __syncthreads();        // keep the CTA's warps on the same rows
+            const uint32_t b = (uint32_t)__ffs((int)i) - 1u;
+            r ^= 1u << b;
+            const int32_t st = s_delta[warp][b - 3][lane];
+            off += (uint32_t)st;
+            s_delta[warp][b - 3][lane] = -st;
+        }
+        emit();
+        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+        r ^= 2u; off += (uint32_t)d1; d1 = -d1; emit();
+        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+        r ^= 4u; off += (uint32_t)d2; d2 = -d2; emit();
+        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+        r ^= 2u; off += (uint32_t)d1; d1 = -d1; emit();
+        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+    }
+}
+
+// K1c: the groups the lanes kernel leaves to its heavy CTAs (more than NT terms), in ascending
+// order: heavy[0..meta[6]); meta[7] = their total number of terms.  One CTA, CTA scan.
+__global__ void __launch_bounds__(512, 1) classify_kernel(PlanDev p, uint32_t nt_light)
+{
+    __shared__ uint32_t scan_scratch[33];
+    __shared__ uint32_t heavy_terms;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t G = p.meta[0];
+    if (tid == 0) heavy_terms = 0;
+    __syncthreads();
+    uint32_t carry = 0;
+    for (uint32_t tile = 0; tile < G; tile += 512u) {
+        const uint32_t g = tile + tid;
+        uint32_t n = 0;
+        if (g < G) n = p.goff[g + 1] - p.goff[g];
+        const uint32_t h = n > nt_light ? 1u : 0u;
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan(h, scan_scratch, &total);
+        if (h) { p.heavy[carry + excl] = g; atomicAdd(&heavy_terms, n); }
+        carry += total;
+    }
+    __syncthreads();
+    if (tid == 0) { p.meta[6] = carry; p.meta[7] = heavy_terms; }
 }
 
 }  // namespace qr

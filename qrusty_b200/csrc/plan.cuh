@@ -17,12 +17,15 @@ namespace qr {
 //   gx    u32[G]          distinct X-masks, ascending
 //   goff  u32[G+1]        group g owns sorted terms [goff[g], goff[g+1])
 //   cnt   u32[G][32]      cnt[g][b] = #{h != g : msb(gx[g]^gx[h]) == b}
+//   cnt_t u32[32][T]      cnt transposed (cnt_t[b*T + g]): lane <-> group kernels read it coalesced
 //   lr5   u32[G][32]      lr5[g][j] = sum_{b<5} cnt[g][b] * bit_b(j)
 //   gflag u32[G]          bit0: every term of the group has z == 0 (value is row-independent)
 //                         bit1: every c' of the group is real (im == +-0)
 //   gconst double2[G]     the group's ordered sum of c' (its value when bit0 is set)
 //   gdesc GroupDesc[G]    {x, flag, t0, t1, gconst} packed in 32 B for the H.v kernels
-//   meta  u32[8]          {G, max terms in a group, B, S, #row-independent groups, #terms after merging, 0, 0}
+//   meta  u32[8]          {G, max terms in a group, B, S, #row-independent groups, #terms after merging,
+//                          #heavy groups, their total terms}
+//   heavy u32[<=G]        large-G path: ids of the groups with more terms than a lane keeps in registers
 //   blk_start u32[B+1]    large-G path: the sorted groups cut into B trie subtrees ("blocks")
 //   blk_p     u32[B]      of <= S groups; block b = groups [blk_start[b], blk_start[b+1]), all
 //                         sharing the mask bits >= blk_p[b] (>= 5).  A subtree's groups fill
@@ -55,6 +58,8 @@ struct PlanDev {
     uint32_t *meta;
     uint32_t *blk_start;
     uint32_t *blk_p;
+    uint32_t *heavy;
+    uint32_t *cnt_t;
 };
 
 }  // namespace qr

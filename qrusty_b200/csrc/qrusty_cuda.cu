@@ -5,7 +5,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cerrno>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <new>
 #include <map>
 #include <string>
@@ -72,6 +75,9 @@ struct qr_plan {
     // fill configuration chosen from G: staged whole-row tiles (rw,gw) or subtree blocks
     int rw = 0, gw = 0;
     uint32_t block_s = 0, n_blocks = 0;    // blocked kernel: S and the number of subtree blocks
+    // lanes kernel (large G, default): rows per run = 2^lanes_log2r, warps per CTA, heavy groups
+    int lanes = 0, lanes_log2r = 0, lanes_warps = 0, lanes_nt = 0, lanes_resync = 0;
+    uint32_t n_heavy = 0, heavy_terms = 0;
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -130,6 +136,17 @@ void choose_staged(qr_plan *pl)
     pl->rw = pl->gw = 0;
     const uint64_t G = pl->n_groups;
     pl->block_s = 0;
+    pl->lanes = 0;
+    pl->lanes_log2r = 8; pl->lanes_warps = 8;
+    if (const char *env = getenv("QR_FILL_LANES_R")) { int k = atoi(env); if (k >= 5 && k <= qr::FILL_LANES_MAXLOG2R) pl->lanes_log2r = k; }
+    if (const char *env = getenv("QR_FILL_LANES_W")) { int w = atoi(env); if (w == 8 || w == 16 || w == 32) pl->lanes_warps = w; }
+    // terms a lane keeps in registers: 2 when nearly every group is that short (fewer registers, more
+    // resident warps), else 6; longer groups go to the heavy CTAs
+    pl->lanes_nt = pl->n_terms <= pl->n_groups + pl->n_groups / 2 ? 2 : qr::FILL_LANES_NT;
+    if (const char *env = getenv("QR_FILL_LANES_NT")) { int t = atoi(env); if (t == 2 || t == qr::FILL_LANES_NT) pl->lanes_nt = t; }
+    pl->lanes_resync = 0;
+    if (const char *env = getenv("QR_FILL_LANES_SYNC")) pl->lanes_resync = env[0] == '1';
+    if (const char *env = getenv("QR_FILL_LANES")) if (env[0] == '1') { pl->lanes = 1; return; }   // force (tests, sweeps)
     if (const char *env = getenv("QR_FILL_BLOCK")) {         // "S" override: force the blocked kernel
         int S = atoi(env);
         if (S >= 32 && blocked_smem(S, 2) <= MAX_SMEM) { pl->block_s = (uint32_t)S; return; }
@@ -147,9 +164,11 @@ void choose_staged(qr_plan *pl)
     else if (64 * row_bytes <= 113 * 1024)    { pl->rw = 2; pl->gw = 8; }   // 2+ CTAs/SM
     else if (32 * row_bytes <= 113 * 1024)    { pl->rw = 1; pl->gw = 8; }
     else {
-        // whole rows do not fit (twice): subtree blocks of <= 32 groups.  Measured
-        // (profiles/r01_fill_sweep_largeG.jsonl): C3 4.52 TB/s at S=32, 3.73 at 64, 2.08 at 128.
-        pl->block_s = 32;
+        // whole rows do not fit (twice) in shared memory: the lanes kernel (lane <-> group, rows in
+        // Gray-code order).  QR_FILL_LANES=0 falls back to subtree blocks of <= 32 groups through
+        // shared memory (profiles/r01_fill_sweep_largeG.jsonl: C3 4.52 TB/s at S=32, 3.73 at 64).
+        pl->lanes = 1;
+        if (const char *env = getenv("QR_FILL_LANES")) if (env[0] == '0') { pl->lanes = 0; pl->block_s = 32; }
     }
 }
 
@@ -177,6 +196,11 @@ static int run_canonicalise(qr_plan *pl, cudaStream_t st)
 
 static int run_partition(qr_plan *pl, cudaStream_t st)
 {
+    if (pl->lanes) {
+        qr::classify_kernel<<<1, 512, 0, st>>>(pl->dev, (uint32_t)pl->lanes_nt);
+        QR_LAUNCH_CHECK("classify_kernel");
+        return QR_OK;
+    }
     if (!pl->block_s) return QR_OK;
     qr::partition_kernel<<<1, qr::K1_THREADS, 0, st>>>(pl->dev, pl->block_s);
     QR_LAUNCH_CHECK("partition_kernel");
@@ -214,6 +238,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     const size_t o_cnt = carve(T * 128), o_lr5 = carve(T * 128), o_meta = carve(32);
     const size_t o_bs = carve((T + 1) * 4), o_bp = carve(T * 4);
     const size_t o_gf = carve(T * 4), o_gc = carve(T * 16), o_gd = carve(T * sizeof(qr::GroupDesc));
+    const size_t o_hv = carve(T * 4), o_ct = carve(T * 128);
     cudaError_t e = cudaMalloc(&pl->slab, off);
     if (e != cudaSuccess) { delete pl; return fail(QR_ERR_OOM, std::string("qr_plan_create: cudaMalloc: ") + cudaGetErrorString(e)); }
     char *b = static_cast<char *>(pl->slab);
@@ -230,6 +255,8 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     d.blk_start = reinterpret_cast<uint32_t *>(b + o_bs); d.blk_p = reinterpret_cast<uint32_t *>(b + o_bp);
     d.gflag = reinterpret_cast<uint32_t *>(b + o_gf); d.gconst = reinterpret_cast<double2 *>(b + o_gc);
     d.gdesc = reinterpret_cast<qr::GroupDesc *>(b + o_gd);
+    d.heavy = reinterpret_cast<uint32_t *>(b + o_hv);
+    d.cnt_t = reinterpret_cast<uint32_t *>(b + o_ct);
 
     auto bail = [&](int code) { cudaFree(pl->slab); delete pl; return code; };
     e = cudaMemcpy(b + o_raw, terms, T * sizeof(qr_term), cudaMemcpyHostToDevice);
@@ -245,6 +272,13 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     pl->n_terms_canonical = meta[5];
     if (pl->n_groups == 0 || pl->n_groups > T) return bail(fail(QR_ERR_CUDA, "qr_plan_create: canonicalisation produced no groups"));
     choose_staged(pl);
+    if (pl->lanes) {
+        rc = run_partition(pl, nullptr);
+        if (rc != QR_OK) return bail(rc);
+        e = cudaMemcpy(meta, d.meta, sizeof(meta), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: classify: ") + cudaGetErrorString(e)));
+        pl->n_heavy = meta[6]; pl->heavy_terms = meta[7];
+    }
     if (pl->block_s) {
         rc = run_partition(pl, nullptr);
         if (rc != QR_OK) return bail(rc);
@@ -337,6 +371,40 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
     const uint64_t G = pl->n_groups;
     const uint64_t indptr_base = (flags & QR_INDPTR_GLOBAL) ? row_lo * G : 0;
     uint64_t lo = row_lo, hi = row_hi;
+    if (!(flags & QR_FILL_DIRECT) && pl->lanes) {
+        int k = pl->lanes_log2r;
+        while (k > 5 && align_up(row_lo, 1ull << k) + (1ull << k) > row_hi) k--;     // short windows: shorter runs
+        while (k > 5 && (G << k) >= (1ull << 28)) k--;                                // 32-bit byte offsets inside a run
+        const uint64_t R = 1ull << k;
+        const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
+        if (s1 > s0 && (G << k) < (1ull << 28)) {
+            const uint32_t LW = (uint32_t)pl->lanes_warps;
+            const uint32_t n_light = (uint32_t)((G + 32ull * LW - 1) / (32ull * LW));
+            // heavy CTAs per row range: one warp visit of a heavy group costs about as much per term as a
+            // light lane does per entry, so size them for roughly the work of a light CTA
+            uint32_t n_heavy_ctas = 0;
+            if (pl->n_heavy) n_heavy_ctas = (uint32_t)std::max<uint64_t>(1, (pl->heavy_terms + 160ull * LW - 1) / (160ull * LW));
+            const uint64_t ctas = (s1 - s0) / R * (n_light + n_heavy_ctas);
+            if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_lanes: row window too large for one launch");
+            int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+            if (rc != QR_OK) return rc;
+            using LanesFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t,
+                                     uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
+            LanesFn kern;
+            if (pl->lanes_nt == 2)
+                kern = LW == 16 ? (LanesFn)qr::fill_lanes_kernel<2, 16> : LW == 32 ? (LanesFn)qr::fill_lanes_kernel<2, 32>
+                                                                                   : (LanesFn)qr::fill_lanes_kernel<2, 8>;
+            else
+                kern = LW == 16 ? (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 16>
+                     : LW == 32 ? (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 32>
+                                : (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 8>;
+            kern<<<(unsigned)ctas, 32 * LW, 0, st>>>(pl->dev, (uint32_t)G, n_light, n_heavy_ctas, (uint32_t)k,
+                                                     (uint32_t)pl->lanes_resync, s0, row_lo, indptr_base, d_indptr, d_indices,
+                                                     d_data, row_hi - row_lo);
+            QR_LAUNCH_CHECK("fill_lanes_kernel");
+            return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+        }
+    }
     if (!(flags & QR_FILL_DIRECT) && pl->block_s) {
         const uint64_t s0 = align_up(row_lo, 32), s1 = row_hi / 32 * 32;
         if (s1 > s0) {
@@ -442,6 +510,88 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
         const uint64_t base = row_lo * G;
         if (base) for (uint64_t i = 0; i <= rows; i++) indptr[i] -= base;
     }
+    return QR_OK;
+}
+
+// rawio::write (qrusty/src/rawio.rs:128-148) streamed from the GPU: the file is
+//   "MI" (native-endian u16 mark, rawio.rs:59-68) | u64 storage (0 = CSR) | u64 rows | u64 cols |
+//   u64 len, indptr u64[] | u64 len, indices u64[] | u64 len, data complex128[]
+// Every section's offset is known up front (nnz = G * rows), so row windows are filled on the
+// device, copied to pinned staging on two streams and written with pwrite at their final offsets;
+// the matrix is never resident as a whole on either side.
+extern "C" int qr_write_rawio(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const char *path)
+{
+    if (!pl || !path) return fail(QR_ERR_INVALID, "qr_write_rawio: NULL argument");
+    if (row_lo >= row_hi || row_hi > pl->dim) return fail(QR_ERR_INVALID, "qr_write_rawio: bad row range");
+    QR_CUDA(cudaSetDevice(pl->device));
+    const uint64_t G = pl->n_groups, rows = row_hi - row_lo, nnz = rows * G;
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(QR_ERR_INVALID, std::string("qr_write_rawio: cannot open ") + path + ": " + strerror(errno));
+    auto put = [&](const void *buf, size_t bytes, uint64_t off) {
+        const char *b = static_cast<const char *>(buf);
+        while (bytes) {
+            const ssize_t w = pwrite(fd, b, bytes, (off_t)off);
+            if (w <= 0) return false;
+            b += w; off += (uint64_t)w; bytes -= (size_t)w;
+        }
+        return true;
+    };
+    const unsigned char mark_bytes[2] = {'M', 'I'};                 // u16::from_ne_bytes(['M','I']).to_ne_bytes()
+    const uint64_t o_ptr = 2 + 4 * 8, o_idx = o_ptr + (rows + 1) * 8 + 8, o_dat = o_idx + nnz * 8 + 8;
+    const uint64_t head[4] = {0 /* CSR */, rows, pl->dim, rows + 1};
+    bool ok = put(mark_bytes, 2, 0) && put(head, sizeof(head), 2);
+    ok = ok && put(&nnz, 8, o_idx - 8) && put(&nnz, 8, o_dat - 8);
+
+    uint64_t win = std::max<uint64_t>(32, (64ull << 20) / (G * 24 + 8) / 32 * 32);
+    if (win > rows) win = rows;
+    const size_t dat_b = align_up(win * G * 16, 256), idx_b = align_up(win * G * 8, 256), ptr_b = align_up((win + 1) * 8, 256);
+    void *dbuf[2] = {nullptr, nullptr}, *hbuf[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaMalloc(&dbuf[i], dat_b + idx_b + ptr_b);
+        if (e == cudaSuccess) e = cudaMallocHost(&hbuf[i], dat_b + idx_b + ptr_b);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    }
+    int rc = e == cudaSuccess ? QR_OK : fail(QR_ERR_OOM, std::string("qr_write_rawio: ") + cudaGetErrorString(e));
+    struct Win { uint64_t w0 = 0, n = 0; bool live = false; } pending[2];
+    auto flush = [&](int k) {                                       // window k: wait for its copy, write it out
+        if (!pending[k].live) return true;
+        pending[k].live = false;
+        if (cudaStreamSynchronize(st[k]) != cudaSuccess) return false;
+        char *h = static_cast<char *>(hbuf[k]);
+        const uint64_t w0 = pending[k].w0, n = pending[k].n, o = (w0 - row_lo) * G;
+        const bool last = w0 + n == row_hi;
+        if (row_lo) {                                               // the file's indptr starts at 0
+            uint64_t *ip = reinterpret_cast<uint64_t *>(h + dat_b + idx_b);
+            for (uint64_t i = 0; i <= n; i++) ip[i] -= row_lo * G;
+        }
+        return put(h, n * G * 16, o_dat + o * 16) && put(h + dat_b, n * G * 8, o_idx + o * 8) &&
+               put(h + dat_b + idx_b, (n + (last ? 1 : 0)) * 8, o_ptr + (w0 - row_lo) * 8);
+    };
+    int k = 0;
+    for (uint64_t w0 = row_lo; w0 < row_hi && rc == QR_OK && ok; w0 += win, k ^= 1) {
+        ok = flush(k);
+        if (!ok) break;
+        const uint64_t n = std::min(win, row_hi - w0);
+        char *d = static_cast<char *>(dbuf[k]);
+        rc = build_rows(pl, w0, w0 + n, reinterpret_cast<uint64_t *>(d + dat_b + idx_b), reinterpret_cast<uint64_t *>(d + dat_b),
+                        reinterpret_cast<double2 *>(d), QR_INDPTR_GLOBAL, st[k]);
+        if (rc != QR_OK) break;
+        e = cudaMemcpyAsync(hbuf[k], dbuf[k], dat_b + idx_b + (n + 1) * 8, cudaMemcpyDeviceToHost, st[k]);
+        if (e != cudaSuccess) { rc = fail(QR_ERR_CUDA, std::string("qr_write_rawio: D2H: ") + cudaGetErrorString(e)); break; }
+        pending[k].w0 = w0; pending[k].n = n; pending[k].live = true;
+    }
+    // the windows still in flight, in submission order
+    for (int j = 0; j < 2 && rc == QR_OK && ok; j++) { ok = flush(k); k ^= 1; }
+    for (int i = 0; i < 2; i++) {
+        if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+        if (dbuf[i]) cudaFree(dbuf[i]);
+        if (hbuf[i]) cudaFreeHost(hbuf[i]);
+    }
+    if (close(fd) != 0) ok = false;
+    if (rc != QR_OK) return rc;
+    if (!ok) return fail(QR_ERR_INVALID, std::string("qr_write_rawio: write to ") + path + " failed: " + strerror(errno));
     return QR_OK;
 }
 
@@ -675,6 +825,26 @@ extern "C" int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const u
 // =====================================================================================
 // K2: count + scan + compaction (eliminate_zeros)
 // =====================================================================================
+// counts in d_indptr[1..rows] (d_indptr[0] = 0) -> inclusive prefix sums in place; total -> *nnz_out
+static int scan_counts(uint64_t n_rows, uint64_t *d_indptr, uint64_t *nnz_out, cudaStream_t st, const char *who)
+{
+    const uint64_t n_tiles = (n_rows + qr::SCAN_TILE - 1) / qr::SCAN_TILE;
+    uint64_t *d_tiles = nullptr;
+    QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_tiles), (n_tiles + 1) * 8));
+    qr::scan_tile_sums_kernel<<<(unsigned)n_tiles, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr, d_tiles);
+    g_launches.fetch_add(1);
+    qr::scan_tile_offsets_kernel<<<1, qr::K2_THREADS, 0, st>>>(n_tiles, d_tiles, d_tiles + n_tiles);
+    g_launches.fetch_add(1);
+    qr::scan_apply_kernel<<<(unsigned)n_tiles, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr, d_tiles);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nnz_out, d_tiles + n_tiles, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_tiles);
+    if (e != cudaSuccess) return fail(QR_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+    return QR_OK;
+}
+
 extern "C" int qr_count_kept_device(uint64_t n_rows, uint64_t G, const double *d_data, double tol,
                                     uint64_t *d_indptr_out, uint64_t *nnz_out, void *stream)
 {
@@ -688,21 +858,7 @@ extern "C" int qr_count_kept_device(uint64_t n_rows, uint64_t G, const double *d
     qr::count_kept_kernel<<<(unsigned)ctas, qr::K2_THREADS, R * 4, st>>>(
         n_rows, (uint32_t)G, R, reinterpret_cast<const double2 *>(d_data), tol, d_indptr_out);
     QR_LAUNCH_CHECK("count_kept_kernel");
-    const uint64_t n_tiles = (n_rows + qr::SCAN_TILE - 1) / qr::SCAN_TILE;
-    uint64_t *d_tiles = nullptr;
-    QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_tiles), (n_tiles + 1) * 8));
-    qr::scan_tile_sums_kernel<<<(unsigned)n_tiles, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr_out, d_tiles);
-    g_launches.fetch_add(1);
-    qr::scan_tile_offsets_kernel<<<1, qr::K2_THREADS, 0, st>>>(n_tiles, d_tiles, d_tiles + n_tiles);
-    g_launches.fetch_add(1);
-    qr::scan_apply_kernel<<<(unsigned)n_tiles, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr_out, d_tiles);
-    g_launches.fetch_add(1);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(nnz_out, d_tiles + n_tiles, 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_tiles);
-    if (e != cudaSuccess) return fail(QR_ERR_CUDA, std::string("qr_count_kept_device: ") + cudaGetErrorString(e));
-    return QR_OK;
+    return scan_counts(n_rows, d_indptr_out, nnz_out, st, "qr_count_kept_device");
 }
 
 extern "C" int qr_compact_rows_device(uint64_t n_rows, uint64_t G, const uint64_t *d_indices, const double *d_data,
@@ -719,6 +875,64 @@ extern "C" int qr_compact_rows_device(uint64_t n_rows, uint64_t G, const uint64_
         reinterpret_cast<double2 *>(d_data_out));
     QR_LAUNCH_CHECK("compact_rows_kernel");
     return QR_OK;
+}
+
+extern "C" int qr_build_compact_count(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, double tol,
+                                      uint64_t *d_indptr, uint64_t *nnz_out, void *stream)
+{
+    if (!pl || !d_indptr || !nnz_out) return fail(QR_ERR_INVALID, "qr_build_compact_count: NULL argument");
+    if (row_lo >= row_hi || row_hi > pl->dim) return fail(QR_ERR_INVALID, "qr_build_compact_count: bad row range");
+    QR_CUDA(cudaSetDevice(pl->device));
+    cudaStream_t st = as_stream(stream);
+    const uint64_t rows = row_hi - row_lo, per_cta = 64ull * qr::COUNT_ROWS_WARPS;
+    const uint64_t ctas = (rows + per_cta - 1) / per_cta;
+    if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "qr_build_compact_count: row window too large for one launch");
+    qr::count_rows_kernel<<<(unsigned)ctas, 32 * qr::COUNT_ROWS_WARPS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, tol, d_indptr);
+    QR_LAUNCH_CHECK("count_rows_kernel");
+    return scan_counts(rows, d_indptr, nnz_out, st, "qr_build_compact_count");
+}
+
+extern "C" int qr_build_compact_fill(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, double tol,
+                                     const uint64_t *d_indptr, uint64_t *d_indices, double *d_data, void *stream)
+{
+    if (!pl || !d_indptr || !d_indices || !d_data) return fail(QR_ERR_INVALID, "qr_build_compact_fill: NULL argument");
+    if (row_lo >= row_hi || row_hi > pl->dim) return fail(QR_ERR_INVALID, "qr_build_compact_fill: bad row range");
+    QR_CUDA(cudaSetDevice(pl->device));
+    cudaStream_t st = as_stream(stream);
+    const uint64_t G = pl->n_groups, rows = row_hi - row_lo;
+    const size_t smem = (size_t)32 * G * 24;
+    if (smem <= MAX_SMEM) {
+        const uint64_t t0 = row_lo / 32 * 32, tiles = (row_hi - t0 + 31) / 32;
+        if (tiles > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "qr_build_compact_fill: row window too large for one launch");
+        auto kern = qr::fill_compact_kernel<8>;
+        QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)tiles, 256, smem, st>>>(pl->dev, (uint32_t)G, t0, row_lo, row_hi, tol, d_indptr, d_indices,
+                                                 reinterpret_cast<double2 *>(d_data));
+        QR_LAUNCH_CHECK("fill_compact_kernel");
+        return QR_OK;
+    }
+    // rows too long for a shared-memory tile: build row windows into scratch, compact each window
+    uint64_t win = std::max<uint64_t>(32, (256ull << 20) / (G * 24) / 32 * 32);
+    if (win > rows) win = rows;
+    void *scratch = nullptr;
+    QR_CUDA(cudaMalloc(&scratch, win * G * 24));
+    double2 *t_dat = static_cast<double2 *>(scratch);
+    uint64_t *t_idx = reinterpret_cast<uint64_t *>(static_cast<char *>(scratch) + win * G * 16);
+    int rc = QR_OK;
+    for (uint64_t w0 = row_lo; w0 < row_hi && rc == QR_OK; w0 += win) {
+        const uint64_t w1 = std::min(row_hi, w0 + win), n = w1 - w0;
+        rc = build_rows(pl, w0, w1, nullptr, t_idx, t_dat, 0, st);
+        if (rc != QR_OK) break;
+        const uint64_t per_cta = qr::K2_THREADS / 32;
+        const uint64_t ctas = std::min<uint64_t>((n + per_cta - 1) / per_cta, 148ull * 64);
+        qr::compact_rows_kernel<<<(unsigned)ctas, qr::K2_THREADS, 0, st>>>(
+            n, (uint32_t)G, t_idx, t_dat, tol, d_indptr + (w0 - row_lo), d_indices, reinterpret_cast<double2 *>(d_data));
+        g_launches.fetch_add(1);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(QR_ERR_CUDA, "qr_build_compact_fill: compact_rows_kernel launch failed");
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    return rc;
 }
 
 static unsigned vec_grid(uint64_t n)
@@ -757,6 +971,18 @@ extern "C" int qr_ax_device(uint64_t n, const double a[2], const double *x, doub
         n, make_double2(a[0], a[1]), reinterpret_cast<const double2 *>(x), make_double2(0, 0),
         nullptr, reinterpret_cast<double2 *>(z));
     QR_LAUNCH_CHECK("vec_ax_kernel");
+    return QR_OK;
+}
+
+extern "C" int qr_precond2_device(uint64_t n, const double *d_diag, const double *d_dx, const double e[2], double tol,
+                                  double *d_out, void *stream)
+{
+    if (!d_diag || !d_dx || !e || !d_out) return fail(QR_ERR_INVALID, "qr_precond2_device: NULL argument");
+    if (n == 0) return QR_OK;
+    qr::precond2_kernel<<<vec_grid(n), 256, 0, as_stream(stream)>>>(
+        n, reinterpret_cast<const double2 *>(d_diag), reinterpret_cast<const double2 *>(d_dx), make_double2(e[0], e[1]),
+        tol, reinterpret_cast<double2 *>(d_out));
+    QR_LAUNCH_CHECK("precond2_kernel");
     return QR_OK;
 }
 

@@ -41,6 +41,18 @@ def golden_sums():
         return json.load(f)
 
 
+@pytest.fixture(scope="session")
+def precond_vectors():
+    """pyqrusty/tests/test_it.py:284-301: the reference's own precond fixture on H2 -- (dx, e,
+    expected rv as printed there, 9 significant digits)."""
+    import numpy as np
+    dx = np.zeros(16, complex)
+    dx[[6, 9, 10]] = [-9.57567359e-14, -9.57428581e-14, 1.74695127e-01]
+    rv = np.zeros(16, complex)
+    rv[[6, 9, 10]] = [-9.91433685e-14, -9.91289999e-14, 8.88073154e-02]
+    return dx, -1.7037077186606393 + 0j, rv
+
+
 def has_gpu():
     from qrusty_b200 import _ffi
     return _ffi.device_count() > 0

@@ -191,6 +191,42 @@ def test_blocked_kernel(fixtures, monkeypatch, name, S, E):
             assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
 
 
+@pytest.mark.parametrize("W,NT,sync", [(8, 6, 0), (16, 2, 1), (32, 6, 1), (32, 2, 0)])
+@pytest.mark.parametrize("R", [5, 6, 8])
+@pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
+def test_lanes_kernel(fixtures, monkeypatch, name, R, W, NT, sync):
+    """Large-G path (classify_kernel + fill_lanes_kernel: lane <-> group, rows in Gray-code order,
+    heavy groups on their own CTAs) forced on every case: whole matrix and ragged windows."""
+    monkeypatch.setenv("QR_FILL_LANES", "1")
+    monkeypatch.setenv("QR_FILL_LANES_R", str(R))
+    monkeypatch.setenv("QR_FILL_LANES_W", str(W))
+    monkeypatch.setenv("QR_FILL_LANES_NT", str(NT))
+    monkeypatch.setenv("QR_FILL_LANES_SYNC", str(sync))
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    G, dim = plan.n_groups, 1 << n
+    assert_same(device_build(plan, 0, dim), ref, f"{name} R={R} W={W} NT={NT} sync={sync}")
+    if dim >= 128:
+        for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 33)]:
+            ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
+            assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G])), (lo, hi)
+            assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
+
+
+def test_lanes_kernel_is_the_large_G_default(fixtures):
+    """G = 286 rows do not fit the staged kernel's shared-memory tile: the default path must be the
+    lanes kernel, and it must agree with the shared-memory blocked kernel and the oracle."""
+    labels, coeffs = fixtures["H6"]
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    before = _ffi.kernel_launches()
+    assert_same(device_build(plan, 0, 1 << n), ref, "H6 default")
+    assert _ffi.kernel_launches() - before == 1          # one fill_lanes_kernel, no edge launches
+
+
 def test_build_host_windows(fixtures):
     labels, coeffs = fixtures["H4"]
     n, params = O.make_params(labels, coeffs)
@@ -423,6 +459,28 @@ def test_vector_ops_bit_exact():
         assert np.allclose(Q.axpy(1j, x, y), 1j * x + y) and np.allclose(Q.ax(1j, x), 1j * x)
 
 
+def test_precond_bit_exact(fixtures, precond_vectors):
+    """precond / precond2 (pyqrusty/src/lib.rs:436-468; test_it.py:303-313) against the oracle."""
+    PRECOND_DX, PRECOND_E, PRECOND_RV = precond_vectors
+    labels, coeffs = fixtures["H2"]
+    m = make_op(labels, coeffs).to_matrix_mode("Cuda")
+    diag = m.diagonal()
+    got = Q.precond2(diag, PRECOND_DX, PRECOND_E, 1e-14)
+    assert np.array_equal(u64(got), u64(O.precond2(diag, PRECOND_DX, PRECOND_E, 1e-14)))
+    assert np.allclose(got, PRECOND_RV, rtol=1e-8, atol=0)
+    assert np.array_equal(u64(Q.precond(m, PRECOND_DX, PRECOND_E, 1e-14)), u64(got))
+    rng = np.random.default_rng(3)
+    n = (1 << 20) + 5
+    d = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    dx = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    d[::7] = 0.25 + 0j                                    # denominators that hit reg()
+    e = 0.25 + 1e-9j
+    assert np.array_equal(u64(Q.precond2(d, dx, e, 1e-7)), u64(O.precond2(d, dx, e, 1e-7)))
+    m.export()
+    with pytest.raises(Exception, match="exported"):
+        Q.precond(m, PRECOND_DX, PRECOND_E, 1e-14)
+
+
 def test_lanczos_matches_numpy(fixtures):
     """The device Lanczos loop (BASELINE config 4's measurement loop) against numpy on the oracle's CSR."""
     import scipy.sparse as sps
@@ -460,14 +518,19 @@ def test_dotc():
 
 
 # ---- K2: count + scan + compaction (test_it.py:141-148, util.rs:144-171) -----------------------
+@pytest.mark.parametrize("resident", [False, True])
 @pytest.mark.parametrize("name", ["H2", "H4", "H6", "C1", "random_n10", "xxz_n10"])
-def test_eliminate_zeros(fixtures, name):
+def test_eliminate_zeros(fixtures, name, resident):
+    """resident=False: the fused drop-zeros build (count_rows_kernel + scan + fill_compact_kernel) on a
+    matrix that was never written; resident=True: count + scan + compaction of the built shard."""
     labels, coeffs = SMALL[name](fixtures)
     n, params = O.make_params(labels, coeffs)
     ref = O.build_csr(params, n)
     for tol in (1e-7, 0.0, 0.05):
         want = O.eliminate_zeros(*ref, tolerance=tol)
         m = make_op(labels, coeffs).to_matrix()
+        if resident:
+            m.to_device()
         assert m.count_zeros(tol) == O.count_zeros(ref[2], tol)
         m2 = m.eliminate_zeros(tol)
         assert m2.nnz() == len(want[2]) and m2.shape() == (1 << n, 1 << n)
@@ -490,6 +553,25 @@ def test_eliminate_zeros_tiny_values():
     assert len(data) == 0 and np.array_equal(indptr, [0, 0, 0])
 
 
+@pytest.mark.parametrize("name,lo,hi", [("H4", 3, 250), ("H4", 32, 96), ("xxz_n10", 1, 1023), ("H6", 100, 3001),
+                                        ("H8", 4096 + 7, 8192 + 100)])
+def test_fused_drop_zeros_row_windows(fixtures, name, lo, hi):
+    """qr_build_compact_* on ragged row windows (first/last tile partly outside the window); H8's rows
+    (G = 981) do not fit a shared-memory tile and take the windowed build + compaction inside the library."""
+    labels, coeffs = fixtures[name] if name in fixtures else SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    G = len(np.unique(params["x"]))
+    ref = O.build_csr(params, n, lo, hi)
+    ref = (ref[0] - ref[0][0], ref[1], ref[2])
+    for tol in (1e-7, 0.02):
+        want = O.eliminate_zeros(*ref, tolerance=tol)
+        m = make_op(labels, coeffs).to_matrix_rows(lo, hi)
+        assert m.count_zeros(tol) == O.count_zeros(ref[2], tol)
+        shape, data, indices, indptr = m.eliminate_zeros(tol).export()
+        assert shape == (hi - lo, 1 << n)
+        assert_same((indptr, indices, data), want, f"{name}[{lo},{hi}) tol={tol}")
+
+
 def test_eliminate_zeros_C2_full():
     labels, coeffs = H.xxz_chain(20, 1.0, 0.7)
     n, params = O.make_params(labels, coeffs)
@@ -497,6 +579,57 @@ def test_eliminate_zeros_C2_full():
     shape, data, indices, indptr = make_op(labels, coeffs).to_matrix().eliminate_zeros().export()
     assert_same((indptr, indices, data), want, "C2 compacted")
     assert len(data) < 22020096 * 0.6
+
+
+# ---- on-disk formats (rawio.rs:128-179, pyqrusty/src/lib.rs:216-259) ----------------------------
+@pytest.mark.parametrize("name,lo,hi", [("H4", 0, 256), ("H6", 0, 4096), ("xxz_n10", 100, 901), ("C1", 0, 4096)])
+def test_rawio_streamed_write(fixtures, tmp_path, name, lo, hi):
+    """qr_write_rawio (fill -> pinned staging -> pwrite, row windows) byte for byte against the
+    restatement of rawio::write applied to the oracle's CSR; then read back."""
+    labels, coeffs = fixtures[name] if name in fixtures else SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n, lo, hi)
+    op = make_op(labels, coeffs)
+    m = op.to_matrix() if (lo, hi) == (0, 1 << n) else op.to_matrix_rows(lo, hi)
+    path = tmp_path / "m.rawio"
+    m.rawio_write(path)
+    want = O.rawio_bytes((hi - lo, 1 << n), *ref)
+    assert path.read_bytes() == want
+    back = Q.SpMat.rawio_read(path)
+    shape, data, indices, indptr = back.export()
+    assert shape == (hi - lo, 1 << n)
+    assert_same((indptr, indices, data), ref, name + " rawio round trip")
+    # a resident (already built) matrix takes the export path: same bytes
+    m2 = op.to_matrix_rows(lo, hi).to_device()
+    m2.rawio_write(path)
+    assert path.read_bytes() == want
+    # a file written on a machine of the other endianness (rawio.rs:150-152: need_swab)
+    import sys
+    path.write_bytes(O.rawio_bytes((hi - lo, 1 << n), *ref, byteorder=">" if sys.byteorder == "little" else "<"))
+    shape, data, indices, indptr = Q.SpMat.rawio_read(path).export()
+    assert_same((indptr, indices, data), ref, name + " rawio swabbed")
+
+
+def test_rawio_many_windows(tmp_path):
+    """A matrix larger than the writer's 64 MB staging window: several windows, two streams."""
+    labels, coeffs = H.xxz_chain(18, 1.0, 0.7)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    path = tmp_path / "xxz18.rawio"
+    make_op(labels, coeffs).to_matrix().rawio_write(path)
+    assert hashlib.sha256(path.read_bytes()).hexdigest() == hashlib.sha256(O.rawio_bytes((1 << n, 1 << n), *ref)).hexdigest()
+
+
+def test_matrixmarket_round_trip(fixtures, tmp_path):
+    labels, coeffs = fixtures["H4"]
+    n, params = O.make_params(labels, coeffs)
+    want = O.eliminate_zeros(*O.build_csr(params, n), tolerance=0.0)       # a reader drops nothing, but
+    m = make_op(labels, coeffs).to_matrix().eliminate_zeros(0.0)           # scipy's mmread sums/drops zeros
+    path = tmp_path / "h4.mtx"
+    m.matrixmarket_write(path)
+    assert path.read_text().splitlines()[0] == "%%MatrixMarket matrix coordinate complex general"
+    shape, data, indices, indptr = Q.SpMat.matrixmarket_read(path).export()
+    assert_same((indptr, indices, data), want, "H4 MatrixMarket round trip")
 
 
 def test_multi_gpu_single_process(fixtures):

@@ -216,5 +216,47 @@ def test_spmv(fixtures, name):
     assert np.array_equal(O.apply_rows(params, rows, v), y[rows.astype(np.int64)])
 
 
+def h2_diagonal(fixtures):
+    labels, coeffs = fixtures["H2"]
+    n, params = O.make_params(labels, coeffs)
+    indptr, indices, data = O.build_csr(params, n)
+    G = len(indices) // (1 << n)
+    rows = np.repeat(np.arange(1 << n, dtype=np.uint64), G)
+    diag = np.zeros(1 << n, complex)
+    diag[rows[indices == rows].astype(np.int64)] = data[indices == rows]
+    return diag
+
+
+def test_precond2_known_answer(fixtures, precond_vectors):
+    """test_it.py:303-313 with the vectors stored there (rv printed to 9 digits)."""
+    PRECOND_DX, PRECOND_E, PRECOND_RV = precond_vectors
+    diag = h2_diagonal(fixtures)
+    got = O.precond2(diag, PRECOND_DX, PRECOND_E, 1e-14)
+    assert np.allclose(got, PRECOND_RV, rtol=1e-8, atol=0)
+    # test_it.py:271-282: numpy restatement dx / reg(diag - e, tol)
+    x = diag - PRECOND_E
+    x = np.where(np.abs(x) < 1e-14, 1e-14, x)
+    assert np.allclose(got, PRECOND_DX / x, rtol=1e-15, atol=0)
+    # reg(): a denominator below tol becomes (tol, 0)
+    got = O.precond2([PRECOND_E + 1e-16j], [2.0 + 4.0j], PRECOND_E, 1e-3)[0]
+    assert got == complex(2.0 * 1e-3 / (1e-3 * 1e-3), 4.0 * 1e-3 / (1e-3 * 1e-3))        # num-complex's division
+
+
+def test_rawio_layout():
+    """rawio.rs:181-234: write_matrix (2x2 identity) and the swab constants, on the restatement."""
+    indptr, indices, data = np.array([0, 1, 2], np.uint64), np.array([0, 1], np.uint64), np.array([1, 1], complex)
+    b = O.rawio_bytes((2, 2), indptr, indices, data, byteorder="<")
+    assert b[:2] == b"MI" and len(b) == 2 + 4 * 8 + 3 * 8 + 8 + 2 * 8 + 8 + 2 * 16
+    head = np.frombuffer(b, "<u8", 4, 2)
+    assert head.tolist() == [0, 2, 2, 3]                               # CSR, rows, cols, len(indptr)
+    assert np.frombuffer(b, "<u8", 3, 34).tolist() == [0, 1, 2]
+    assert np.frombuffer(b, "<u8", 1, 58)[0] == 2 and np.frombuffer(b, "<u8", 2, 66).tolist() == [0, 1]
+    assert np.frombuffer(b, "<u8", 1, 82)[0] == 2 and np.frombuffer(b, "<c16", 2, 90).tolist() == [1, 1]
+    big = O.rawio_bytes((2, 2), indptr, indices, data, byteorder=">")
+    assert big[:2] == b"IM"                                            # the reader sees a foreign mark -> swab
+    assert np.frombuffer(big, ">u8", 4, 2).tolist() == [0, 2, 2, 3]
+    assert np.array([0x0123456789abcdef], "<u8").byteswap()[0] == 0xefcdab8967452301    # rawio.rs:188-200
+
+
 def test_pair_t_layout():
     assert O.PARAM_DTYPE.itemsize == 32

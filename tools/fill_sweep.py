@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Times the fill kernel (events on the launching stream) for one workload under several
 (RW,GW) tile configurations, the direct kernel, and a row window size.  GPU box only.
-  python tools/fill_sweep.py C2 | C4 | C3 | xxz<n> | H8 ...   [--rows LOG2] [--cfgs "2,4 1,8 direct"]
+  python tools/fill_sweep.py C2 | C4 | C3 | xxz<n> | H8 ...   [--rows LOG2] [--cfgs "2,4 1,8 direct lanes:8:8 blocked:32:1"]
 """
 import argparse, ctypes as C, gzip, json, os, sys
 from pathlib import Path
@@ -38,9 +38,22 @@ def main():
     bufs = None
     for cfg in a.cfgs.split():
         flags = 0
-        os.environ.pop("QR_FILL_CFG", None)
+        for k in [k for k in os.environ if k.startswith("QR_FILL_")]:
+            os.environ.pop(k)
         if cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
+        elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:NT[:sync]]]]
+            parts = cfg.split(":")
+            os.environ["QR_FILL_LANES"] = "1"
+            if len(parts) > 1: os.environ["QR_FILL_LANES_R"] = parts[1]
+            if len(parts) > 2: os.environ["QR_FILL_LANES_W"] = parts[2]
+            if len(parts) > 3: os.environ["QR_FILL_LANES_NT"] = parts[3]
+            if len(parts) > 4: os.environ["QR_FILL_LANES_SYNC"] = parts[4]
+        elif cfg.startswith("blocked"):               # blocked[:S[:E]]
+            parts = cfg.split(":")
+            os.environ["QR_FILL_LANES"] = "0"
+            os.environ["QR_FILL_BLOCK"] = parts[1] if len(parts) > 1 else "32"
+            if len(parts) > 2: os.environ["QR_FILL_BLOCK_E"] = parts[2]
         elif cfg != "auto":
             os.environ["QR_FILL_CFG"] = cfg
         op = Q.SparsePauliOp.from_terms(n, terms)
