@@ -230,6 +230,8 @@ QR_API int qr_event_destroy(void *event);
 QR_API int qr_event_record(void *event, void *stream);
 QR_API int qr_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchronises on `stop` */
 
+/* Frees the per-device staging windows qr_build_host keeps between calls (2 x <= 256 MB of HBM). */
+QR_API int qr_release_scratch(void);
 /* Number of this library's kernels launched by the calling process so far. */
 QR_API uint64_t qr_kernel_launches(void);
 QR_API const char *qr_last_error(void);

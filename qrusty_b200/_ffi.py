@@ -80,6 +80,7 @@ SIGNATURES = {
     "qr_ipc_get_handle": [_vp, _vp],
     "qr_ipc_open_handle": [_vp, C.POINTER(_vp)],
     "qr_ipc_close_handle": [_vp],
+    "qr_release_scratch": [],
     "qr_device_count": [C.POINTER(_int)],
     "qr_device_name": [_int, C.c_char_p, _sz],
     "qr_set_device": [_int],

@@ -342,21 +342,23 @@ fill_blocked_kernel(PlanDev p, uint32_t G, uint32_t S, uint32_t n_blocks, uint32
 //
 // lane <-> group: a warp owns 32 consecutive sorted groups and walks a run of R = 2^k
 // aligned rows in GRAY-CODE order.  Everything that depends only on the group -- mask,
-// up to NT (z, c') terms, the rank-table row -- lives in the lane's registers for the
+// up to NT (z, c') terms, the rank-table column -- lives in the lane's registers for the
 // whole run, and moving to the next row flips exactly one row bit b, so
-//     slot(r ^ 2^b, g) = slot(r, g) +- cnt[g][b]        (one IADD; the sign alternates)
-// and a row costs ~13 + 7*terms thread instructions per entry with no shared-memory
-// staging and no barrier.  The 32 entries a warp stores per row are the block's slots of
-// that row: consecutive sorted masks are a union of a few trie subtrees, each of which
-// fills one contiguous slot range in every row (XOR never splits a subtree), so one
-// STG.128 + one STG.64 per row cover a few contiguous segments (<= 512 B + 256 B).
-// All warps of a CTA -- and the sibling CTAs that own the other groups of the same rows,
-// adjacent in blockIdx -- walk the same row sequence, so the sectors shared by two
-// segments are completed in L2 within the warps' drift, long before they are evicted.
+//     offset(r ^ 2^b, g) = offset(r, g) +- (cnt[g][b] +- G*2^b)     (one IADD; the sign alternates)
+// and a row costs ~13 + 6*(terms-1) thread instructions per entry with no shared-memory
+// staging.  The 32 entries a warp stores per row are the block's slots of that row:
+// consecutive sorted masks are a union of a few trie subtrees, each of which fills one
+// contiguous slot range in every row (XOR never splits a subtree), so one STG.128 + one
+// STG.64 per row cover a few contiguous segments (<= 512 B + 256 B).  All warps of a CTA --
+// and the sibling CTAs that own the other groups of the same rows, adjacent in blockIdx --
+// walk the same row sequence and re-align every 32 rows (`resync`), so the sectors shared by
+// two segments are completed in L2 within the warps' drift, long before they are evicted
+// (ncu: without the re-alignment 0.5 GB of DRAM read-modify-write traffic per 4.7 GB written).
 //
-// Groups with more than NT terms ("heavy": the Z-only group of a molecular Hamiltonian,
-// a few dozen others) are left to heavy CTAs in the same grid: lane <-> row, one
-// (heavy group, 32-row strip) item per warp visit, warp-uniform term loop.
+// Groups with more than NT terms ("heavy": the Z-only group of a molecular Hamiltonian, a
+// few dozen others) are collected per CTA and handled lane <-> row at the start of every
+// 32-row strip, round-robin over the CTA's warps, with a warp-uniform term loop -- in the
+// same time window as their neighbours in the row.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void st_global_f64x2(uintptr_t addr, double a, double b)
 {
@@ -372,39 +374,23 @@ constexpr int FILL_LANES_MAXLOG2R = 12;
 
 template <int NT, int LW>
 __global__ void __launch_bounds__(32 * LW, 32 / LW)
-fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t n_heavy_ctas, uint32_t log2R, uint32_t resync,
+fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint32_t resync,
                   uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
                   uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
                   double2 *__restrict__ data, uint64_t indptr_last_row)
 {
-    __shared__ int32_t s_delta[LW][FILL_LANES_MAXLOG2R - 3][32];   // +-cnt[g][b] for the row bits b >= 3
+    __shared__ int32_t s_delta[LW][FILL_LANES_MAXLOG2R - 3][32];   // signed step of the row bits b >= 3
+    __shared__ uint32_t s_heavy[LW * 32];                          // heavy groups of this CTA's blocks
+    __shared__ uint32_t s_nheavy;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t per_range = n_light + n_heavy_ctas;
-    const uint32_t rho = blockIdx.x / per_range, beta = blockIdx.x % per_range;
+    const uint32_t rho = blockIdx.x / n_light, beta = blockIdx.x % n_light;
     const uint32_t R = 1u << log2R;
     const uint64_t r0_64 = tile_row0 + (uint64_t)rho * R;          // first row of the run (aligned to R)
     const uint32_t r0 = (uint32_t)r0_64;
-    double2 *const dbase = data + (r0_64 - row_lo) * G;
-    uint64_t *const ibase = indices + (r0_64 - row_lo) * G;
+    const uintptr_t dptr = reinterpret_cast<uintptr_t>(data + (r0_64 - row_lo) * G);
+    const uintptr_t iptr = reinterpret_cast<uintptr_t>(indices + (r0_64 - row_lo) * G);
 
-    if (beta >= n_light) {
-        // ---- heavy CTA: items (heavy group h, strip s), lane <-> row ---------------------------
-        const uint32_t nh = __ldg(&p.meta[6]);
-        const uint32_t strips = R >> 5;
-        const uint32_t n_items = nh * strips;
-        for (uint32_t q = (beta - n_light) * LW + warp; q < n_items; q += n_heavy_ctas * LW) {
-            const uint32_t g = __ldg(&p.heavy[q / strips]), s = q % strips;
-            const GroupDesc d = p.gdesc[g];
-            const uint32_t wbase = r0 + 32u * s, r = wbase + lane;
-            const uint32_t slot = group_slot(p, g, d.x, wbase, lane);
-            const double2 v = (d.flag & 1u) ? make_double2(d.cre, d.cim) : group_value(p.tz, p.tc, d.t0, d.t1, r);
-            const uint32_t off = (32u * s + lane) * G + slot;
-            dbase[off] = v;
-            ibase[off] = (uint64_t)(r ^ d.x);
-        }
-        return;
-    }
-
+    if (threadIdx.x == 0) s_nheavy = 0;
     if (beta == 0 && indptr != nullptr) {
         for (uint32_t i = threadIdx.x; i < R; i += 32 * LW) {
             const uint64_t lr = r0_64 + i - row_lo;
@@ -412,16 +398,15 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t n_heavy_ctas
             if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
         }
     }
+    __syncthreads();
 
-    // ---- light CTA: warp <-> block of 32 groups, lane <-> group ---------------------------------
+    // ---- warp <-> block of 32 groups, lane <-> group ---------------------------------------------
     const uint32_t g = (beta * LW + warp) * 32u + lane;
-    if ((beta * LW + warp) * 32u >= G) {                          // warp-uniform: no groups left for this warp
-        if (resync) for (uint32_t i = 32u; i < R; i += 32u) __syncthreads();
-        return;
-    }
+    const bool warp_live = (beta * LW + warp) * 32u < G;          // warp-uniform
     uint32_t x = 0, nt = 0, t0 = 0;
     if (g < G) { const GroupDesc d = p.gdesc[g]; x = d.x; nt = d.t1 - d.t0; t0 = d.t0; }
     const bool active = g < G && nt <= (uint32_t)NT;
+    if (g < G && !active) s_heavy[atomicAdd(&s_nheavy, 1u)] = g;
     if (!active) nt = 0;
     // terms beyond the lane's own are padded with (z = 0, c' = -0.0): x + (-0.0) == x for every x,
     // signed zeros included, so padding never needs a predicate
@@ -439,7 +424,7 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t n_heavy_ctas
     // one signed step per (lane, bit) carries both.  R*G*16 < 2^32 (host-checked): 32-bit byte offsets.
     uint32_t off = 0;
     int32_t d0 = 0, d1 = 0, d2 = 0;
-    {
+    if (warp_live) {
         const uint32_t nq = (uint32_t)p.n_qubits, T = p.n_terms, gg = g < G ? g : G - 1u;
 #pragma unroll
         for (uint32_t b0 = 0; b0 < 32u; b0 += 8u) {
@@ -459,8 +444,8 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t n_heavy_ctas
             }
         }
     }
-    __syncwarp();
-    const uintptr_t dptr = reinterpret_cast<uintptr_t>(dbase), iptr = reinterpret_cast<uintptr_t>(ibase);
+    __syncthreads();                                               // s_heavy complete
+    const uint32_t n_heavy = s_nheavy;
 
     uint32_t r = r0;                                               // warp-uniform current row
     // +-1.0 from the parity of r & z: (+-1.0) * c' and fma(+-1.0, c', acc) are exactly the sign flip
@@ -481,15 +466,32 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t n_heavy_ctas
             st_global_u64(iptr + ((size_t)off << 3), (uint64_t)(r ^ x));
         }
     };
+    // heavy groups of the CTA for the 32-row strip that holds r: lane <-> row, round-robin over warps
+    auto heavy_strip = [&]() {
+        const uint32_t wbase = r & ~31u, rr = wbase + lane;
+        for (uint32_t q = warp; q < n_heavy; q += LW) {
+            const uint32_t hg = s_heavy[q];
+            const GroupDesc d = p.gdesc[hg];
+            const uint32_t slot = group_slot(p, hg, d.x, wbase, lane);
+            const double2 v = group_value(p.tz, p.tc, d.t0, d.t1, rr);
+            const uint32_t o = (rr - r0) * G + slot;
+            st_global_f64x2(dptr + ((size_t)o << 4), v.x, v.y);
+            st_global_u64(iptr + ((size_t)o << 3), (uint64_t)(rr ^ d.x));
+        }
+    };
     for (uint32_t i = 0; i < R; i += 8u) {
         if (i != 0u) {                                             // Gray code: step i flips bit ctz(i) >= 3
             if (resync && (i & 31u) == 0u) __syncthreads();        // keep the CTA's warps on the same rows
             const uint32_t b = (uint32_t)__ffs((int)i) - 1u;
             r ^= 1u << b;
-            const int32_t st = s_delta[warp][b - 3][lane];
-            off += (uint32_t)st;
-            s_delta[warp][b - 3][lane] = -st;
+            if (warp_live) {
+                const int32_t st = s_delta[warp][b - 3][lane];
+                off += (uint32_t)st;
+                s_delta[warp][b - 3][lane] = -st;
+            }
         }
+        if ((i & 31u) == 0u && n_heavy != 0u) heavy_strip();
+        if (!warp_live) { r ^= 4u; continue; }                     // the 8 steps below leave r ^ 4 (Gray: 0,1,3,2,6,7,5,4)
         emit();
         r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
         r ^= 2u; off += (uint32_t)d1; d1 = -d1; emit();
@@ -499,31 +501,6 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t n_heavy_ctas
         r ^= 2u; off += (uint32_t)d1; d1 = -d1; emit();
         r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
     }
-}
-
-// K1c: the groups the lanes kernel leaves to its heavy CTAs (more than NT terms), in ascending
-// order: heavy[0..meta[6]); meta[7] = their total number of terms.  One CTA, CTA scan.
-__global__ void __launch_bounds__(512, 1) classify_kernel(PlanDev p, uint32_t nt_light)
-{
-    __shared__ uint32_t scan_scratch[33];
-    __shared__ uint32_t heavy_terms;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t G = p.meta[0];
-    if (tid == 0) heavy_terms = 0;
-    __syncthreads();
-    uint32_t carry = 0;
-    for (uint32_t tile = 0; tile < G; tile += 512u) {
-        const uint32_t g = tile + tid;
-        uint32_t n = 0;
-        if (g < G) n = p.goff[g + 1] - p.goff[g];
-        const uint32_t h = n > nt_light ? 1u : 0u;
-        uint32_t total;
-        const uint32_t excl = block_exclusive_scan(h, scan_scratch, &total);
-        if (h) { p.heavy[carry + excl] = g; atomicAdd(&heavy_terms, n); }
-        carry += total;
-    }
-    __syncthreads();
-    if (tid == 0) { p.meta[6] = carry; p.meta[7] = heavy_terms; }
 }
 
 }  // namespace qr

@@ -23,9 +23,7 @@ namespace qr {
 //                         bit1: every c' of the group is real (im == +-0)
 //   gconst double2[G]     the group's ordered sum of c' (its value when bit0 is set)
 //   gdesc GroupDesc[G]    {x, flag, t0, t1, gconst} packed in 32 B for the H.v kernels
-//   meta  u32[8]          {G, max terms in a group, B, S, #row-independent groups, #terms after merging,
-//                          #heavy groups, their total terms}
-//   heavy u32[<=G]        large-G path: ids of the groups with more terms than a lane keeps in registers
+//   meta  u32[8]          {G, max terms in a group, B, S, #row-independent groups, #terms after merging, 0, 0}
 //   blk_start u32[B+1]    large-G path: the sorted groups cut into B trie subtrees ("blocks")
 //   blk_p     u32[B]      of <= S groups; block b = groups [blk_start[b], blk_start[b+1]), all
 //                         sharing the mask bits >= blk_p[b] (>= 5).  A subtree's groups fill
@@ -58,7 +56,6 @@ struct PlanDev {
     uint32_t *meta;
     uint32_t *blk_start;
     uint32_t *blk_p;
-    uint32_t *heavy;
     uint32_t *cnt_t;
 };
 

@@ -11,6 +11,7 @@
 #include <unistd.h>
 #include <new>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -52,6 +53,11 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr size_t MAX_SMEM = 227 * 1024;
 
+// qr_build_host's device-side staging (two row windows, two streams), one set per device
+struct WinScratch { void *buf[2] = {nullptr, nullptr}; size_t bytes = 0; cudaStream_t stream[2] = {nullptr, nullptr}; };
+std::mutex g_win_mutex;
+std::map<int, WinScratch> g_win;
+
 }  // namespace
 
 // H.v pass plan for a local row block of 2^m rows (see apply.cuh)
@@ -76,17 +82,13 @@ struct qr_plan {
     int rw = 0, gw = 0;
     uint32_t block_s = 0, n_blocks = 0;    // blocked kernel: S and the number of subtree blocks
     // lanes kernel (large G, default): rows per run = 2^lanes_log2r, warps per CTA, heavy groups
-    int lanes = 0, lanes_log2r = 0, lanes_warps = 0, lanes_nt = 0, lanes_resync = 0;
-    uint32_t n_heavy = 0, heavy_terms = 0;
+    int lanes = 0, lanes_log2r = 0, lanes_warps = 0, lanes_resync = 1;
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
     uint64_t n_terms_canonical = 0;
     // lazily allocated scratch
     double2 *dot_partials = nullptr;
-    void *win_buf[2] = {nullptr, nullptr};
-    size_t win_bytes = 0;
-    cudaStream_t win_stream[2] = {nullptr, nullptr};
 };
 
 struct qr_comm {
@@ -137,15 +139,11 @@ void choose_staged(qr_plan *pl)
     const uint64_t G = pl->n_groups;
     pl->block_s = 0;
     pl->lanes = 0;
-    pl->lanes_log2r = 8; pl->lanes_warps = 8;
+    pl->lanes_log2r = 8; pl->lanes_warps = 16;
     if (const char *env = getenv("QR_FILL_LANES_R")) { int k = atoi(env); if (k >= 5 && k <= qr::FILL_LANES_MAXLOG2R) pl->lanes_log2r = k; }
     if (const char *env = getenv("QR_FILL_LANES_W")) { int w = atoi(env); if (w == 8 || w == 16 || w == 32) pl->lanes_warps = w; }
-    // terms a lane keeps in registers: 2 when nearly every group is that short (fewer registers, more
-    // resident warps), else 6; longer groups go to the heavy CTAs
-    pl->lanes_nt = pl->n_terms <= pl->n_groups + pl->n_groups / 2 ? 2 : qr::FILL_LANES_NT;
-    if (const char *env = getenv("QR_FILL_LANES_NT")) { int t = atoi(env); if (t == 2 || t == qr::FILL_LANES_NT) pl->lanes_nt = t; }
-    pl->lanes_resync = 0;
-    if (const char *env = getenv("QR_FILL_LANES_SYNC")) pl->lanes_resync = env[0] == '1';
+    pl->lanes_resync = 1;
+    if (const char *env = getenv("QR_FILL_LANES_SYNC")) pl->lanes_resync = env[0] != '0';
     if (const char *env = getenv("QR_FILL_LANES")) if (env[0] == '1') { pl->lanes = 1; return; }   // force (tests, sweeps)
     if (const char *env = getenv("QR_FILL_BLOCK")) {         // "S" override: force the blocked kernel
         int S = atoi(env);
@@ -196,11 +194,6 @@ static int run_canonicalise(qr_plan *pl, cudaStream_t st)
 
 static int run_partition(qr_plan *pl, cudaStream_t st)
 {
-    if (pl->lanes) {
-        qr::classify_kernel<<<1, 512, 0, st>>>(pl->dev, (uint32_t)pl->lanes_nt);
-        QR_LAUNCH_CHECK("classify_kernel");
-        return QR_OK;
-    }
     if (!pl->block_s) return QR_OK;
     qr::partition_kernel<<<1, qr::K1_THREADS, 0, st>>>(pl->dev, pl->block_s);
     QR_LAUNCH_CHECK("partition_kernel");
@@ -238,7 +231,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     const size_t o_cnt = carve(T * 128), o_lr5 = carve(T * 128), o_meta = carve(32);
     const size_t o_bs = carve((T + 1) * 4), o_bp = carve(T * 4);
     const size_t o_gf = carve(T * 4), o_gc = carve(T * 16), o_gd = carve(T * sizeof(qr::GroupDesc));
-    const size_t o_hv = carve(T * 4), o_ct = carve(T * 128);
+    const size_t o_ct = carve(T * 128);
     cudaError_t e = cudaMalloc(&pl->slab, off);
     if (e != cudaSuccess) { delete pl; return fail(QR_ERR_OOM, std::string("qr_plan_create: cudaMalloc: ") + cudaGetErrorString(e)); }
     char *b = static_cast<char *>(pl->slab);
@@ -255,7 +248,6 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     d.blk_start = reinterpret_cast<uint32_t *>(b + o_bs); d.blk_p = reinterpret_cast<uint32_t *>(b + o_bp);
     d.gflag = reinterpret_cast<uint32_t *>(b + o_gf); d.gconst = reinterpret_cast<double2 *>(b + o_gc);
     d.gdesc = reinterpret_cast<qr::GroupDesc *>(b + o_gd);
-    d.heavy = reinterpret_cast<uint32_t *>(b + o_hv);
     d.cnt_t = reinterpret_cast<uint32_t *>(b + o_ct);
 
     auto bail = [&](int code) { cudaFree(pl->slab); delete pl; return code; };
@@ -272,13 +264,6 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     pl->n_terms_canonical = meta[5];
     if (pl->n_groups == 0 || pl->n_groups > T) return bail(fail(QR_ERR_CUDA, "qr_plan_create: canonicalisation produced no groups"));
     choose_staged(pl);
-    if (pl->lanes) {
-        rc = run_partition(pl, nullptr);
-        if (rc != QR_OK) return bail(rc);
-        e = cudaMemcpy(meta, d.meta, sizeof(meta), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: classify: ") + cudaGetErrorString(e)));
-        pl->n_heavy = meta[6]; pl->heavy_terms = meta[7];
-    }
     if (pl->block_s) {
         rc = run_partition(pl, nullptr);
         if (rc != QR_OK) return bail(rc);
@@ -295,10 +280,6 @@ extern "C" int qr_plan_destroy(qr_plan *pl)
 {
     if (!pl) return QR_OK;
     cudaSetDevice(pl->device);
-    for (int i = 0; i < 2; i++) {
-        if (pl->win_buf[i]) cudaFree(pl->win_buf[i]);
-        if (pl->win_stream[i]) cudaStreamDestroy(pl->win_stream[i]);
-    }
     for (auto &kv : pl->apply_plans) if (kv.second.slab) cudaFree(kv.second.slab);
     if (pl->diag_cache) cudaFree(pl->diag_cache);
     if (pl->dot_partials) cudaFree(pl->dot_partials);
@@ -380,27 +361,17 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         if (s1 > s0 && (G << k) < (1ull << 28)) {
             const uint32_t LW = (uint32_t)pl->lanes_warps;
             const uint32_t n_light = (uint32_t)((G + 32ull * LW - 1) / (32ull * LW));
-            // heavy CTAs per row range: one warp visit of a heavy group costs about as much per term as a
-            // light lane does per entry, so size them for roughly the work of a light CTA
-            uint32_t n_heavy_ctas = 0;
-            if (pl->n_heavy) n_heavy_ctas = (uint32_t)std::max<uint64_t>(1, (pl->heavy_terms + 160ull * LW - 1) / (160ull * LW));
-            const uint64_t ctas = (s1 - s0) / R * (n_light + n_heavy_ctas);
+            const uint64_t ctas = (s1 - s0) / R * n_light;
             if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_lanes: row window too large for one launch");
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
-            using LanesFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t,
-                                     uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
-            LanesFn kern;
-            if (pl->lanes_nt == 2)
-                kern = LW == 16 ? (LanesFn)qr::fill_lanes_kernel<2, 16> : LW == 32 ? (LanesFn)qr::fill_lanes_kernel<2, 32>
-                                                                                   : (LanesFn)qr::fill_lanes_kernel<2, 8>;
-            else
-                kern = LW == 16 ? (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 16>
-                     : LW == 32 ? (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 32>
-                                : (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 8>;
-            kern<<<(unsigned)ctas, 32 * LW, 0, st>>>(pl->dev, (uint32_t)G, n_light, n_heavy_ctas, (uint32_t)k,
-                                                     (uint32_t)pl->lanes_resync, s0, row_lo, indptr_base, d_indptr, d_indices,
-                                                     d_data, row_hi - row_lo);
+            using LanesFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t,
+                                     uint64_t *, uint64_t *, double2 *, uint64_t);
+            const LanesFn kern = LW == 8 ? (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 8>
+                               : LW == 32 ? (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 32>
+                                          : (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 16>;
+            kern<<<(unsigned)ctas, 32 * LW, 0, st>>>(pl->dev, (uint32_t)G, n_light, (uint32_t)k, (uint32_t)pl->lanes_resync, s0,
+                                                     row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo);
             QR_LAUNCH_CHECK("fill_lanes_kernel");
             return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
         }
@@ -480,23 +451,28 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
     const size_t idx_bytes = align_up(win_rows * G * 8, 256), dat_bytes = align_up(win_rows * G * 16, 256);
     const size_t ptr_bytes = align_up((win_rows + 1) * 8, 256);
     const size_t need = idx_bytes + dat_bytes + ptr_bytes;
-    if (pl->win_bytes < need) {
-        for (int i = 0; i < 2; i++) { if (pl->win_buf[i]) cudaFree(pl->win_buf[i]); pl->win_buf[i] = nullptr; }
-        pl->win_bytes = 0;
-        for (int i = 0; i < 2; i++) QR_CUDA(cudaMalloc(&pl->win_buf[i], need));
-        pl->win_bytes = need;
+    // the staging windows and their streams belong to the device, not to the plan: a caller that
+    // builds one matrix per plan (the reference's to_matrix call pattern) does not pay two
+    // cudaMalloc/cudaFree of 256 MB per call
+    std::lock_guard<std::mutex> lock(g_win_mutex);
+    WinScratch &ws = g_win[pl->device];
+    if (ws.bytes < need) {
+        for (int i = 0; i < 2; i++) { if (ws.buf[i]) cudaFree(ws.buf[i]); ws.buf[i] = nullptr; }
+        ws.bytes = 0;
+        for (int i = 0; i < 2; i++) QR_CUDA(cudaMalloc(&ws.buf[i], need));
+        ws.bytes = need;
     }
     for (int i = 0; i < 2; i++)
-        if (!pl->win_stream[i]) QR_CUDA(cudaStreamCreateWithFlags(&pl->win_stream[i], cudaStreamNonBlocking));
+        if (!ws.stream[i]) QR_CUDA(cudaStreamCreateWithFlags(&ws.stream[i], cudaStreamNonBlocking));
 
     int k = 0;
     for (uint64_t w0 = row_lo; w0 < row_hi; w0 += win_rows, k ^= 1) {
         const uint64_t w1 = w0 + win_rows < row_hi ? w0 + win_rows : row_hi, n = w1 - w0;
-        char *buf = static_cast<char *>(pl->win_buf[k]);
+        char *buf = static_cast<char *>(ws.buf[k]);
         double2 *dd = reinterpret_cast<double2 *>(buf);
         uint64_t *di = reinterpret_cast<uint64_t *>(buf + dat_bytes);
         uint64_t *dp = reinterpret_cast<uint64_t *>(buf + dat_bytes + idx_bytes);
-        cudaStream_t st = pl->win_stream[k];
+        cudaStream_t st = ws.stream[k];
         // window indptr is built "global" relative to the request, then rebased below
         int rc = build_rows(pl, w0, w1, indptr ? dp : nullptr, di, dd, QR_INDPTR_GLOBAL, st);
         if (rc != QR_OK) return rc;
@@ -505,7 +481,7 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
         QR_CUDA(cudaMemcpyAsync(indices + o, di, n * G * 8, cudaMemcpyDeviceToHost, st));
         if (indptr) QR_CUDA(cudaMemcpyAsync(indptr + (w0 - row_lo), dp, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < 2; i++) QR_CUDA(cudaStreamSynchronize(pl->win_stream[i]));
+    for (int i = 0; i < 2; i++) QR_CUDA(cudaStreamSynchronize(ws.stream[i]));
     if (indptr && !(flags & QR_INDPTR_GLOBAL)) {       // windows wrote r*G; local shards want (r-row_lo)*G
         const uint64_t base = row_lo * G;
         if (base) for (uint64_t i = 0; i <= rows; i++) indptr[i] -= base;
@@ -592,6 +568,20 @@ extern "C" int qr_write_rawio(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, con
     if (close(fd) != 0) ok = false;
     if (rc != QR_OK) return rc;
     if (!ok) return fail(QR_ERR_INVALID, std::string("qr_write_rawio: write to ") + path + " failed: " + strerror(errno));
+    return QR_OK;
+}
+
+extern "C" int qr_release_scratch(void)
+{
+    std::lock_guard<std::mutex> lock(g_win_mutex);
+    for (auto &kv : g_win) {
+        if (cudaSetDevice(kv.first) != cudaSuccess) continue;
+        for (int i = 0; i < 2; i++) {
+            if (kv.second.buf[i]) cudaFree(kv.second.buf[i]);
+            if (kv.second.stream[i]) cudaStreamDestroy(kv.second.stream[i]);
+        }
+    }
+    g_win.clear();
     return QR_OK;
 }
 

@@ -50,6 +50,17 @@ extern "C" {
     fn qr_build_host(plan: *mut QrPlan, row_lo: u64, row_hi: u64, indptr: *mut u64,
                      indices: *mut u64, data: *mut f64, flags: u32) -> c_int;
     fn qr_apply_host(plan: *mut QrPlan, v: *const f64, y: *mut f64) -> c_int;
+    fn qr_build_compact_count(plan: *mut QrPlan, row_lo: u64, row_hi: u64, tol: f64,
+                              d_indptr: *mut u64, nnz_out: *mut u64, stream: *mut c_void) -> c_int;
+    fn qr_build_compact_fill(plan: *mut QrPlan, row_lo: u64, row_hi: u64, tol: f64, d_indptr: *const u64,
+                             d_indices: *mut u64, d_data: *mut f64, stream: *mut c_void) -> c_int;
+    fn qr_write_rawio(plan: *mut QrPlan, row_lo: u64, row_hi: u64, path: *const c_char) -> c_int;
+    fn qr_precond2_device(n: u64, d_diag: *const f64, d_dx: *const f64, e: *const f64, tol: f64,
+                          d_out: *mut f64, stream: *mut c_void) -> c_int;
+    fn qr_malloc_device(ptr: *mut *mut c_void, bytes: usize) -> c_int;
+    fn qr_free_device(ptr: *mut c_void) -> c_int;
+    fn qr_memcpy_h2d(dst: *mut c_void, src: *const c_void, bytes: usize, stream: *mut c_void) -> c_int;
+    fn qr_memcpy_d2h(dst: *mut c_void, src: *const c_void, bytes: usize, stream: *mut c_void) -> c_int;
     fn qr_device_count(count: *mut c_int) -> c_int;
     fn qr_last_error() -> *const c_char;
     #[allow(dead_code)]
@@ -110,6 +121,40 @@ impl Plan {
         Ok(UnsafeVectors { data, indices, indptr })
     }
 
+    /// The build followed by `util::csmatrix_eliminate_zeroes(m, tol)` (util.rs:154-171) as one device
+    /// pass: counts + prefix scan give indptr and nnz, then only the kept entries are written.
+    pub fn build_rows_compact(&self, row_lo: u64, row_hi: u64, tol: f64) -> Result<UnsafeVectors, QrustyErr> {
+        let rows = (row_hi - row_lo) as usize;
+        let null = std::ptr::null_mut::<c_void>();
+        let (mut d_ptr, mut d_idx, mut d_dat) = (null, null, null);
+        let mut nnz: u64 = 0;
+        check(unsafe { qr_malloc_device(&mut d_ptr, (rows + 1) * 8) })?;
+        let res = (|| {
+            check(unsafe { qr_build_compact_count(self.raw, row_lo, row_hi, tol, d_ptr as *mut u64, &mut nnz, null) })?;
+            let n = nnz as usize;
+            check(unsafe { qr_malloc_device(&mut d_idx, n.max(2) * 8) })?;
+            check(unsafe { qr_malloc_device(&mut d_dat, n.max(1) * 16) })?;
+            check(unsafe { qr_build_compact_fill(self.raw, row_lo, row_hi, tol, d_ptr as *const u64,
+                                                 d_idx as *mut u64, d_dat as *mut f64, null) })?;
+            let mut indptr: Vec<u64> = Vec::with_capacity(rows + 1);
+            let mut indices: Vec<u64> = Vec::with_capacity(n);
+            let mut data: Vec<Complex64> = Vec::with_capacity(n);
+            check(unsafe { qr_memcpy_d2h(indptr.as_mut_ptr() as *mut c_void, d_ptr, (rows + 1) * 8, null) })?;
+            check(unsafe { qr_memcpy_d2h(indices.as_mut_ptr() as *mut c_void, d_idx, n * 8, null) })?;
+            check(unsafe { qr_memcpy_d2h(data.as_mut_ptr() as *mut c_void, d_dat, n * 16, null) })?;
+            unsafe { indptr.set_len(rows + 1); indices.set_len(n); data.set_len(n); }
+            Ok(UnsafeVectors { data, indices, indptr })
+        })();
+        unsafe { qr_free_device(d_ptr); qr_free_device(d_idx); qr_free_device(d_dat); }
+        res
+    }
+
+    /// `rawio::write` (rawio.rs:128-148) of rows [row_lo,row_hi), streamed from the GPU.
+    pub fn write_rawio(&self, row_lo: u64, row_hi: u64, path: &std::path::Path) -> Result<(), QrustyErr> {
+        let c = std::ffi::CString::new(path.to_string_lossy().as_bytes()).map_err(|_| QrustyErr::new("bad path"))?;
+        check(unsafe { qr_write_rawio(self.raw, row_lo, row_hi, c.as_ptr()) })
+    }
+
     /// Matrix-free y = H v (replaces build + `spmat_dot_densevec`, accel.rs:338-370).
     pub fn apply(&self, v: &[Complex64]) -> Result<Vec<Complex64>, QrustyErr> {
         assert_eq!(v.len() as u64, self.info.dim);
@@ -122,6 +167,29 @@ impl Plan {
 
 impl Drop for Plan {
     fn drop(&mut self) { unsafe { qr_plan_destroy(self.raw); } }
+}
+
+/// `precond2` (pyqrusty/src/lib.rs:457-468): dx / reg(diag - e, tol), host slices in and out.
+pub fn precond2(diag: &[Complex64], dx: &[Complex64], e: Complex64, tol: f64) -> Result<Vec<Complex64>, QrustyErr> {
+    assert_eq!(diag.len(), dx.len());
+    let (n, bytes, null) = (dx.len(), dx.len() * 16, std::ptr::null_mut::<c_void>());
+    let (mut d_diag, mut d_dx, mut d_out) = (null, null, null);
+    let res = (|| {
+        check(unsafe { qr_malloc_device(&mut d_diag, bytes.max(16)) })?;
+        check(unsafe { qr_malloc_device(&mut d_dx, bytes.max(16)) })?;
+        check(unsafe { qr_malloc_device(&mut d_out, bytes.max(16)) })?;
+        check(unsafe { qr_memcpy_h2d(d_diag, diag.as_ptr() as *const c_void, bytes, null) })?;
+        check(unsafe { qr_memcpy_h2d(d_dx, dx.as_ptr() as *const c_void, bytes, null) })?;
+        let ev = [e.re, e.im];
+        check(unsafe { qr_precond2_device(n as u64, d_diag as *const f64, d_dx as *const f64, ev.as_ptr(), tol,
+                                          d_out as *mut f64, null) })?;
+        let mut out: Vec<Complex64> = Vec::with_capacity(n);
+        check(unsafe { qr_memcpy_d2h(out.as_mut_ptr() as *mut c_void, d_out, bytes, null) })?;
+        unsafe { out.set_len(n); }
+        Ok(out)
+    })();
+    unsafe { qr_free_device(d_diag); qr_free_device(d_dx); qr_free_device(d_out); }
+    res
 }
 
 pub fn device_count() -> i32 {

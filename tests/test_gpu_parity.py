@@ -191,23 +191,22 @@ def test_blocked_kernel(fixtures, monkeypatch, name, S, E):
             assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
 
 
-@pytest.mark.parametrize("W,NT,sync", [(8, 6, 0), (16, 2, 1), (32, 6, 1), (32, 2, 0)])
+@pytest.mark.parametrize("W,sync", [(8, 0), (16, 1), (32, 1)])
 @pytest.mark.parametrize("R", [5, 6, 8])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
-def test_lanes_kernel(fixtures, monkeypatch, name, R, W, NT, sync):
-    """Large-G path (classify_kernel + fill_lanes_kernel: lane <-> group, rows in Gray-code order,
-    heavy groups on their own CTAs) forced on every case: whole matrix and ragged windows."""
+def test_lanes_kernel(fixtures, monkeypatch, name, R, W, sync):
+    """Large-G path (fill_lanes_kernel: lane <-> group, rows in Gray-code order, heavy groups
+    lane <-> row at the start of every 32-row strip) forced on every case: whole matrix and ragged windows."""
     monkeypatch.setenv("QR_FILL_LANES", "1")
     monkeypatch.setenv("QR_FILL_LANES_R", str(R))
     monkeypatch.setenv("QR_FILL_LANES_W", str(W))
-    monkeypatch.setenv("QR_FILL_LANES_NT", str(NT))
     monkeypatch.setenv("QR_FILL_LANES_SYNC", str(sync))
     labels, coeffs = SMALL[name](fixtures)
     n, params = O.make_params(labels, coeffs)
     ref = O.build_csr(params, n)
     plan = make_op(labels, coeffs).plan()
     G, dim = plan.n_groups, 1 << n
-    assert_same(device_build(plan, 0, dim), ref, f"{name} R={R} W={W} NT={NT} sync={sync}")
+    assert_same(device_build(plan, 0, dim), ref, f"{name} R={R} W={W} sync={sync}")
     if dim >= 128:
         for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 33)]:
             ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="log2 of the row window (default: all rows that fit 8 GB)")
     ap.add_argument("--cfgs", default="auto direct")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--max-gb", type=float, default=8.0, help="cap on the output size of one build")
     a = ap.parse_args()
     labels, coeffs = get_workload(a.workload)
     terms = Q.SparsePauliOp([Q.Pauli(l) for l in labels], coeffs).terms()
@@ -42,13 +43,12 @@ def main():
             os.environ.pop(k)
         if cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
-        elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:NT[:sync]]]]
+        elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:sync]]]
             parts = cfg.split(":")
             os.environ["QR_FILL_LANES"] = "1"
             if len(parts) > 1: os.environ["QR_FILL_LANES_R"] = parts[1]
             if len(parts) > 2: os.environ["QR_FILL_LANES_W"] = parts[2]
-            if len(parts) > 3: os.environ["QR_FILL_LANES_NT"] = parts[3]
-            if len(parts) > 4: os.environ["QR_FILL_LANES_SYNC"] = parts[4]
+            if len(parts) > 3: os.environ["QR_FILL_LANES_SYNC"] = parts[3]
         elif cfg.startswith("blocked"):               # blocked[:S[:E]]
             parts = cfg.split(":")
             os.environ["QR_FILL_LANES"] = "0"
@@ -62,7 +62,7 @@ def main():
         rows = dim
         if a.rows is not None:
             rows = min(dim, 1 << a.rows)
-        while rows * G * 24 > 8e9:
+        while rows * G * 24 > a.max_gb * 1e9:
             rows //= 2
         if bufs is None:
             bufs = (DeviceBuffer((rows + 1) * 8), DeviceBuffer(rows * G * 8), DeviceBuffer(rows * G * 16))
