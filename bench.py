@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-hv", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     return ap.parse_args()
 
 
@@ -367,6 +368,71 @@ def run_b200(args, rank, local_rank, world):
                "path": "SparsePauliOp.from_terms(terms).to_matrix_mode('Cuda').export(): plan (H2D + K1), K3, D2H of the CSR into pinned host arrays (per rank: its row block)"}
     barrier()
 
+    # ---- extras (N=1 only): the other regimes of the build, each timed with events on `stream` --------
+    extras = {}
+    if world == 1 and not args.no_extras:
+        peak, _ = peak_hbm()
+
+        def timed(fn, reps):
+            for _ in range(3):
+                fn()
+            call("qr_stream_synchronize", stream)
+            a, b = ev(), ev()
+            call("qr_event_record", a, stream)
+            for _ in range(reps):
+                fn()
+            call("qr_event_record", b, stream)
+            call("qr_stream_synchronize", stream)
+            return elapsed(a, b) / reps
+
+        # (1) BASELINE config 3: random 2000-term sum, G = 1500 -> the large-G (lanes) kernel on a row window
+        from qrusty_b200 import hamiltonians as H
+        cl, cc = H.random_pauli_sum(24, 2000, 1500, 100, 24)
+        cplan = Q.SparsePauliOp([Q.Pauli(l) for l in cl], cc).plan(device)
+        crow = 1 << 18                                                  # 9.4 GB per window (2^18-row windows)
+        cG = cplan.n_groups
+        c_ip, c_ix, c_dt = DeviceBuffer((crow + 1) * 8, device), DeviceBuffer(crow * cG * 8, device), DeviceBuffer(crow * cG * 16, device)
+        clo = (cplan.dim // 2)
+        ms = timed(lambda: call("qr_build_rows_device", cplan.handle, clo, clo + crow, c_ip.ptr, c_ix.ptr, c_dt.ptr, 0, stream), 5)
+        cbytes = crow * cG * 24 + (crow + 1) * 8
+        extras["large_g"] = {"workload": "random_T2000_n24 (BASELINE config 3), rows [2^23, 2^23 + 2^18)", "n_groups": cG,
+                             "kernel": "fill_lanes_kernel", "ms": ms, "nnz_per_s": crow * cG / ms * 1e3,
+                             "achieved_GBps": cbytes / ms / 1e6, "frac_of_peak": cbytes / ms / 1e6 / peak}
+        del c_ip, c_ix, c_dt, cplan
+
+        # (2) fused drop-zeros build of the bench operator: count_rows + scan + fill_compact
+        kept = C.c_uint64()
+        z_ip = DeviceBuffer((rows + 1) * 8, device)
+        call("qr_build_compact_count", plan.handle, lo, hi, 1e-7, z_ip.ptr, C.byref(kept), stream)
+        z_ix, z_dt = DeviceBuffer(max(kept.value * 8, 16), device), DeviceBuffer(max(kept.value * 16, 16), device)
+
+        def drop_zeros():
+            k2 = C.c_uint64()
+            call("qr_build_compact_count", plan.handle, lo, hi, 1e-7, z_ip.ptr, C.byref(k2), stream)
+            call("qr_build_compact_fill", plan.handle, lo, hi, 1e-7, z_ip.ptr, z_ix.ptr, z_dt.ptr, stream)
+        ms = timed(drop_zeros, 10)
+        extras["drop_zeros"] = {"workload": name, "tolerance": 1e-7, "stored_entries": int(nnz_local), "kept_entries": int(kept.value),
+                                "ms": ms, "kept_nnz_per_s": kept.value / ms * 1e3, "entries_evaluated_per_s": 2 * nnz_local / ms * 1e3,
+                                "bytes_written": int(kept.value * 24 + (rows + 1) * 8),
+                                "note": "count_rows_kernel + 3 scan kernels + fill_compact_kernel; includes one 8-byte D2H of nnz"}
+        del z_ip, z_ix, z_dt
+
+        # (3) e2e with ORDINARY (pageable) numpy arrays as the destination -- what a Rust Vec is
+        p_ip, p_ix, p_dt = np.empty(rows + 1, np.uint64), np.empty(nnz_local, np.uint64), np.empty(nnz_local, np.complex128)
+        p_ix[:] = 0; p_dt[:] = 0; p_ip[:] = 0                            # fault the pages in once, as a reused buffer would be
+
+        def e2e_pageable(flags):
+            t0 = time.perf_counter()
+            o = Q.SparsePauliOp.from_terms(n, op.terms())
+            call("qr_build_host", o.plan(device).handle, lo, hi, p_ip.ctypes.data, p_ix.ctypes.data, p_dt.ctypes.data, flags)
+            return time.perf_counter() - t0
+        for fl, key in ((0, "staged"), (_ffi.QR_HOST_NO_STAGING, "plain_cudaMemcpy")):
+            e2e_pageable(fl)
+            t = float(np.median([e2e_pageable(fl) for _ in range(5)]))
+            extras.setdefault("e2e_pageable", {})[key] = {"ms": t * 1e3, "nnz_per_s": nnz_local / t}
+        extras["e2e_pageable"]["note"] = ("qr_build_host into plain numpy arrays: pinned staging windows + host copy threads vs "
+                                          "cudaMemcpy straight into pageable memory")
+
     if rank == 0:
         peak, peak_src = peak_hbm()
         achieved = bytes_local / (fill_ms * 1e-3) / 1e9
@@ -389,6 +455,8 @@ def run_b200(args, rank, local_rank, world):
             line["hv"] = hv
         if e2e:
             line["e2e"] = e2e
+        if extras:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_build_rate(labels, coeffs, budget_s=12.0)
         print(json.dumps(line), flush=True)

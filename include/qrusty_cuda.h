@@ -116,7 +116,10 @@ QR_API int qr_build_rows_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
 
 /* Same, into caller-allocated HOST buffers (what the Rust shim hands to
  * CsMatI::new_unchecked): builds on the device in row windows and copies back.
- * Synchronous.  Pinned host buffers (qr_malloc_host) copy fastest. */
+ * Synchronous.  Page-locked buffers (qr_malloc_host) receive the windows directly; ordinary
+ * pageable memory (a Rust Vec, a numpy array) is filled through pinned staging windows by a
+ * few host threads, which keeps the PCIe copy at full rate (QR_HOST_NO_STAGING: plain cudaMemcpy). */
+#define QR_HOST_NO_STAGING 4u
 QR_API int qr_build_host(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
                   uint64_t *indptr, uint64_t *indices, double *data, uint32_t flags);
 

@@ -11,7 +11,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("QRUSTY_CUDA_LIB", _PKG / "lib" / "libqrusty_cuda.so"))
 
 QR_OK, QR_ERR_INVALID, QR_ERR_CUDA, QR_ERR_NCCL, QR_ERR_OOM, QR_ERR_UNSUPPORTED = range(6)
-QR_INDPTR_LOCAL, QR_INDPTR_GLOBAL, QR_FILL_DIRECT = 0, 1, 2
+QR_INDPTR_LOCAL, QR_INDPTR_GLOBAL, QR_FILL_DIRECT, QR_HOST_NO_STAGING = 0, 1, 2, 4
 QR_PLAN_MERGE_DUPLICATES = 1
 QR_UNIQUE_ID_BYTES = 128
 QR_IPC_HANDLE_BYTES = 64

@@ -372,35 +372,166 @@ __device__ __forceinline__ void st_global_u64(uintptr_t addr, uint64_t v)
 constexpr int FILL_LANES_NT = 6;
 constexpr int FILL_LANES_MAXLOG2R = 12;
 
+// CTA-wide barrier that does not care which code path a warp arrives from (the warps of a CTA run
+// differently specialised row walks): bar.sync on a named barrier with an explicit thread count.
+__device__ __forceinline__ void lanes_barrier(uint32_t n_threads)
+{
+    asm volatile("bar.sync 1, %0;" :: "r"(n_threads) : "memory");
+}
+// The same across the thread-block cluster that holds the sibling CTAs of a row run (pure
+// rendezvous: no data is exchanged, so the relaxed form is enough).
+__device__ __forceinline__ void lanes_cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
+struct LanesCtx {
+    const PlanDev *p;
+    uintptr_t dptr, iptr;          // outputs, pre-offset to the run's first row
+    const uint32_t *s_heavy;       // heavy groups of this CTA
+    uint32_t n_heavy, G, r0, R, resync, n_threads, lane, warp, n_warps;   // resync: 0 none, 1 CTA, 2 cluster
+};
+
+// heavy groups of the CTA for the 32-row strip that holds r: lane <-> row, round-robin over warps
+__device__ __forceinline__ void lanes_heavy_strip(const LanesCtx &c, uint32_t r)
+{
+    const PlanDev &p = *c.p;
+    const uint32_t wbase = r & ~31u, rr = wbase + c.lane;
+    for (uint32_t q = c.warp; q < c.n_heavy; q += c.n_warps) {
+        const uint32_t hg = c.s_heavy[q];
+        const GroupDesc d = p.gdesc[hg];
+        const uint32_t slot = group_slot(p, hg, d.x, wbase, c.lane);
+        const double2 v = group_value(p.tz, p.tc, d.t0, d.t1, rr);
+        const uint32_t o = (rr - c.r0) * c.G + slot;
+        st_global_f64x2(c.dptr + ((size_t)o << 4), v.x, v.y);
+        st_global_u64(c.iptr + ((size_t)o << 3), (uint64_t)(rr ^ d.x));
+    }
+}
+
+// The Gray-code row walk of one warp, specialised for the number K of terms its longest light
+// group holds (a warp-uniform switch picks the instance, so no slot is spent on absent terms).
+// K == 0: the warp owns no groups and only takes part in the heavy strips and the barriers.
+template <int K, int NT>
+__device__ __forceinline__ void lanes_walk(const LanesCtx &c, bool active, uint32_t x, uint32_t off,
+                                           int32_t d0, int32_t d1, int32_t d2, int32_t *s_delta /* [bit-3][32] + lane */,
+                                           const uint32_t (&z)[NT], const double (&cr)[NT], const double (&ci)[NT])
+{
+    uint32_t r = c.r0;                                             // warp-uniform current row
+    // +-1.0 from the parity of r & z: (+-1.0) * c' and fma(+-1.0, c', acc) are exactly the sign flip
+    // and the __dadd_rn of the reference fold (accel.rs:191-205), signed zeros included
+    auto sign_of = [](uint32_t m) { return __hiloint2double((int)(0x3ff00000u | ((uint32_t)__popc(m) << 31)), 0); };
+    auto emit = [&]() {
+        if (K == 0) return;
+        const double s0 = sign_of(r & z[0]);
+        double re = __dmul_rn(s0, cr[0]), im = __dmul_rn(s0, ci[0]);
+#pragma unroll
+        for (int t = 1; t < K; t++) {
+            const double sg = sign_of(r & z[t]);
+            re = __fma_rn(sg, cr[t], re); im = __fma_rn(sg, ci[t], im);
+        }
+        if (active) {
+            st_global_f64x2(c.dptr + ((size_t)off << 4), re, im);
+            st_global_u64(c.iptr + ((size_t)off << 3), (uint64_t)(r ^ x));
+        }
+    };
+    for (uint32_t i = 0; i < c.R; i += 8u) {
+        if (i != 0u) {                                             // Gray code: step i flips bit ctz(i) >= 3
+            if ((i & 31u) == 0u) {                                 // keep every writer of these rows on the same strip
+                if (c.resync == 2u) lanes_cluster_barrier(); else if (c.resync == 1u) lanes_barrier(c.n_threads);
+            }
+            const uint32_t b = (uint32_t)__ffs((int)i) - 1u;
+            r ^= 1u << b;
+            if (K != 0) {
+                const int32_t st = s_delta[(b - 3u) * 32u];
+                off += (uint32_t)st;
+                s_delta[(b - 3u) * 32u] = -st;
+            }
+        }
+        if ((i & 31u) == 0u && c.n_heavy != 0u) lanes_heavy_strip(c, r);
+        emit();
+        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+        r ^= 2u; off += (uint32_t)d1; d1 = -d1; emit();
+        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+        r ^= 4u; off += (uint32_t)d2; d2 = -d2; emit();
+        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+        r ^= 2u; off += (uint32_t)d1; d1 = -d1; emit();
+        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+    }
+}
+
+// All runs of one persistent CTA for a fixed K (only the first K terms stay live in registers).
+template <int K, int NT, int LW>
+__device__ __forceinline__ void lanes_runs(LanesCtx &c, uint32_t j0, uint32_t J, uint32_t n_runs, uint32_t log2R, uint32_t beta,
+                                           bool warp_live, bool active, uint32_t x, const uint32_t *s_cnt, int32_t *sd,
+                                           uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base, uint64_t *indptr,
+                                           uint64_t *indices, double2 *data, uint64_t indptr_last_row,
+                                           const uint32_t (&z)[NT], const double (&cr)[NT], const double (&ci)[NT])
+{
+    const uint32_t nq = (uint32_t)c.p->n_qubits, G = c.G, R = c.R;
+    for (uint32_t run = j0; run < n_runs; run += J) {
+        const uint64_t r0_64 = tile_row0 + (uint64_t)run * R;      // first row of the run (aligned to R)
+        const uint32_t r0 = (uint32_t)r0_64;
+        if (beta == 0 && indptr != nullptr) {
+            for (uint32_t i = threadIdx.x; i < R; i += 32 * LW) {
+                const uint64_t lr = r0_64 + i - row_lo;
+                indptr[lr] = indptr_base + lr * G;
+                if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+            }
+        }
+        // entry offset (in entries, relative to the run's first row) at the first row of the run, and
+        // the signed step for every row bit of the run.  Flipping row bit b moves the row by +-2^b (the
+        // offset by +-G*2^b) and the slot by +-cnt[g][b]; both signs alternate with every flip of b, so
+        // one signed step per (lane, bit) carries both.  R*G*16 < 2^32 (host-checked): 32-bit byte offsets.
+        uint32_t off = 0;
+        int32_t d0 = 0, d1 = 0, d2 = 0;
+        if (warp_live) {
+            const uint32_t xr = x ^ r0;
+            for (uint32_t b = 0; b < nq; b++) {
+                const uint32_t cb = s_cnt[b * 32u];
+                const bool one = (xr >> b) & 1u;
+                if (one) off += cb;
+                if (b < log2R) {
+                    // r0 is aligned to R: its bits < log2R are 0, the first flip of b moves the row up
+                    const int32_t step = (one ? -(int32_t)cb : (int32_t)cb) + (int32_t)(G << b);
+                    if (b == 0) d0 = step; else if (b == 1) d1 = step; else if (b == 2) d2 = step;
+                    else sd[(b - 3u) * 32u] = step;
+                }
+            }
+        }
+        c.dptr = reinterpret_cast<uintptr_t>(data + (r0_64 - row_lo) * G);
+        c.iptr = reinterpret_cast<uintptr_t>(indices + (r0_64 - row_lo) * G);
+        c.r0 = r0;
+        // the CTA's warps -- with a cluster launch: all CTAs that write these rows -- start the run together
+        if (c.resync == 2u) lanes_cluster_barrier(); else if (c.resync == 1u) lanes_barrier(c.n_threads);
+        lanes_walk<K, NT>(c, active, x, off, d0, d1, d2, sd, z, cr, ci);
+    }
+}
+
+// Persistent CTAs: CTA (beta, j) owns the 32*LW groups of batch beta for good -- masks and terms
+// stay in registers, the groups' rank-table columns in shared memory -- and takes the runs
+// j, j + J, j + 2J, ... of the window; sibling CTAs (same j, other batches) take the same runs in
+// the same order.  Per run only the entry offsets are re-derived (from shared memory, no global
+// load), so short runs (R = 32: all of a row's segments are written within a few microseconds of
+// each other) cost no memory latency.
 template <int NT, int LW>
 __global__ void __launch_bounds__(32 * LW, 32 / LW)
-fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint32_t resync,
+fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint32_t resync, uint32_t n_runs,
                   uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
                   uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
                   double2 *__restrict__ data, uint64_t indptr_last_row)
 {
+    extern __shared__ uint32_t s_cnt_all[];                        // [LW][n_qubits][32]: cnt[g][b] of the warp's groups
     __shared__ int32_t s_delta[LW][FILL_LANES_MAXLOG2R - 3][32];   // signed step of the row bits b >= 3
     __shared__ uint32_t s_heavy[LW * 32];                          // heavy groups of this CTA's blocks
     __shared__ uint32_t s_nheavy;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t rho = blockIdx.x / n_light, beta = blockIdx.x % n_light;
-    const uint32_t R = 1u << log2R;
-    const uint64_t r0_64 = tile_row0 + (uint64_t)rho * R;          // first row of the run (aligned to R)
-    const uint32_t r0 = (uint32_t)r0_64;
-    const uintptr_t dptr = reinterpret_cast<uintptr_t>(data + (r0_64 - row_lo) * G);
-    const uintptr_t iptr = reinterpret_cast<uintptr_t>(indices + (r0_64 - row_lo) * G);
+    const uint32_t beta = blockIdx.x % n_light, j0 = blockIdx.x / n_light, J = gridDim.x / n_light;
+    const uint32_t R = 1u << log2R, nq = (uint32_t)p.n_qubits;
 
     if (threadIdx.x == 0) s_nheavy = 0;
-    if (beta == 0 && indptr != nullptr) {
-        for (uint32_t i = threadIdx.x; i < R; i += 32 * LW) {
-            const uint64_t lr = r0_64 + i - row_lo;
-            indptr[lr] = indptr_base + lr * G;
-            if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
-        }
-    }
     __syncthreads();
 
-    // ---- warp <-> block of 32 groups, lane <-> group ---------------------------------------------
+    // ---- once per CTA: warp <-> block of 32 groups, lane <-> group -----------------------------------
     const uint32_t g = (beta * LW + warp) * 32u + lane;
     const bool warp_live = (beta * LW + warp) * 32u < G;          // warp-uniform
     uint32_t x = 0, nt = 0, t0 = 0;
@@ -418,89 +549,34 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
         if ((uint32_t)t < nt) { z[t] = __ldg(&p.tz[t0 + t]); const double2 c = __ldg(&p.tc[t0 + t]); cr[t] = c.x; ci[t] = c.y; }
     }
     const uint32_t nt_max = __reduce_max_sync(0xffffffffu, nt);
-    // entry offset (in entries, relative to the run's first row) at the first row of the run, and
-    // the signed step for every row bit of the run.  Flipping row bit b moves the row by +-2^b (the
-    // offset by +-G*2^b) and the slot by +-cnt[g][b]; both signs alternate with every flip of b, so
-    // one signed step per (lane, bit) carries both.  R*G*16 < 2^32 (host-checked): 32-bit byte offsets.
-    uint32_t off = 0;
-    int32_t d0 = 0, d1 = 0, d2 = 0;
+    uint32_t *s_cnt = s_cnt_all + (size_t)warp * nq * 32u + lane;   // this lane's column: s_cnt[b * 32]
     if (warp_live) {
-        const uint32_t nq = (uint32_t)p.n_qubits, T = p.n_terms, gg = g < G ? g : G - 1u;
-#pragma unroll
-        for (uint32_t b0 = 0; b0 < 32u; b0 += 8u) {
-            if (b0 >= nq) break;
-            uint32_t c[8];
-#pragma unroll
-            for (uint32_t j = 0; j < 8u; j++) c[j] = b0 + j < nq ? __ldg(&p.cnt_t[(b0 + j) * T + gg]) : 0u;   // coalesced, independent
-#pragma unroll
-            for (uint32_t j = 0; j < 8u; j++) {
-                const uint32_t b = b0 + j;
-                const bool one = ((x ^ r0) >> b) & 1u;
-                if (one) off += c[j];
-                // r0 is aligned to R: its bits < log2R are 0, the first flip of b moves the row up
-                const int32_t step = (one ? -(int32_t)c[j] : (int32_t)c[j]) + (int32_t)(G << b);
-                if (b == 0) d0 = step; else if (b == 1) d1 = step; else if (b == 2) d2 = step;
-                else if (b < (uint32_t)FILL_LANES_MAXLOG2R && b < log2R) s_delta[warp][b - 3][lane] = step;
-            }
-        }
+        const uint32_t T = p.n_terms, gg = g < G ? g : G - 1u;
+        for (uint32_t b = 0; b < nq; b++) s_cnt[b * 32u] = __ldg(&p.cnt_t[b * T + gg]);        // coalesced
     }
     __syncthreads();                                               // s_heavy complete
-    const uint32_t n_heavy = s_nheavy;
 
-    uint32_t r = r0;                                               // warp-uniform current row
-    // +-1.0 from the parity of r & z: (+-1.0) * c' and fma(+-1.0, c', acc) are exactly the sign flip
-    // and the __dadd_rn of the reference fold (accel.rs:191-205), signed zeros included
-    auto sign_of = [](uint32_t m) { return __hiloint2double((int)(0x3ff00000u | ((uint32_t)__popc(m) << 31)), 0); };
-    auto emit = [&]() {
-        const double s0 = sign_of(r & z[0]);
-        double re = __dmul_rn(s0, cr[0]), im = __dmul_rn(s0, ci[0]);
-#pragma unroll
-        for (int t = 1; t < NT; t++) {
-            if ((uint32_t)t < nt_max) {                            // warp-uniform
-                const double sg = sign_of(r & z[t]);
-                re = __fma_rn(sg, cr[t], re); im = __fma_rn(sg, ci[t], im);
-            }
-        }
-        if (active) {
-            st_global_f64x2(dptr + ((size_t)off << 4), re, im);
-            st_global_u64(iptr + ((size_t)off << 3), (uint64_t)(r ^ x));
-        }
-    };
-    // heavy groups of the CTA for the 32-row strip that holds r: lane <-> row, round-robin over warps
-    auto heavy_strip = [&]() {
-        const uint32_t wbase = r & ~31u, rr = wbase + lane;
-        for (uint32_t q = warp; q < n_heavy; q += LW) {
-            const uint32_t hg = s_heavy[q];
-            const GroupDesc d = p.gdesc[hg];
-            const uint32_t slot = group_slot(p, hg, d.x, wbase, lane);
-            const double2 v = group_value(p.tz, p.tc, d.t0, d.t1, rr);
-            const uint32_t o = (rr - r0) * G + slot;
-            st_global_f64x2(dptr + ((size_t)o << 4), v.x, v.y);
-            st_global_u64(iptr + ((size_t)o << 3), (uint64_t)(rr ^ d.x));
-        }
-    };
-    for (uint32_t i = 0; i < R; i += 8u) {
-        if (i != 0u) {                                             // Gray code: step i flips bit ctz(i) >= 3
-            if (resync && (i & 31u) == 0u) __syncthreads();        // keep the CTA's warps on the same rows
-            const uint32_t b = (uint32_t)__ffs((int)i) - 1u;
-            r ^= 1u << b;
-            if (warp_live) {
-                const int32_t st = s_delta[warp][b - 3][lane];
-                off += (uint32_t)st;
-                s_delta[warp][b - 3][lane] = -st;
-            }
-        }
-        if ((i & 31u) == 0u && n_heavy != 0u) heavy_strip();
-        if (!warp_live) { r ^= 4u; continue; }                     // the 8 steps below leave r ^ 4 (Gray: 0,1,3,2,6,7,5,4)
-        emit();
-        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
-        r ^= 2u; off += (uint32_t)d1; d1 = -d1; emit();
-        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
-        r ^= 4u; off += (uint32_t)d2; d2 = -d2; emit();
-        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
-        r ^= 2u; off += (uint32_t)d1; d1 = -d1; emit();
-        r ^= 1u; off += (uint32_t)d0; d0 = -d0; emit();
+    LanesCtx c;
+    c.p = &p;
+    c.s_heavy = s_heavy; c.n_heavy = s_nheavy; c.G = G; c.R = R; c.resync = resync;
+    c.n_threads = 32u * LW; c.lane = lane; c.warp = warp; c.n_warps = LW;
+    int32_t *sd = &s_delta[warp][0][lane];
+    const uint32_t k_sel = warp_live ? (nt_max == 0u ? 1u : nt_max) : 0u;   // all-heavy live warp: K = 1, stores off
+
+    static_assert(NT == 6, "the switch below enumerates 0..NT terms");
+#define QR_LANES_RUNS(K_, ACT_)                                                                                         \
+    lanes_runs<K_, NT, LW>(c, j0, J, n_runs, log2R, beta, warp_live, ACT_, x, s_cnt, sd, tile_row0, row_lo, indptr_base, \
+                           indptr, indices, data, indptr_last_row, z, cr, ci)
+    switch (k_sel) {                                               // warp-uniform, once per CTA
+    case 0: QR_LANES_RUNS(0, false); break;
+    case 1: QR_LANES_RUNS(1, active); break;
+    case 2: QR_LANES_RUNS(2, active); break;
+    case 3: QR_LANES_RUNS(3, active); break;
+    case 4: QR_LANES_RUNS(4, active); break;
+    case 5: QR_LANES_RUNS(5, active); break;
+    default: QR_LANES_RUNS(6, active); break;
     }
+#undef QR_LANES_RUNS
 }
 
 }  // namespace qr

@@ -11,7 +11,9 @@
 #include <unistd.h>
 #include <new>
 #include <map>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -54,7 +56,10 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr size_t MAX_SMEM = 227 * 1024;
 
 // qr_build_host's device-side staging (two row windows, two streams), one set per device
-struct WinScratch { void *buf[2] = {nullptr, nullptr}; size_t bytes = 0; cudaStream_t stream[2] = {nullptr, nullptr}; };
+struct WinScratch {
+    void *buf[2] = {nullptr, nullptr}; size_t bytes = 0; cudaStream_t stream[2] = {nullptr, nullptr};
+    void *host[2] = {nullptr, nullptr}; size_t host_bytes = 0;     // pinned staging for pageable destinations
+};
 std::mutex g_win_mutex;
 std::map<int, WinScratch> g_win;
 
@@ -82,7 +87,7 @@ struct qr_plan {
     int rw = 0, gw = 0;
     uint32_t block_s = 0, n_blocks = 0;    // blocked kernel: S and the number of subtree blocks
     // lanes kernel (large G, default): rows per run = 2^lanes_log2r, warps per CTA, heavy groups
-    int lanes = 0, lanes_log2r = 0, lanes_warps = 0, lanes_resync = 1;
+    int lanes = 0, lanes_log2r = 0, lanes_warps = 0, lanes_resync = 2, lanes_persist = 0;
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -139,11 +144,15 @@ void choose_staged(qr_plan *pl)
     const uint64_t G = pl->n_groups;
     pl->block_s = 0;
     pl->lanes = 0;
-    pl->lanes_log2r = 8; pl->lanes_warps = 16;
+    // measured (profiles/r02_lanes_sweep.jsonl): runs of 32 rows, one run per CTA, 8 warps up to 1024 groups
+    // and 16 beyond, sibling CTAs as one cluster: C3 4.85 TB/s, H10 2.53, H12 2.82, H8 2.15
+    pl->lanes_log2r = 5; pl->lanes_warps = G <= 1024 ? 8 : 16;
     if (const char *env = getenv("QR_FILL_LANES_R")) { int k = atoi(env); if (k >= 5 && k <= qr::FILL_LANES_MAXLOG2R) pl->lanes_log2r = k; }
     if (const char *env = getenv("QR_FILL_LANES_W")) { int w = atoi(env); if (w == 8 || w == 16 || w == 32) pl->lanes_warps = w; }
-    pl->lanes_resync = 1;
-    if (const char *env = getenv("QR_FILL_LANES_SYNC")) pl->lanes_resync = env[0] != '0';
+    pl->lanes_resync = 2;                                            // 0 none, 1 per CTA, 2 per cluster of sibling CTAs
+    if (const char *env = getenv("QR_FILL_LANES_SYNC")) { int v = atoi(env); if (v >= 0 && v <= 2) pl->lanes_resync = v; }
+    pl->lanes_persist = 0;                                           // 1: persistent CTAs looping over runs (measured slower)
+    if (const char *env = getenv("QR_FILL_LANES_PERSIST")) pl->lanes_persist = env[0] != '0';
     if (const char *env = getenv("QR_FILL_LANES")) if (env[0] == '1') { pl->lanes = 1; return; }   // force (tests, sweeps)
     if (const char *env = getenv("QR_FILL_BLOCK")) {         // "S" override: force the blocked kernel
         int S = atoi(env);
@@ -361,17 +370,47 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         if (s1 > s0 && (G << k) < (1ull << 28)) {
             const uint32_t LW = (uint32_t)pl->lanes_warps;
             const uint32_t n_light = (uint32_t)((G + 32ull * LW - 1) / (32ull * LW));
-            const uint64_t ctas = (s1 - s0) / R * n_light;
-            if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_lanes: row window too large for one launch");
+            // persistent CTAs: J groups of n_light sibling CTAs, as many as are resident at once
+            const uint64_t n_runs = (s1 - s0) / R;
+            if (n_runs > 0xffffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_lanes: row window too large for one launch");
+            const uint32_t resident = 148u * (32u / LW);
+            const uint64_t J = std::min<uint64_t>(n_runs, std::max<uint32_t>(1u, (resident + n_light - 1) / n_light));
+            uint64_t J2 = pl->lanes_persist ? J : n_runs;
+            if (J2 * n_light > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_lanes: row window too large for one launch");
+            const size_t smem = (size_t)LW * pl->n_qubits * 32 * 4;
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
-            using LanesFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t,
-                                     uint64_t *, uint64_t *, double2 *, uint64_t);
+            using LanesFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t,
+                                     uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
             const LanesFn kern = LW == 8 ? (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 8>
                                : LW == 32 ? (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 32>
                                           : (LanesFn)qr::fill_lanes_kernel<qr::FILL_LANES_NT, 16>;
-            kern<<<(unsigned)ctas, 32 * LW, 0, st>>>(pl->dev, (uint32_t)G, n_light, (uint32_t)k, (uint32_t)pl->lanes_resync, s0,
-                                                     row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo);
+            QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // sibling CTAs (the other group batches of the same rows) form one thread-block cluster and
+            // rendezvous every 32 rows: every segment of a row is written in the same short time window
+            const bool cluster = pl->lanes_resync == 2 && n_light > 1 && n_light <= 8;
+            uint32_t resync = (uint32_t)pl->lanes_resync;
+            if (resync == 2 && !cluster) resync = 1;
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(32 * LW, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            if (cluster) {
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = n_light; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                cfg.gridDim = dim3(n_light, 1, 1);
+                int max_clusters = 0;
+                if (!pl->lanes_persist) { /* one cluster per run */ }
+                else if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0)
+                    J2 = std::min<uint64_t>(n_runs, (uint64_t)max_clusters);
+                else
+                    cudaGetLastError();
+            }
+            cfg.gridDim = dim3((unsigned)(J2 * n_light), 1, 1);
+            QR_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->dev, (uint32_t)G, n_light, (uint32_t)k, resync, (uint32_t)n_runs, s0, row_lo,
+                                       indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo));
             QR_LAUNCH_CHECK("fill_lanes_kernel");
             return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
         }
@@ -435,6 +474,87 @@ extern "C" int qr_build_rows_device(qr_plan *pl, uint64_t row_lo, uint64_t row_h
     return build_rows(pl, row_lo, row_hi, d_indptr, d_indices, reinterpret_cast<double2 *>(d_data), flags, as_stream(stream));
 }
 
+namespace {
+
+// Copies a list of (dst, src, bytes) pieces with several host threads (the calling thread included).
+// Used when the caller's output arrays are ordinary pageable memory (a Rust Vec, a numpy array):
+// cudaMemcpy into pageable memory runs at about a third of the PCIe rate, so the windows land in
+// pinned staging at full rate and are moved on by the host cores while the next window is in flight.
+struct CopyPiece { char *dst; const char *src; size_t bytes; };
+
+class CopyPool {
+public:
+    explicit CopyPool(unsigned n_threads)
+    {
+        for (unsigned i = 1; i < n_threads; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void run(const std::vector<CopyPiece> &pieces)
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            pieces_ = &pieces; next_.store(0); busy_ = (unsigned)workers_.size(); gen_++;
+        }
+        cv_.notify_all();
+        drain();
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return busy_ == 0; });
+    }
+private:
+    void drain()
+    {
+        for (;;) {
+            const size_t i = next_.fetch_add(1);
+            if (i >= pieces_->size()) return;
+            const CopyPiece &c = (*pieces_)[i];
+            memcpy(c.dst, c.src, c.bytes);
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            drain();
+            { std::lock_guard<std::mutex> l(m_); if (--busy_ == 0) done_.notify_one(); }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::vector<CopyPiece> *pieces_ = nullptr;
+    std::atomic<size_t> next_{0};
+    unsigned busy_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+bool is_page_locked(const void *ptr)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void add_pieces(std::vector<CopyPiece> &v, void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t CH = 2u << 20;
+    for (size_t o = 0; o < bytes; o += CH)
+        v.push_back({static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, std::min(CH, bytes - o)});
+}
+
+}  // namespace
+
 extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *indptr,
                              uint64_t *indices, double *data, uint32_t flags)
 {
@@ -445,7 +565,9 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
     // Row windows through two device buffers / two streams, so the fill of window
     // k+1 overlaps the PCIe copy of window k (host buffers should be pinned for that).
     const uint64_t per_row = G * 24 + 8;
-    uint64_t win_rows = (256ull << 20) / per_row;
+    // pageable destination (not cudaHostAlloc'ed / registered): smaller windows through pinned staging
+    const bool staged = !(flags & QR_HOST_NO_STAGING) && (!is_page_locked(data) || !is_page_locked(indices));
+    uint64_t win_rows = ((staged ? 32ull : 256ull) << 20) / per_row;
     if (win_rows >= rows) win_rows = rows;
     else { win_rows = win_rows / 256 * 256; if (win_rows == 0) win_rows = 32; }
     const size_t idx_bytes = align_up(win_rows * G * 8, 256), dat_bytes = align_up(win_rows * G * 16, 256);
@@ -464,6 +586,56 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
     }
     for (int i = 0; i < 2; i++)
         if (!ws.stream[i]) QR_CUDA(cudaStreamCreateWithFlags(&ws.stream[i], cudaStreamNonBlocking));
+
+    if (staged) {
+        if (ws.host_bytes < need) {
+            for (int i = 0; i < 2; i++) { if (ws.host[i]) cudaFreeHost(ws.host[i]); ws.host[i] = nullptr; }
+            ws.host_bytes = 0;
+            for (int i = 0; i < 2; i++) QR_CUDA(cudaMallocHost(&ws.host[i], need));
+            ws.host_bytes = need;
+        }
+        unsigned n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char *env = getenv("QR_HOST_COPY_THREADS")) { int t = atoi(env); if (t >= 1 && t <= 64) n_threads = (unsigned)t; }
+        CopyPool pool(n_threads);
+        std::vector<CopyPiece> pieces;
+        const uint64_t n_win = (rows + win_rows - 1) / win_rows;
+        auto submit = [&](uint64_t w) -> int {                      // fill window w, copy it to pinned staging
+            const uint64_t w0 = row_lo + w * win_rows, w1 = std::min(row_hi, w0 + win_rows), n = w1 - w0;
+            const int k = (int)(w & 1);
+            char *buf = static_cast<char *>(ws.buf[k]);
+            int rc = build_rows(pl, w0, w1, indptr ? reinterpret_cast<uint64_t *>(buf + dat_bytes + idx_bytes) : nullptr,
+                                reinterpret_cast<uint64_t *>(buf + dat_bytes), reinterpret_cast<double2 *>(buf),
+                                QR_INDPTR_GLOBAL, ws.stream[k]);
+            if (rc != QR_OK) return rc;
+            char *h = static_cast<char *>(ws.host[k]);
+            QR_CUDA(cudaMemcpyAsync(h, buf, n * G * 16, cudaMemcpyDeviceToHost, ws.stream[k]));
+            QR_CUDA(cudaMemcpyAsync(h + dat_bytes, buf + dat_bytes, n * G * 8, cudaMemcpyDeviceToHost, ws.stream[k]));
+            if (indptr) QR_CUDA(cudaMemcpyAsync(h + dat_bytes + idx_bytes, buf + dat_bytes + idx_bytes, (n + 1) * 8,
+                                                cudaMemcpyDeviceToHost, ws.stream[k]));
+            return QR_OK;
+        };
+        int rc = submit(0);
+        for (uint64_t w = 0; w < n_win && rc == QR_OK; w++) {
+            if (w + 1 < n_win) rc = submit(w + 1);                   // the other staging buffer is free: its copy-out finished
+            if (rc != QR_OK) break;
+            const int k = (int)(w & 1);
+            QR_CUDA(cudaStreamSynchronize(ws.stream[k]));
+            const uint64_t w0 = row_lo + w * win_rows, n = std::min(row_hi, w0 + win_rows) - w0, o = (w0 - row_lo) * G;
+            const char *h = static_cast<const char *>(ws.host[k]);
+            pieces.clear();
+            add_pieces(pieces, data + 2 * o, h, n * G * 16);
+            add_pieces(pieces, indices + o, h + dat_bytes, n * G * 8);
+            if (indptr) add_pieces(pieces, indptr + (w0 - row_lo), h + dat_bytes + idx_bytes, (n + 1) * 8);
+            pool.run(pieces);
+        }
+        for (int i = 0; i < 2; i++) cudaStreamSynchronize(ws.stream[i]);
+        if (rc != QR_OK) return rc;
+        if (indptr && !(flags & QR_INDPTR_GLOBAL)) {
+            const uint64_t base = row_lo * G;
+            if (base) for (uint64_t i = 0; i <= rows; i++) indptr[i] -= base;
+        }
+        return QR_OK;
+    }
 
     int k = 0;
     for (uint64_t w0 = row_lo; w0 < row_hi; w0 += win_rows, k ^= 1) {
@@ -578,6 +750,7 @@ extern "C" int qr_release_scratch(void)
         if (cudaSetDevice(kv.first) != cudaSuccess) continue;
         for (int i = 0; i < 2; i++) {
             if (kv.second.buf[i]) cudaFree(kv.second.buf[i]);
+            if (kv.second.host[i]) cudaFreeHost(kv.second.host[i]);
             if (kv.second.stream[i]) cudaStreamDestroy(kv.second.stream[i]);
         }
     }

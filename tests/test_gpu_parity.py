@@ -191,7 +191,7 @@ def test_blocked_kernel(fixtures, monkeypatch, name, S, E):
             assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
 
 
-@pytest.mark.parametrize("W,sync", [(8, 0), (16, 1), (32, 1)])
+@pytest.mark.parametrize("W,sync", [(8, 0), (8, 2), (16, 1), (16, 2), (32, 2)])
 @pytest.mark.parametrize("R", [5, 6, 8])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
 def test_lanes_kernel(fixtures, monkeypatch, name, R, W, sync):
@@ -212,6 +212,24 @@ def test_lanes_kernel(fixtures, monkeypatch, name, R, W, sync):
             ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
             assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G])), (lo, hi)
             assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
+
+
+@pytest.mark.parametrize("W", [8, 16, 32])
+def test_lanes_kernel_clusters(monkeypatch, W):
+    """G = 1100: 5 / 3 / 2 sibling CTAs per row run, launched as one thread-block cluster that
+    re-aligns every 32 rows (odd cluster sizes included); rows in runs of 32 and 256."""
+    labels, coeffs = H.random_pauli_sum(12, 1500, 1100, 50, 5)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    for R in (5, 8):
+        monkeypatch.setenv("QR_FILL_LANES_R", str(R))
+        monkeypatch.setenv("QR_FILL_LANES_W", str(W))
+        plan = make_op(labels, coeffs).plan()
+        assert plan.n_groups == 1100
+        assert_same(device_build(plan, 0, 1 << n), ref, f"G=1100 W={W} R={R}")
+        lo, hi = 100, 4000
+        ip, ix, dt = device_build(plan, lo, hi)
+        assert np.array_equal(ix, ref[1][lo * 1100:hi * 1100]) and np.array_equal(u64(dt), u64(ref[2][lo * 1100:hi * 1100]))
 
 
 def test_lanes_kernel_is_the_large_G_default(fixtures):
@@ -238,6 +256,27 @@ def test_build_host_windows(fixtures):
         _ffi.call("qr_build_host", plan.handle, lo, hi, ip.ctypes.data, ix.ctypes.data, dt.ctypes.data, 0)
         assert np.array_equal(ip, np.arange(rows + 1, dtype=np.uint64) * G)
         assert np.array_equal(ix, full[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(full[2][lo * G:hi * G]))
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_build_host_pageable_destination(monkeypatch, threads):
+    """Ordinary (pageable) numpy arrays as the destination -- what a Rust Vec is: several 32 MB windows
+    through pinned staging and the host copy pool, against pinned destinations and the plain-cudaMemcpy
+    path (QR_HOST_NO_STAGING), on ragged and global-indptr requests."""
+    monkeypatch.setenv("QR_HOST_COPY_THREADS", threads)
+    labels, coeffs = H.xxz_chain(18, 1.0, 0.7)                      # 113 MB: four staging windows
+    n, params = O.make_params(labels, coeffs)
+    plan = make_op(labels, coeffs).plan()
+    G, dim = plan.n_groups, 1 << n
+    for lo, hi, flags in [(0, dim, 0), (77, dim - 5, _ffi.QR_INDPTR_GLOBAL), (1000, 1032, 0)]:
+        rows = hi - lo
+        ref = O.build_csr(params, n, lo, hi)
+        want_ip = ref[0] + (np.uint64(lo * G) if flags & _ffi.QR_INDPTR_GLOBAL else np.uint64(0))
+        for extra in (0, _ffi.QR_HOST_NO_STAGING):
+            ip = np.full(rows + 1, 0xFFFF, np.uint64); ix = np.full(rows * G, 0xFFFF, np.uint64)
+            dt = np.full(rows * G, np.nan, np.complex128)
+            _ffi.call("qr_build_host", plan.handle, lo, hi, ip.ctypes.data, ix.ctypes.data, dt.ctypes.data, flags | extra)
+            assert_same((ip, ix, dt), (want_ip, ref[1], ref[2]), f"pageable [{lo},{hi}) flags={flags | extra}")
 
 
 def test_abi_argument_errors(fixtures):

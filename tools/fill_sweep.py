@@ -43,12 +43,13 @@ def main():
             os.environ.pop(k)
         if cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
-        elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:sync]]]
+        elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:sync[:persist]]]]
             parts = cfg.split(":")
             os.environ["QR_FILL_LANES"] = "1"
             if len(parts) > 1: os.environ["QR_FILL_LANES_R"] = parts[1]
             if len(parts) > 2: os.environ["QR_FILL_LANES_W"] = parts[2]
             if len(parts) > 3: os.environ["QR_FILL_LANES_SYNC"] = parts[3]
+            if len(parts) > 4: os.environ["QR_FILL_LANES_PERSIST"] = parts[4]
         elif cfg.startswith("blocked"):               # blocked[:S[:E]]
             parts = cfg.split(":")
             os.environ["QR_FILL_LANES"] = "0"
