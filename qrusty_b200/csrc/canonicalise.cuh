@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
     __shared__ uint32_t max_group, n_const;
     // small operators (the usual case: tens of terms) sort entirely in shared memory
     constexpr uint32_t SMALL_T = 1024;
+    constexpr uint32_t RANK_T = 512;                 // up to here one rank-sort pass beats the radix passes
     __shared__ uint32_t s_sort[4][SMALL_T];
 
     const uint32_t tid = threadIdx.x;
@@ -110,18 +111,37 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
     if (tid == 0) { max_group = 0; n_const = 0; }
     __syncthreads();
 
-    // ---- 1. stable LSD radix sort(s) --------------------------------------------------------
+    // ---- 1. stable sort of (x, original index) -- with merge_dups: of ((x, z), original index) --------
     uint32_t *kin = p.key_a, *kout = p.key_b, *iin = p.idx_a, *iout = p.idx_b;
     if (T <= SMALL_T) { kin = s_sort[0]; kout = s_sort[1]; iin = s_sort[2]; iout = s_sort[3]; }
-    for (uint32_t i = tid; i < T; i += K1_THREADS) iin[i] = i;
-    if (merge_dups) {
-        for (uint32_t i = tid; i < T; i += K1_THREADS) kin[i] = (uint32_t)p.raw[i].z;
+    if (T <= RANK_T) {
+        // short term lists (the usual Hamiltonian: tens of terms): one rank-sort pass in shared memory.
+        // rank(i) = #{j : key_j < key_i or (key_j == key_i and j < i)} -- stable by construction; every
+        // thread scans the same j, so the shared-memory reads are broadcasts.
+        for (uint32_t i = tid; i < T; i += K1_THREADS) { kout[i] = (uint32_t)p.raw[i].x; iout[i] = merge_dups ? (uint32_t)p.raw[i].z : 0u; }
+        __syncthreads();
+        for (uint32_t i = tid; i < T; i += K1_THREADS) {
+            const uint64_t ki = ((uint64_t)kout[i] << 32) | iout[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < T; j++) {
+                const uint64_t kj = ((uint64_t)kout[j] << 32) | iout[j];
+                rank += (kj < ki || (kj == ki && j < i)) ? 1u : 0u;
+            }
+            kin[rank] = kout[i]; iin[rank] = i;
+        }
+        __syncthreads();
+    } else {
+        // stable LSD radix sort(s)
+        for (uint32_t i = tid; i < T; i += K1_THREADS) iin[i] = i;
+        if (merge_dups) {
+            for (uint32_t i = tid; i < T; i += K1_THREADS) kin[i] = (uint32_t)p.raw[i].z;
+            __syncthreads();
+            radix_sort_cta(sm, T, p.n_qubits, kin, kout, iin, iout);
+        }
+        for (uint32_t i = tid; i < T; i += K1_THREADS) kin[i] = (uint32_t)p.raw[iin[i]].x;
         __syncthreads();
         radix_sort_cta(sm, T, p.n_qubits, kin, kout, iin, iout);
     }
-    for (uint32_t i = tid; i < T; i += K1_THREADS) kin[i] = (uint32_t)p.raw[iin[i]].x;
-    __syncthreads();
-    radix_sort_cta(sm, T, p.n_qubits, kin, kout, iin, iout);
     // sorted (x, idx) now in (kin, iin)
 
     // ---- 2. head flags -> groups; gather the sorted term table ------------------------------

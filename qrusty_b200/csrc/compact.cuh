@@ -128,8 +128,7 @@ compact_rows_kernel(uint64_t n_rows, uint32_t G, const uint64_t *__restrict__ in
 //                        ones per row (no matrix traffic: 8 B written per row)
 //   scan_*               counts -> indptr (above)
 //   fill_compact_kernel  assembles a 32-row tile in shared memory in column order exactly as
-//                        fill_staged_kernel does, then each warp compacts whole rows:
-//                        ballot + popc rank, kept entries stored at indptr[row] + rank.
+//                        fill_staged_kernel does, then compacts the tile CTA-wide.
 //                        24 B written per KEPT entry.
 // ---------------------------------------------------------------------------------
 constexpr int COUNT_ROWS_WARPS = 8;
@@ -168,49 +167,77 @@ count_rows_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi, doubl
     if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
 }
 
-template <int GW>
+// The tile's kept entries, taken in tile order (row-major = output order), fill the contiguous output
+// range that starts at indptr[first row of the tile].  Each warp takes one contiguous share of the
+// tile's entries: it counts its kept entries (ballot + popc), the 8 counts are prefixed through shared
+// memory behind ONE barrier, and the warp then stores its kept entries in order -- consecutive lanes
+// write consecutive output entries.
+template <int E, int GW>
 __global__ void __launch_bounds__(32 * GW)
 fill_compact_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, uint64_t row_hi, double tol,
                     const uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices, double2 *__restrict__ data)
 {
+    constexpr uint32_t R = 32u * E;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                          // 32*G * 16 B
-    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)32u * G * 16u);  // 32*G *  8 B
+    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                         // R*G * 16 B
+    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)R * G * 16u);  // R*G *  8 B
+    __shared__ uint32_t s_wcnt[GW];
     const uint32_t lane = threadIdx.x & 31u, gw = threadIdx.x >> 5;
-    const uint64_t tile_base = tile_row0 + (uint64_t)blockIdx.x * 32u;              // multiple of 32
+    const uint64_t tile_base = tile_row0 + (uint64_t)blockIdx.x * R;               // multiple of R
     const uint32_t tbase = (uint32_t)tile_base;
-    const uint32_t r[1] = {tbase + lane};
-    for (uint32_t g = gw; g < G; g += GW) {
+    uint32_t r[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) r[e] = tbase + 32u * e + lane;
+    for (uint32_t g = gw; g < G; g += GW) {                                         // as fill_staged_kernel
         const GroupDesc d = p.gdesc[g];
         const uint32_t c = __ldg(&p.cnt[g * 32u + lane]);
         const uint32_t lo = __ldg(&p.lr5[g * 32u + ((d.x ^ lane) & 31u)]);
-        double ar[1], ai[1];
-        if (d.flag & 1u) { ar[0] = d.cre; ai[0] = d.cim; }
-        else group_values<1>(p, d.t0, d.t1, r, ar, ai);
-        const uint32_t bit = ((d.x ^ tbase) >> lane) & 1u;
-        const uint32_t slot = __reduce_add_sync(0xffffffffu, (lane >= 5u && bit) ? c : 0u) + lo;
-        const uint32_t o = lane * G + slot;
-        sidx[o] = (uint64_t)(r[0] ^ d.x);
-        sdat[o] = make_double2(ar[0], ai[0]);
+        double ar[E], ai[E];
+        if (d.flag & 1u) {
+#pragma unroll
+            for (int e = 0; e < E; e++) { ar[e] = d.cre; ai[e] = d.cim; }
+        } else {
+            group_values<E>(p, d.t0, d.t1, r, ar, ai);
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint32_t bit = ((d.x ^ (tbase + 32u * e)) >> lane) & 1u;
+            const uint32_t slot = __reduce_add_sync(0xffffffffu, (lane >= 5u && bit) ? c : 0u) + lo;
+            const uint32_t o = (32u * e + lane) * G + slot;
+            sidx[o] = (uint64_t)(r[e] ^ d.x);
+            sdat[o] = make_double2(ar[e], ai[e]);
+        }
     }
     __syncthreads();
-    for (uint32_t l = gw; l < 32u; l += GW) {
-        const uint64_t row = tile_base + l;
-        if (row < row_lo || row >= row_hi) continue;                               // ragged first / last tile
-        uint64_t out = indptr[row - row_lo];
-        for (uint32_t j0 = 0; j0 < G; j0 += 32u) {
-            const uint32_t j = j0 + lane;
-            double2 d = make_double2(0.0, 0.0);
-            if (j < G) d = sdat[l * G + j];
-            const bool keep = j < G && keep_entry(d, tol);
-            const unsigned mask = __ballot_sync(FULL_MASK, keep);
-            if (keep) {
-                const uint64_t pos = out + __popc(mask & ((1u << lane) - 1u));
-                data[pos] = d;
-                indices[pos] = sidx[l * G + j];
-            }
-            out += __popc(mask);
+    // the tile's rows inside the request (ragged first / last tile), as a range of tile entries
+    const uint64_t first = tile_base < row_lo ? row_lo : tile_base;
+    const uint64_t last = tile_base + R < row_hi ? tile_base + R : row_hi;             // exclusive
+    const uint32_t e_lo = (uint32_t)(first - tile_base) * G, e_hi = (uint32_t)(last - tile_base) * G;
+    const uint32_t per = ((e_hi - e_lo + GW - 1) / GW + 31u) & ~31u;                  // entries per warp, whole chunks
+    const uint32_t w_lo = min(e_hi, e_lo + gw * per), w_hi = min(e_hi, w_lo + per);
+    uint32_t mine = 0;
+    for (uint32_t e0 = w_lo; e0 < w_hi; e0 += 32u) {
+        const uint32_t e = e0 + lane;
+        const bool keep = e < w_hi && keep_entry(sdat[e < w_hi ? e : w_lo], tol);
+        mine += __popc(__ballot_sync(FULL_MASK, keep));
+    }
+    if (lane == 0) s_wcnt[gw] = mine;
+    __syncthreads();
+    uint64_t out = indptr[first - row_lo];
+#pragma unroll
+    for (int w = 0; w < GW; w++) out += w < (int)gw ? s_wcnt[w] : 0u;
+    for (uint32_t e0 = w_lo; e0 < w_hi; e0 += 32u) {
+        const uint32_t e = e0 + lane;
+        double2 d = make_double2(0.0, 0.0);
+        if (e < w_hi) d = sdat[e];
+        const bool keep = e < w_hi && keep_entry(d, tol);
+        const unsigned mask = __ballot_sync(FULL_MASK, keep);
+        if (keep) {
+            const uint64_t pos = out + __popc(mask & ((1u << lane) - 1u));
+            data[pos] = d;
+            indices[pos] = sidx[e];
         }
+        out += __popc(mask);
     }
 }
 

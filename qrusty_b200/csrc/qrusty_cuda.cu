@@ -1063,11 +1063,15 @@ extern "C" int qr_build_compact_fill(qr_plan *pl, uint64_t row_lo, uint64_t row_
     QR_CUDA(cudaSetDevice(pl->device));
     cudaStream_t st = as_stream(stream);
     const uint64_t G = pl->n_groups, rows = row_hi - row_lo;
-    const size_t smem = (size_t)32 * G * 24;
-    if (smem <= MAX_SMEM) {
-        const uint64_t t0 = row_lo / 32 * 32, tiles = (row_hi - t0 + 31) / 32;
+    const size_t smem32 = (size_t)32 * G * 24;
+    if (smem32 <= MAX_SMEM) {
+        // 64-row tiles (two strips per warp visit, as the staged fill) while two CTAs still fit per SM
+        const bool two = 2 * smem32 <= 113 * 1024;
+        const uint64_t R = two ? 64 : 32;
+        const size_t smem = two ? 2 * smem32 : smem32;
+        const uint64_t t0 = row_lo / R * R, tiles = (row_hi - t0 + R - 1) / R;
         if (tiles > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "qr_build_compact_fill: row window too large for one launch");
-        auto kern = qr::fill_compact_kernel<8>;
+        auto kern = two ? qr::fill_compact_kernel<2, 8> : qr::fill_compact_kernel<1, 8>;
         QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)tiles, 256, smem, st>>>(pl->dev, (uint32_t)G, t0, row_lo, row_hi, tol, d_indptr, d_indices,
                                                  reinterpret_cast<double2 *>(d_data));
