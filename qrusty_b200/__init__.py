@@ -518,13 +518,11 @@ class SpMat:
         indices = pinned_empty(nnz, np.uint64)
         indptr = pinned_empty(self._shape[0] + 1, np.uint64)
         off = 0
-        streams = []
+        streams, lazy = [], []
         for s in shards:
             rows = s.hi - s.lo
             if s.data is None:
-                call("qr_build_host", s.plan.handle, s.lo, s.hi, indptr[s.off:].ctypes.data,
-                     indices[off:].ctypes.data, data[off:].ctypes.data,
-                     _ffi.QR_INDPTR_LOCAL if s.local else _ffi.QR_INDPTR_GLOBAL)
+                lazy.append((s, off))
             else:
                 call("qr_set_device", s.device)
                 st = C.c_void_p()
@@ -534,6 +532,22 @@ class SpMat:
                 s.indices.download(indices[off:off + s.nnz], stream=st)
                 s.indptr.download(indptr[s.off:s.off + rows + 1], stream=st)
             off += s.nnz
+
+        def build_host(item):
+            s, o = item
+            call("qr_build_host", s.plan.handle, s.lo, s.hi, indptr[s.off:].ctypes.data,
+                 indices[o:].ctypes.data, data[o:].ctypes.data,
+                 _ffi.QR_INDPTR_LOCAL if s.local else _ffi.QR_INDPTR_GLOBAL)
+        if len(lazy) > 1:
+            # one host thread per GPU: every shard streams over its own PCIe link at the same time
+            # (ctypes drops the GIL for the duration of the call).  Shards overlap by one indptr entry
+            # (a shard's last = the next one's first, the same value), so concurrent writes agree.
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(len(lazy)) as pool:
+                list(pool.map(build_host, lazy))
+        else:
+            for item in lazy:
+                build_host(item)
         for dev, st in streams:
             call("qr_set_device", dev)
             call("qr_stream_synchronize", st)

@@ -59,8 +59,9 @@ constexpr size_t MAX_SMEM = 227 * 1024;
 struct WinScratch {
     void *buf[2] = {nullptr, nullptr}; size_t bytes = 0; cudaStream_t stream[2] = {nullptr, nullptr};
     void *host[2] = {nullptr, nullptr}; size_t host_bytes = 0;     // pinned staging for pageable destinations
+    std::mutex busy;                                               // one qr_build_host at a time per device
 };
-std::mutex g_win_mutex;
+std::mutex g_win_mutex;                                            // guards the map, not the transfers
 std::map<int, WinScratch> g_win;
 
 }  // namespace
@@ -576,8 +577,10 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
     // the staging windows and their streams belong to the device, not to the plan: a caller that
     // builds one matrix per plan (the reference's to_matrix call pattern) does not pay two
     // cudaMalloc/cudaFree of 256 MB per call
-    std::lock_guard<std::mutex> lock(g_win_mutex);
-    WinScratch &ws = g_win[pl->device];
+    WinScratch *wsp = nullptr;
+    { std::lock_guard<std::mutex> lock(g_win_mutex); wsp = &g_win[pl->device]; }   // std::map nodes never move
+    WinScratch &ws = *wsp;
+    std::lock_guard<std::mutex> busy(ws.busy);                      // shards on different GPUs copy concurrently
     if (ws.bytes < need) {
         for (int i = 0; i < 2; i++) { if (ws.buf[i]) cudaFree(ws.buf[i]); ws.buf[i] = nullptr; }
         ws.bytes = 0;
@@ -992,8 +995,19 @@ extern "C" int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const u
 static int scan_counts(uint64_t n_rows, uint64_t *d_indptr, uint64_t *nnz_out, cudaStream_t st, const char *who)
 {
     const uint64_t n_tiles = (n_rows + qr::SCAN_TILE - 1) / qr::SCAN_TILE;
-    uint64_t *d_tiles = nullptr;
-    QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_tiles), (n_tiles + 1) * 8));
+    // tile sums: a small scratch kept per host thread and device (cudaFree would serialise the device)
+    static thread_local uint64_t *d_tiles = nullptr;
+    static thread_local uint64_t tiles_cap = 0;
+    static thread_local int tiles_dev = -1;
+    int dev = 0;
+    QR_CUDA(cudaGetDevice(&dev));
+    if (!d_tiles || tiles_dev != dev || tiles_cap < n_tiles + 1) {
+        if (d_tiles && tiles_dev == dev) cudaFree(d_tiles);
+        d_tiles = nullptr;
+        tiles_cap = std::max<uint64_t>(n_tiles + 1, 4096);
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_tiles), tiles_cap * 8));
+        tiles_dev = dev;
+    }
     qr::scan_tile_sums_kernel<<<(unsigned)n_tiles, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr, d_tiles);
     g_launches.fetch_add(1);
     qr::scan_tile_offsets_kernel<<<1, qr::K2_THREADS, 0, st>>>(n_tiles, d_tiles, d_tiles + n_tiles);
@@ -1003,7 +1017,6 @@ static int scan_counts(uint64_t n_rows, uint64_t *d_indptr, uint64_t *nnz_out, c
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(nnz_out, d_tiles + n_tiles, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_tiles);
     if (e != cudaSuccess) return fail(QR_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
     return QR_OK;
 }
