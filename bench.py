@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-hv", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time K eager step launches instead of one CUDA graph of K steps")
     return ap.parse_args()
 
 
@@ -271,17 +272,37 @@ def run_b200(args, rank, local_rank, world):
     for _ in range(W):
         step()
     call("qr_stream_synchronize", stream)
+    # The K timed steps are recorded once into a CUDA graph and replayed with one launch: with 8 ranks
+    # sharing one host the Python launch rate (4 ctypes calls per 95 us step) is otherwise what gets timed.
+    fill_ev = [(ev(), ev()) for _ in range(K)]                  # around every fill launch of the timed steps
+    graph, launches0 = None, _ffi.kernel_launches()
+    if not args.no_graph:
+        try:
+            call("qr_graph_begin_capture", stream)
+            for i in range(K):
+                step(*fill_ev[i])
+            g = C.c_void_p()
+            call("qr_graph_end_capture", stream, C.byref(g))
+            graph = g
+            call("qr_graph_launch", graph, stream)               # untimed: uploads the graph
+            call("qr_stream_synchronize", stream)
+        except _ffi.QrustyCudaError as exc:                       # capture unsupported: eager launches
+            sys.stderr.write("bench.py: CUDA graph capture failed (%s); timing eager launches\n" % exc)
+            graph = None
+    launches_per_k = _ffi.kernel_launches() - launches0
     e0, e1 = ev(), ev()
-    fill_ev = [(ev(), ev()) for _ in range(K)]
     barrier()
     sampler.start()
     launches0 = _ffi.kernel_launches()
     call("qr_event_record", e0, stream)
-    for i in range(K):
-        step(*fill_ev[i])
+    if graph is not None:
+        call("qr_graph_launch", graph, stream)                   # exactly K steps
+    else:
+        for i in range(K):
+            step(*fill_ev[i])
     call("qr_event_record", e1, stream)
     call("qr_stream_synchronize", stream)
-    launches = _ffi.kernel_launches() - launches0
+    launches = launches_per_k if graph is not None else _ffi.kernel_launches() - launches0
     barrier()
     t_ms = max_over_ranks(elapsed(e0, e1))
     fill_ms = float(np.mean([elapsed(a, b) for a, b in fill_ev]))
@@ -443,6 +464,7 @@ def run_b200(args, rank, local_rank, world):
             "config": {"workload": name, "n_qubits": n, "n_terms": len(labels), "n_groups": G, "nnz": nnz_total,
                        "rows_per_gpu": rows, "bytes_per_gpu": bytes_local, "parallelism": "row-block x%d, no collective" % world,
                        "step": "canonicalise kernel + fill kernel(s), outputs device-resident",
+                       "launch": ("one CUDA graph holding the K steps" if graph is not None else "K eager step launches"),
                        "l2": "each step writes %.0f MB per GPU (> 126 MB L2), no flush needed" % (bytes_local / 1e6)},
             "roofline": {"bound": "hbm", "kernel": "fill_staged_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic_from_profile(name), "peak_source": peak_src,

@@ -228,6 +228,12 @@ QR_API int qr_memset_device(void *dst, int value, size_t bytes, void *stream);
 QR_API int qr_stream_create(void **stream);
 QR_API int qr_stream_destroy(void *stream);
 QR_API int qr_stream_synchronize(void *stream);          /* NULL = whole device */
+/* CUDA graphs: record the asynchronous calls issued on `stream` between begin and end (every *_device /
+ * *_async entry point of this header is capturable), replay them with one launch. */
+QR_API int qr_graph_begin_capture(void *stream);
+QR_API int qr_graph_end_capture(void *stream, void **graph_exec);
+QR_API int qr_graph_launch(void *graph_exec, void *stream);
+QR_API int qr_graph_destroy(void *graph_exec);
 QR_API int qr_event_create(void **event);
 QR_API int qr_event_destroy(void *event);
 QR_API int qr_event_record(void *event, void *stream);

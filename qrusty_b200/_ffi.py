@@ -94,6 +94,10 @@ SIGNATURES = {
     "qr_stream_create": [C.POINTER(_vp)],
     "qr_stream_destroy": [_vp],
     "qr_stream_synchronize": [_vp],
+    "qr_graph_begin_capture": [_vp],
+    "qr_graph_end_capture": [_vp, C.POINTER(_vp)],
+    "qr_graph_launch": [_vp, _vp],
+    "qr_graph_destroy": [_vp],
     "qr_event_create": [C.POINTER(_vp)],
     "qr_event_destroy": [_vp],
     "qr_event_record": [_vp, _vp],

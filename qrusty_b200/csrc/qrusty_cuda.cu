@@ -1461,6 +1461,39 @@ extern "C" int qr_stream_synchronize(void *stream)
     else QR_CUDA(cudaDeviceSynchronize());
     return QR_OK;
 }
+// ---- CUDA graphs: a caller that repeats the same device sequence (canonicalise -> fill, an H.v
+// iteration) records it once and replays it with one launch, so the host's launch rate stops mattering.
+extern "C" int qr_graph_begin_capture(void *stream)
+{
+    if (!stream) return fail(QR_ERR_INVALID, "qr_graph_begin_capture: capture needs an explicit stream");
+    QR_CUDA(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal));
+    return QR_OK;
+}
+extern "C" int qr_graph_end_capture(void *stream, void **graph_exec)
+{
+    if (!stream || !graph_exec) return fail(QR_ERR_INVALID, "qr_graph_end_capture: NULL argument");
+    *graph_exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    QR_CUDA(cudaStreamEndCapture(as_stream(stream), &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(QR_ERR_CUDA, std::string("qr_graph_end_capture: ") + cudaGetErrorString(e));
+    *graph_exec = exec;
+    return QR_OK;
+}
+extern "C" int qr_graph_launch(void *graph_exec, void *stream)
+{
+    if (!graph_exec) return fail(QR_ERR_INVALID, "qr_graph_launch: NULL graph");
+    QR_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)));
+    return QR_OK;
+}
+extern "C" int qr_graph_destroy(void *graph_exec)
+{
+    if (graph_exec) QR_CUDA(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec)));
+    return QR_OK;
+}
+
 extern "C" int qr_event_create(void **event)
 {
     if (!event) return fail(QR_ERR_INVALID, "qr_event_create: NULL argument");
@@ -1472,6 +1505,12 @@ extern "C" int qr_event_create(void **event)
 extern "C" int qr_event_destroy(void *event) { if (event) QR_CUDA(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event))); return QR_OK; }
 extern "C" int qr_event_record(void *event, void *stream)
 {
+    // inside a stream capture the record becomes a graph node of its own (timestamps usable after replay)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (stream && cudaStreamIsCapturing(as_stream(stream), &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) {
+        QR_CUDA(cudaEventRecordWithFlags(reinterpret_cast<cudaEvent_t>(event), as_stream(stream), cudaEventRecordExternal));
+        return QR_OK;
+    }
     QR_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), as_stream(stream)));
     return QR_OK;
 }
