@@ -9,8 +9,8 @@ buffers, and the CPU port of the reference algorithm timed beside it.
 A "step" is one pass of the hot path over one operator already resident in HBM: the
 canonicalisation kernel (K1) followed by the fill kernel(s) (K3, which also writes indptr),
 writing a device-resident CSR shard.  N=1: BASELINE config 2 (XXZ periodic chain n=20).
-N>1: the same chain with n = 20 + log2(N) qubits, row-block sharded, 2^20 rows per GPU
-(weak scaling; the build needs no collective).  torch is used only for the rendezvous,
+N>1: the same operator with log2(N) spectator qubits (H (x) I), row-block sharded, 2^20 rows of 21
+entries per GPU at every N (weak scaling; the build needs no collective).  torch is used only for the rendezvous,
 the barrier and the max-over-ranks reduction.
 """
 import argparse
@@ -47,18 +47,24 @@ def parse_args():
 
 
 def workload(args, world):
-    """-> (name, labels, coeffs).  See module docstring."""
+    """-> (name, labels, coeffs).  N=1: BASELINE config 2.  N>1 (weak scaling): the same operator with
+    log2(N) spectator qubits on top, H (x) I -- 2^20 rows of 21 entries per GPU at every N, so the
+    per-GPU work is exactly that of the N=1 line."""
     from qrusty_b200 import hamiltonians as H
     cfg = args.config
-    if cfg == "auto":
-        cfg = "xxz%d" % (20 + int(math.log2(world)))
-    if cfg == "C2":
+    spect = int(math.log2(world)) if cfg == "auto" else 0
+    if cfg in ("auto", "C2"):
         cfg = "xxz20"
     if cfg == "C4":
         return "tfim_5x5_n25", *H.tfim_lattice(5, 5, 1.0, 3.0)
     if cfg.startswith("xxz"):
         n = int(cfg[3:])
-        return "xxz_periodic_n%d_J1_delta0.7" % n, *H.xxz_chain(n, 1.0, 0.7)
+        labels, coeffs = H.xxz_chain(n, 1.0, 0.7)
+        name = "xxz_periodic_n%d_J1_delta0.7" % n
+        if spect:
+            labels = ["I" * spect + l for l in labels]
+            name += " (x) I^%d (%d spectator qubits on top: %d qubits, rows sharded over %d GPUs)" % (spect, spect, n + spect, world)
+        return name, labels, coeffs
     raise SystemExit("unknown --config " + cfg)
 
 

@@ -241,6 +241,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
         p.gconst[g] = make_double2(re, im);
         GroupDesc d; d.x = p.gx[g]; d.flag = p.gflag[g]; d.t0 = t0; d.t1 = t1; d.cre = re; d.cim = im;
         p.gdesc[g] = d;
+        p.lt_xn[g] = make_uint2(d.x, t1 - t0);
+        for (uint32_t t = 0; t < (uint32_t)LANE_TERMS; t++) {
+            const bool has = t0 + t < t1;
+            p.lt_z[t * T + g] = has ? p.tz[t0 + t] : 0u;
+            p.lt_c[t * T + g] = has ? p.tc[t0 + t] : make_double2(-0.0, -0.0);
+        }
     }
     __syncthreads();
     for (uint32_t q = tid; q < G * 32u; q += K1_THREADS) {

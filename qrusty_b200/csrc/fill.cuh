@@ -143,25 +143,38 @@ __device__ __forceinline__ void bulk_store_smem_to_global(void *gdst, const void
                  :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
 
-template <int E, int GW>
+// PAD: the 32 lanes of a store hold one row each, G*16 bytes apart.  When G is a multiple of 8 they all
+// fall on the same shared-memory banks (8-way conflicts: 1.9x slower on XXZ n=23, l1tex 93 % busy with
+// 30 M conflict cycles).  The padded layout inserts one 16-byte gap after every 2^ps rows, which spreads
+// the rows over the banks, and the tile becomes R >> ps contiguous pieces per array instead of one; the
+// lanes of warp 0 hand them to the TMA.  Measured (profiles/r02_pad_probe.jsonl): ps = 2 is the best
+// period for G = 24 (4.65 vs 3.51 TB/s unpadded; one piece per row is bound by the TMA's request rate);
+// for every other G the single copy of the unpadded tile wins, 4-way-conflict cases (G = 20, 28) included.
+template <int E, int GW, bool PAD>
 __global__ void __launch_bounds__(32 * GW)
 fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
                    uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
-                   double2 *__restrict__ data, uint64_t indptr_last_row)
+                   double2 *__restrict__ data, uint64_t indptr_last_row, uint32_t ps)
 {
     // tile = E strips of 32 rows; each of the GW warps visits its share of the groups and handles
     // all E strips per visit: descriptor, rank-table row and every term are read once per 32*E entries
     constexpr uint32_t R = 32u * E;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                         // R*G * 16 B
-    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)R * G * 16u);  // R*G *  8 B
+    const uint32_t gaps = PAD ? (R >> ps) : 0u;
+    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                                         // (R*G + gaps) * 16 B
+    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + ((size_t)R * G + gaps) * 16u);         // (R*G + 2*gaps) * 8 B
 
     const uint32_t lane = threadIdx.x & 31u, gw = threadIdx.x >> 5;
     const uint64_t tile_base = tile_row0 + (uint64_t)blockIdx.x * R;
     const uint32_t tbase = (uint32_t)tile_base;
-    uint32_t r[E];
+    uint32_t r[E], od[E], oi[E];                                  // row, and where the row starts in sdat / sidx
 #pragma unroll
-    for (int e = 0; e < E; e++) r[e] = tbase + 32u * e + lane;
+    for (int e = 0; e < E; e++) {
+        const uint32_t row = 32u * e + lane;
+        r[e] = tbase + row;
+        od[e] = row * G + (PAD ? (row >> ps) : 0u);
+        oi[e] = row * G + (PAD ? ((row >> ps) << 1) : 0u);
+    }
 
     for (uint32_t g = gw; g < G; g += GW) {
         const GroupDesc d = p.gdesc[g];                                          // warp-uniform, 2 x 16 B
@@ -178,9 +191,8 @@ fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, u
         for (int e = 0; e < E; e++) {
             const uint32_t bit = ((d.x ^ (tbase + 32u * e)) >> lane) & 1u;
             const uint32_t slot = __reduce_add_sync(0xffffffffu, (lane >= 5u && bit) ? c : 0u) + lo;
-            const uint32_t o = (32u * e + lane) * G + slot;
-            sidx[o] = (uint64_t)(r[e] ^ d.x);
-            sdat[o] = make_double2(ar[e], ai[e]);
+            sidx[oi[e] + slot] = (uint64_t)(r[e] ^ d.x);
+            sdat[od[e] + slot] = make_double2(ar[e], ai[e]);
         }
     }
     if (gw == 0 && indptr != nullptr) {
@@ -191,11 +203,21 @@ fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, u
             if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
         }
     }
-    // generic-proxy writes -> visible to the async proxy, then one thread issues the copies
+    // generic-proxy writes -> visible to the async proxy, then the copies are issued
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint64_t off = (tile_base - row_lo) * G;
+    const uint64_t off = (tile_base - row_lo) * G;
+    if (PAD) {
+        if (gw == 0) {
+            const uint32_t piece = G << ps;                                       // entries per contiguous piece
+            for (uint32_t c = lane; c < gaps; c += 32u) {
+                bulk_store_smem_to_global(data + off + (uint64_t)c * piece, sdat + c * (piece + 1u), piece * 16u);
+                bulk_store_smem_to_global(indices + off + (uint64_t)c * piece, sidx + c * (piece + 2u), piece * 8u);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else if (threadIdx.x == 0) {
         bulk_store_smem_to_global(data + off, sdat, R * G * 16u);
         bulk_store_smem_to_global(indices + off, sidx, R * G * 8u);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -369,7 +391,7 @@ __device__ __forceinline__ void st_global_u64(uintptr_t addr, uint64_t v)
     asm volatile("st.global.u64 [%0], %1;" :: "l"(addr), "l"(v) : "memory");
 }
 
-constexpr int FILL_LANES_NT = 6;
+constexpr int FILL_LANES_NT = LANE_TERMS;
 constexpr int FILL_LANES_MAXLOG2R = 12;
 
 // CTA-wide barrier that does not care which code path a warp arrives from (the warps of a CTA run
@@ -534,26 +556,24 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
     // ---- once per CTA: warp <-> block of 32 groups, lane <-> group -----------------------------------
     const uint32_t g = (beta * LW + warp) * 32u + lane;
     const bool warp_live = (beta * LW + warp) * 32u < G;          // warp-uniform
-    uint32_t x = 0, nt = 0, t0 = 0;
-    if (g < G) { const GroupDesc d = p.gdesc[g]; x = d.x; nt = d.t1 - d.t0; t0 = d.t0; }
-    const bool active = g < G && nt <= (uint32_t)NT;
-    if (g < G && !active) s_heavy[atomicAdd(&s_nheavy, 1u)] = g;
-    if (!active) nt = 0;
-    // terms beyond the lane's own are padded with (z = 0, c' = -0.0): x + (-0.0) == x for every x,
-    // signed zeros included, so padding never needs a predicate
+    // one round of coalesced, mutually independent loads: (mask, term count), the first NT terms (padded
+    // with (z = 0, c' = -0.0): x + (-0.0) == x for every x, signed zeros included, so padding never needs a
+    // predicate), and -- below -- the rank-table column
+    const uint32_t T = p.n_terms, gg = g < G ? g : G - 1u;
+    const uint2 xn = __ldg(&p.lt_xn[gg]);
     uint32_t z[NT];
     double cr[NT], ci[NT];
 #pragma unroll
-    for (int t = 0; t < NT; t++) {
-        z[t] = 0u; cr[t] = -0.0; ci[t] = -0.0;
-        if ((uint32_t)t < nt) { z[t] = __ldg(&p.tz[t0 + t]); const double2 c = __ldg(&p.tc[t0 + t]); cr[t] = c.x; ci[t] = c.y; }
-    }
+    for (int t = 0; t < NT; t++) { z[t] = __ldg(&p.lt_z[t * T + gg]); const double2 c = __ldg(&p.lt_c[t * T + gg]); cr[t] = c.x; ci[t] = c.y; }
+    const uint32_t x = xn.x;
+    uint32_t nt = xn.y;
+    const bool active = g < G && nt <= (uint32_t)NT;
+    if (g < G && !active) s_heavy[atomicAdd(&s_nheavy, 1u)] = g;
+    if (!active) nt = 0;
     const uint32_t nt_max = __reduce_max_sync(0xffffffffu, nt);
     uint32_t *s_cnt = s_cnt_all + (size_t)warp * nq * 32u + lane;   // this lane's column: s_cnt[b * 32]
-    if (warp_live) {
-        const uint32_t T = p.n_terms, gg = g < G ? g : G - 1u;
+    if (warp_live)
         for (uint32_t b = 0; b < nq; b++) s_cnt[b * 32u] = __ldg(&p.cnt_t[b * T + gg]);        // coalesced
-    }
     __syncthreads();                                               // s_heavy complete
 
     LanesCtx c;

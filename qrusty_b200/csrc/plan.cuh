@@ -18,6 +18,9 @@ namespace qr {
 //   goff  u32[G+1]        group g owns sorted terms [goff[g], goff[g+1])
 //   cnt   u32[G][32]      cnt[g][b] = #{h != g : msb(gx[g]^gx[h]) == b}
 //   cnt_t u32[32][T]      cnt transposed (cnt_t[b*T + g]): lane <-> group kernels read it coalesced
+//   lt_xn, lt_z, lt_c     the lanes kernel's view of the groups, structure-of-arrays with stride T: mask
+//                         and term count, then the first LANE_TERMS (z, c') of every group padded with
+//                         (0, -0.0) -- everything a lane needs, readable coalesced in one round of loads
 //   lr5   u32[G][32]      lr5[g][j] = sum_{b<5} cnt[g][b] * bit_b(j)
 //   gflag u32[G]          bit0: every term of the group has z == 0 (value is row-independent)
 //                         bit1: every c' of the group is real (im == +-0)
@@ -57,6 +60,11 @@ struct PlanDev {
     uint32_t *blk_start;
     uint32_t *blk_p;
     uint32_t *cnt_t;
+    uint2    *lt_xn;     // lanes kernel: per group (mask, term count)
+    uint32_t *lt_z;      // lanes kernel: z of the group's first LANE_TERMS terms, [t][T], padded with 0
+    double2  *lt_c;      // lanes kernel: c' of those terms, [t][T], padded with -0.0
 };
+
+constexpr int LANE_TERMS = 6;   // terms a lane of the lanes kernel keeps in registers
 
 }  // namespace qr

@@ -112,9 +112,9 @@ namespace {
 // staged fill: template dispatch
 // ---------------------------------------------------------------------------------
 using StagedFn = void (*)(qr::PlanDev, uint32_t, uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *,
-                          double2 *, uint64_t);
-struct StagedCfg { int rw, gw; StagedFn fn; };             // rw = E (row strips per warp visit), gw = warps
-#define QR_STAGED(E, GW) {E, GW, qr::fill_staged_kernel<E, GW>}
+                          double2 *, uint64_t, uint32_t);
+struct StagedCfg { int rw, gw; StagedFn fn, fn_pad; };      // rw = E (row strips per warp visit), gw = warps
+#define QR_STAGED(E, GW) {E, GW, qr::fill_staged_kernel<E, GW, false>, qr::fill_staged_kernel<E, GW, true>}
 const StagedCfg kStaged[] = {
     QR_STAGED(1, 4), QR_STAGED(1, 8), QR_STAGED(1, 16), QR_STAGED(2, 4), QR_STAGED(2, 8), QR_STAGED(2, 16),
     QR_STAGED(4, 4), QR_STAGED(4, 8), QR_STAGED(4, 16),
@@ -242,6 +242,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     const size_t o_bs = carve((T + 1) * 4), o_bp = carve(T * 4);
     const size_t o_gf = carve(T * 4), o_gc = carve(T * 16), o_gd = carve(T * sizeof(qr::GroupDesc));
     const size_t o_ct = carve(T * 128);
+    const size_t o_lx = carve(T * 8), o_lz = carve(T * 4 * qr::LANE_TERMS), o_lc = carve(T * 16 * qr::LANE_TERMS);
     cudaError_t e = cudaMalloc(&pl->slab, off);
     if (e != cudaSuccess) { delete pl; return fail(QR_ERR_OOM, std::string("qr_plan_create: cudaMalloc: ") + cudaGetErrorString(e)); }
     char *b = static_cast<char *>(pl->slab);
@@ -259,6 +260,8 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     d.gflag = reinterpret_cast<uint32_t *>(b + o_gf); d.gconst = reinterpret_cast<double2 *>(b + o_gc);
     d.gdesc = reinterpret_cast<qr::GroupDesc *>(b + o_gd);
     d.cnt_t = reinterpret_cast<uint32_t *>(b + o_ct);
+    d.lt_xn = reinterpret_cast<uint2 *>(b + o_lx); d.lt_z = reinterpret_cast<uint32_t *>(b + o_lz);
+    d.lt_c = reinterpret_cast<double2 *>(b + o_lc);
 
     auto bail = [&](int code) { cudaFree(pl->slab); delete pl; return code; };
     e = cudaMemcpy(b + o_raw, terms, T * sizeof(qr_term), cudaMemcpyHostToDevice);
@@ -446,16 +449,30 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         // the bulk copies need 16-byte aligned global addresses: indices + (s0-row_lo)*G*8
         const bool aligned = (((s0 - row_lo) * G) & 1) == 0;
         if (s1 > s0 && aligned) {
-            const size_t smem = (size_t)(R * G * 24);
+            // G a multiple of 8: the lanes of a store (one row each, G*16 B apart) all hit the same banks
+            // (8-way conflicts, 3.5 TB/s on XXZ n=23).  A 16-byte gap after every 4 rows leaves 2-way
+            // conflicts at the price of R/4 copies per array instead of one: 4.65 TB/s.  For G = 4 mod 8
+            // (4-way conflicts, 4.7-5.0 TB/s) every gap period measured slower than none, as it is for
+            // every other G (profiles/r02_pad_probe.jsonl).
+            uint32_t ps = 2u;
+            bool pad = G % 8 == 0;
+            if (const char *env = getenv("QR_FILL_PAD")) {             // "0": never; "1".."5": force this gap period
+                const int v = atoi(env);
+                pad = v >= 1 && v <= 5;
+                if (pad) ps = (uint32_t)v;
+            }
+            size_t smem = (size_t)(R * G * 24);
+            if (pad) smem += (size_t)(R >> ps) * 32;
+            if (smem > MAX_SMEM) { pad = false; smem = (size_t)(R * G * 24); }
             const uint64_t tiles = (s1 - s0) / R;
             if (tiles > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_staged: row window too large for one launch");
-            StagedFn fn = cfg->fn;
+            StagedFn fn = pad ? cfg->fn_pad : cfg->fn;
             QR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // prefix / suffix rows that do not fill a tile
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
             fn<<<(unsigned)tiles, 32 * cfg->gw, smem, st>>>(
-                pl->dev, (uint32_t)G, s0, row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo);
+                pl->dev, (uint32_t)G, s0, row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo, ps);
             QR_LAUNCH_CHECK("fill_staged_kernel");
             lo = s1; hi = row_hi;
         }

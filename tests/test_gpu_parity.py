@@ -170,6 +170,26 @@ def test_direct_equals_staged(fixtures):
     assert_same(a, b, "staged vs direct")
 
 
+@pytest.mark.parametrize("name,force", [("xxz11", False), ("xxz15", False), ("xxz7", False), ("tfim_3x3", True), ("H2", False)])
+def test_staged_padded_tiles(fixtures, monkeypatch, name, force):
+    """fill_staged_kernel<.,.,PAD>: G a multiple of 4 (xxz n=11/15/7: G = 12/16/8, H2: 4) takes the padded
+    shared-memory pitch and one TMA copy per row automatically; QR_FILL_PAD=1 forces it for any even G."""
+    if force:
+        monkeypatch.setenv("QR_FILL_PAD", "1")
+    labels, coeffs = H.xxz_chain(int(name[3:]), 1.0, 0.7) if name.startswith("xxz") else SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    G, dim = plan.n_groups, 1 << n
+    assert G % 2 == 0
+    assert_same(device_build(plan, 0, dim), ref, name)
+    if dim >= 256:
+        for lo, hi in [(5, dim - 3), (64, 192), (dim // 2 - 1, dim // 2 + 130)]:
+            ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
+            assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G])), (lo, hi)
+            assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
+
+
 @pytest.mark.parametrize("E", [1, 2])
 @pytest.mark.parametrize("S", [32, 48, 64, 128])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2"])

@@ -39,8 +39,9 @@ def main():
     bufs = None
     for cfg in a.cfgs.split():
         flags = 0
-        for k in [k for k in os.environ if k.startswith("QR_FILL_")]:
-            os.environ.pop(k)
+        for k in ("QR_FILL_CFG", "QR_FILL_LANES", "QR_FILL_LANES_R", "QR_FILL_LANES_W", "QR_FILL_LANES_SYNC",
+                  "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E"):      # the ones a cfg string sets
+            os.environ.pop(k, None)
         if cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
         elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:sync[:persist]]]]
