@@ -700,6 +700,43 @@ def test_multi_gpu_single_process(fixtures):
     assert_same((indptr, indices, data), ref, "Cuda/2")
 
 
+def test_graph_capture_replay(fixtures):
+    """qr_graph_*: the canonicalise -> fill sequence recorded once, replayed into zeroed buffers; event
+    records inside the capture become graph nodes whose timestamps are readable after the replay."""
+    labels, coeffs = fixtures["H4"]
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    G, dim = plan.n_groups, 1 << n
+    ip, ix, dt = DeviceBuffer((dim + 1) * 8), DeviceBuffer(dim * G * 8), DeviceBuffer(dim * G * 16)
+    st, g = C.c_void_p(), C.c_void_p()
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    _ffi.call("qr_stream_create", C.byref(st))
+    _ffi.call("qr_event_create", C.byref(e0)); _ffi.call("qr_event_create", C.byref(e1))
+    _ffi.call("qr_graph_begin_capture", st)
+    _ffi.call("qr_plan_canonicalise_async", plan.handle, st)
+    _ffi.call("qr_event_record", e0, st)
+    _ffi.call("qr_build_rows_device", plan.handle, 0, dim, ip.ptr, ix.ptr, dt.ptr, 0, st)
+    _ffi.call("qr_event_record", e1, st)
+    _ffi.call("qr_graph_end_capture", st, C.byref(g))
+    for b in (ip, ix, dt):
+        _ffi.call("qr_memset_device", b.ptr, 0xFF, b.nbytes, st)       # nothing ran during the capture
+    _ffi.call("qr_stream_synchronize", st)
+    assert ix.download(np.empty(4, np.uint64))[0] == 0xFFFFFFFFFFFFFFFF
+    for _ in range(2):
+        _ffi.call("qr_graph_launch", g, st)
+    _ffi.call("qr_stream_synchronize", st)
+    got = (ip.download(np.empty(dim + 1, np.uint64)), ix.download(np.empty(dim * G, np.uint64)),
+           dt.download(np.empty(dim * G, np.complex128)))
+    assert_same(got, ref, "graph replay")
+    ms = C.c_float()
+    _ffi.call("qr_event_elapsed_ms", e0, e1, C.byref(ms))
+    assert 0.0 < ms.value < 50.0
+    _ffi.call("qr_graph_destroy", g)
+    with pytest.raises(_ffi.QrustyCudaError):
+        _ffi.call("qr_graph_begin_capture", None)
+
+
 def test_kernels_were_launched():
     before = _ffi.kernel_launches()
     make_op(*H.tfim_chain(8)).to_matrix().export()
