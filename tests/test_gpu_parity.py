@@ -700,6 +700,28 @@ def test_multi_gpu_single_process(fixtures):
     assert_same((indptr, indices, data), ref, "Cuda/2")
 
 
+@pytest.mark.parametrize("n,n_masks", [(32, 20), (32, 300), (31, 24), (30, 1100)])
+def test_row_windows_at_the_top_of_32_bit_row_space(n, n_masks):
+    """n = 30..32 qubits: windows that end at row 2^n, straddle 2^31, or sit in the middle -- row ids and
+    column ids use every bit of a u32, offsets are 64-bit.  Staged (G = 20, 24), lanes (G = 300, 1100)."""
+    labels, coeffs = H.random_pauli_sum(n, n_masks + n_masks // 2, n_masks, 5, 1000 + n_masks)
+    nq, params = O.make_params(labels, coeffs)
+    plan = make_op(labels, coeffs).plan()
+    G, dim = plan.n_groups, 1 << n
+    assert G == n_masks
+    for lo, hi in [(dim - 4096, dim), (dim // 2 - 100, dim // 2 + 229), (dim - 33, dim), (3 * (dim // 4) + 5, 3 * (dim // 4) + 2053)]:
+        ref = O.build_csr(params, nq, lo, hi)
+        ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
+        assert np.array_equal(ix, ref[1]) and np.array_equal(u64(dt), u64(ref[2])), (lo, hi)
+        assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * np.uint64(G))
+    # the fused drop-zeros build on the last rows
+    lo, hi = dim - 2048, dim
+    ref = O.build_csr(params, nq, lo, hi)
+    want = O.eliminate_zeros(ref[0] - ref[0][0], ref[1], ref[2], tolerance=0.3)
+    shape, data, indices, indptr = make_op(labels, coeffs).to_matrix_rows(lo, hi).eliminate_zeros(0.3).export()
+    assert_same((indptr, indices, data), want, "drop-zeros at the top rows")
+
+
 def test_graph_capture_replay(fixtures):
     """qr_graph_*: the canonicalise -> fill sequence recorded once, replayed into zeroed buffers; event
     records inside the capture become graph nodes whose timestamps are readable after the replay."""

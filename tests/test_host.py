@@ -144,3 +144,33 @@ def test_generators_roundtrip_masks():
         assert (p.x_indices(), p.z_indices(), p.num_qubits()) == (x, z, n)
     v = H.lanczos_start_vector(0, 64)
     assert np.array_equal(v[10:20], H.lanczos_start_vector(10, 20)) and np.all(np.abs(v.real) <= 1) and len(set(v)) == 64
+
+
+# ---- bench.py contract pieces that need no GPU ---------------------------------------------------
+def test_bench_reference_arm_and_workloads():
+    """`bench.py --impl reference` (the CPU port of accel.rs:267-336 on the host threads) prints one JSON
+    line with the contract's keys; the weak-scaling family keeps T = 60 and G = 21 at every N."""
+    import json
+    import subprocess
+    import sys
+    import types
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--config", "xxz12"], capture_output=True, text=True, timeout=300, cwd=str(root))
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "csr_build_nnz_per_s" and line["unit"] == "nnz/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["nnz"] == 13 * 4096 and line["value"] > 0
+
+    sys.path.insert(0, str(root))
+    import bench
+    import numpy as np
+    from oracle import oracle as O
+    for world in (1, 2, 4, 8):
+        name, labels, coeffs = bench.workload(types.SimpleNamespace(config="auto"), world)
+        n, params = O.make_params(labels, coeffs)
+        assert n == 20 + int(np.log2(world)) and len(labels) == 60 and len(np.unique(params["x"])) == 21
+        assert int(params["x"].max()) < 1 << 20 and int(params["z"].max()) < 1 << 20       # spectators untouched
