@@ -11,7 +11,8 @@ csrc/ through the C ABI of include/qrusty_cuda.h; there is no CPU implementation
 here, so the reference's CPU-strategy mode strings ("", "Rowwise", "RowwiseUnsafeChunked/n",
 ...) are accepted and executed by the same CUDA build -- they all denote the same matrix.
 
-Out of scope: SpMat +/-/scale, a_spmat_p_b_spmat, the CPU build strategies.
+Out of scope: SpMat +/-, a_spmat_p_b_spmat, the CPU build strategies (their entry
+points exist and run the CUDA build).
 """
 import ctypes as C
 import re
@@ -242,6 +243,24 @@ class SparsePauliOp:
             shards.append(_Shard.build(plan, lo, hi))
         return SpMat._from_shards((dim, dim), shards)
 
+    # the reference's per-strategy entry points (pyqrusty/src/lib.rs:386-404): one matrix, one CUDA build
+    def to_matrix_binary(self):
+        return self.to_matrix_mode("Cuda")
+
+    def to_matrix_accel(self):
+        return self.to_matrix_mode("Cuda")
+
+    def to_matrix_reduce(self):
+        return self.to_matrix_mode("Cuda")
+
+    def to_matrix_rayon(self):
+        return self.to_matrix_mode("Cuda")
+
+    def to_matrix_rayon_chunked(self, step):
+        if int(step) <= 0:
+            raise Exception("to_matrix_rayon_chunked: step must be positive")
+        return self.to_matrix_mode("Cuda")
+
     def to_matrix_rows(self, row_lo, row_hi, device=0):
         """Rows [row_lo,row_hi) as a self-contained (row_hi-row_lo) x 2^n CSR shard on `device`
         (local indptr, global column ids) -- what one rank of a row-sharded build owns."""
@@ -379,6 +398,19 @@ class SpMat:
             call("qr_diagonal_device", s.plan.handle, s.lo, s.hi, d.ptr, None)
             d.download(out[s.off:s.off + s.hi - s.lo])
         return out
+
+    def scale(self, factor):
+        """In place: every stored value times `factor` (pyqrusty/src/lib.rs:158-164), on the device with the
+        `ax` kernel (num-complex's multiply, so bit-identical to the CPU)."""
+        if self._shards is None:
+            raise Exception("cannot scale already-exported sparse matrix")
+        for s in self.to_device()._shards:
+            if s.nnz:
+                call("qr_set_device", s.device)
+                call("qr_ax_device", s.nnz, _c2(factor), s.data.ptr, s.data.ptr, None)
+        for s in self._shards:
+            call("qr_set_device", s.device)
+            synchronize()
 
     # -- zero elimination (pyqrusty/src/lib.rs:170-183 -> util.rs:144-171) ------------------------
     def _kept(self, tolerance, compact):

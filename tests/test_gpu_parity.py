@@ -722,6 +722,26 @@ def test_row_windows_at_the_top_of_32_bit_row_space(n, n_masks):
     assert_same((indptr, indices, data), want, "drop-zeros at the top rows")
 
 
+def test_spmat_scale_and_strategy_aliases(fixtures):
+    """SpMat.scale (pyqrusty/src/lib.rs:158-164) in place on the device, and the per-strategy to_matrix_*
+    entry points (lib.rs:386-404), which all denote the same matrix."""
+    labels, coeffs = fixtures["H4"]
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    op = make_op(labels, coeffs)
+    m = op.to_matrix()
+    m.scale(0.5 - 2j)
+    shape, data, indices, indptr = m.export()
+    assert np.array_equal(indices, ref[1]) and np.array_equal(indptr, ref[0])
+    assert np.array_equal(u64(data), u64(O.ax(0.5 - 2j, ref[2])))
+    with pytest.raises(Exception, match="exported"):
+        m.scale(2.0)
+    for build in (op.to_matrix_binary, op.to_matrix_accel, op.to_matrix_reduce, op.to_matrix_rayon,
+                  lambda: op.to_matrix_rayon_chunked(100)):
+        shape, data, indices, indptr = build().export()
+        assert_same((indptr, indices, data), ref, "strategy alias")
+
+
 def test_graph_capture_replay(fixtures):
     """qr_graph_*: the canonicalise -> fill sequence recorded once, replayed into zeroed buffers; event
     records inside the capture become graph nodes whose timestamps are readable after the replay."""
