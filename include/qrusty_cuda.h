@@ -91,6 +91,10 @@ QR_API int qr_plan_groups(const qr_plan *plan, uint64_t *xmask, uint32_t *group_
  * (group_offsets then index the merged list and term_order[i] is the first original index of
  * merged term i, for i < the returned count). */
 QR_API int qr_plan_canonical_terms(const qr_plan *plan, uint64_t *count);
+/* Name of the fill kernel qr_build_rows_device launches for an aligned row window of this plan
+ * ("fill_staged_kernel", "fill_rows_kernel", "fill_lanes_kernel", "fill_blocked_kernel" or
+ * "fill_direct_kernel"); a static string, for benchmarks and logs.  Never NULL. */
+QR_API const char *qr_plan_fill_kernel(const qr_plan *plan);
 
 /* Re-runs the canonicalisation kernel from the raw term table already in HBM,
  * asynchronously on `stream` (a cudaStream_t, NULL = default stream).  Lets a

@@ -126,6 +126,11 @@ class _Plan:
         call("qr_plan_canonical_terms", self.handle, C.byref(c))
         self.n_terms_canonical = c.value
 
+    @property
+    def fill_kernel(self):
+        """Name of the fill kernel an aligned row window of this plan is built with."""
+        return (lib.qr_plan_fill_kernel(self.handle) or b"").decode()
+
     def groups(self):
         x = np.zeros(self.n_groups, np.uint64)
         off = np.zeros(self.n_groups + 1, np.uint32)

@@ -111,7 +111,9 @@ lib.qr_last_error.restype = C.c_char_p
 lib.qr_last_error.argtypes = []
 lib.qr_version.restype = C.c_int
 lib.qr_kernel_launches.restype = C.c_uint64
-EXPORTS = sorted(list(SIGNATURES) + ["qr_last_error", "qr_version", "qr_kernel_launches"])
+lib.qr_plan_fill_kernel.restype = C.c_char_p
+lib.qr_plan_fill_kernel.argtypes = [_vp]
+EXPORTS = sorted(list(SIGNATURES) + ["qr_last_error", "qr_version", "qr_kernel_launches", "qr_plan_fill_kernel"])
 
 
 def check(rc):

@@ -599,4 +599,159 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
 #undef QR_LANES_RUNS
 }
 
+// ---------------------------------------------------------------------------------
+// Rows kernel (large G whose rows still fit shared memory a few at a time: G <= ~3000).
+//
+// One persistent CTA owns WHOLE rows, so -- like the staged kernel, and unlike the lanes
+// kernel -- everything it sends to HBM is one sequential stream of full lines issued by the
+// TMA; no LSU store instruction touches global memory and no sector is ever half-written.
+//
+// thread <-> group: thread t keeps groups t, t + TH, ... (<= NG of them) in registers for the
+// whole kernel: mask, first (z, c'), the first-flip slot steps of the lowest Q + 2 row bits.
+// The other terms of a group ("extras": T - G of them in all) sit in shared memory.
+// Rows are visited in batches of RT = 2^Q aligned consecutive rows; the batches of a run of
+// R = 2^log2R rows follow the Gray code of the batch index, so from one batch to the next
+// exactly one row bit b >= Q flips and the slot of group g moves by +-cnt[g][b] (plan.cuh):
+//     off(g) += (bit_b(row) just became 1) ? sd : -sd,     sd = bit_b(x_g) ? -cnt[g][b] : +cnt[g][b]
+// (sd for b < Q + 2 is a register, the rest one coalesced L1-resident load per 4 batches).
+// Within a batch the RT rows differ in bits < Q only: slot(row j) = off + sum_{b in j} sd_b.
+// A batch is assembled in one of two shared-memory buffers in final order -- the lanes of a
+// warp hold consecutive sorted groups, whose slots form a few contiguous runs (XOR never
+// splits a trie subtree), so the 16-byte shared stores are mostly conflict-free -- and is
+// handed to the TMA as two bulk copies (RT*G*16 B of data, RT*G*8 B of column ids) while the
+// CTA fills the other buffer.  One barrier per batch.
+//
+// Values: sign flips and __dadd_rn in original term order, first term taken as is: the fold
+// of accel.rs:191-205, bit for bit (same helpers as the other fill kernels).
+// ---------------------------------------------------------------------------------
+template <int NG, int Q, int TH>
+__global__ void __launch_bounds__(TH, 1)
+fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32_t n_runs,
+                 uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
+                 uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
+                 double2 *__restrict__ data, uint64_t indptr_last_row)
+{
+    constexpr uint32_t RT = 1u << Q;
+    constexpr int NS = Q + 2;                                      // row bits whose slot step lives in a register
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t tile_n = RT * G;                                // entries of one batch
+    double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                               // [2][tile_n]
+    uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)tile_n * 32u);      // [2][tile_n]
+    double2 *s_ec = reinterpret_cast<double2 *>(smem_raw + (size_t)tile_n * 48u);        // [n_extra]
+    uint32_t *s_ez = reinterpret_cast<uint32_t *>(s_ec + n_extra);                       // [n_extra]
+    const uint32_t T = p.n_terms, nq = (uint32_t)p.n_qubits;
+
+    // ---- once per CTA: this thread's groups ------------------------------------------------------
+    uint32_t x[NG], z0[NG], eb[NG], ee[NG], off[NG];
+    int32_t sd[NG][NS];
+    double c0r[NG], c0i[NG];
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        const uint32_t g = threadIdx.x + (uint32_t)k * TH;
+        const uint32_t gg = g < G ? g : G - 1u;
+        const uint32_t t0 = __ldg(&p.goff[gg]), t1 = __ldg(&p.goff[gg + 1]);
+        x[k] = __ldg(&p.gx[gg]);
+        z0[k] = __ldg(&p.tz[t0]);
+        const double2 c = __ldg(&p.tc[t0]);
+        c0r[k] = c.x; c0i[k] = c.y;
+        eb[k] = t0 - gg; ee[k] = t1 - gg - 1u;                     // sorted term t > t0 of group g is extra t - g - 1
+        if (g < G)
+            for (uint32_t t = t0 + 1u; t < t1; t++) { s_ez[t - gg - 1u] = __ldg(&p.tz[t]); s_ec[t - gg - 1u] = __ldg(&p.tc[t]); }
+#pragma unroll
+        for (int b = 0; b < NS; b++) {
+            const int32_t cb = (int32_t)__ldg(&p.cnt_t[(uint32_t)b * T + gg]);
+            sd[k][b] = ((x[k] >> b) & 1u) ? -cb : cb;
+        }
+        off[k] = 0;
+    }
+    __syncthreads();
+
+    const uint32_t R = 1u << log2R, n_batches = R >> Q;
+    uint32_t parity = 0;                                           // buffer of the current batch
+    for (uint32_t run = blockIdx.x; run < n_runs; run += gridDim.x) {
+        const uint64_t r0_64 = tile_row0 + ((uint64_t)run << log2R);   // first row of the run (aligned to R)
+        const uint32_t r0 = (uint32_t)r0_64;
+        if (indptr != nullptr)
+            for (uint32_t i = threadIdx.x; i < R; i += TH) {
+                const uint64_t lr = r0_64 + i - row_lo;
+                indptr[lr] = indptr_base + lr * G;
+                if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+            }
+        // slot of every group in the run's first row
+#pragma unroll
+        for (int k = 0; k < NG; k++) {
+            const uint32_t g = threadIdx.x + (uint32_t)k * TH, gg = g < G ? g : G - 1u, xr = x[k] ^ r0;
+            uint32_t o = 0;
+            for (uint32_t b = 0; b < nq; b++) {
+                const uint32_t cb = __ldg(&p.cnt_t[b * T + gg]);
+                o += ((xr >> b) & 1u) ? cb : 0u;
+            }
+            off[k] = o;
+        }
+        uint32_t rb = r0;                                          // first row of the batch (bits < Q are 0)
+        for (uint32_t i = 0; i < n_batches; i++) {
+            if (i != 0u) {                                         // Gray code over batches: step i flips row bit Q + ctz(i)
+                const uint32_t b = (uint32_t)Q + (uint32_t)__ffs((int)i) - 1u;
+                rb ^= 1u << b;
+                const bool up = (rb >> b) & 1u;                    // CTA-uniform
+#pragma unroll
+                for (int k = 0; k < NG; k++) {
+                    int32_t s;
+                    if (b == (uint32_t)Q) s = sd[k][Q];
+                    else if (b == (uint32_t)Q + 1u) s = sd[k][Q + 1];
+                    else {
+                        const uint32_t g = threadIdx.x + (uint32_t)k * TH, gg = g < G ? g : G - 1u;
+                        const int32_t cb = (int32_t)__ldg(&p.cnt_t[b * T + gg]);
+                        s = ((x[k] >> b) & 1u) ? -cb : cb;
+                    }
+                    off[k] += (uint32_t)(up ? s : -s);
+                }
+            }
+            double2 *bd = sdat + parity * tile_n;
+            uint64_t *bi = sidx + parity * tile_n;
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+                if (threadIdx.x + (uint32_t)k * TH < G) {
+                    double re[RT], im[RT];
+#pragma unroll
+                    for (uint32_t j = 0; j < RT; j++) {
+                        const uint32_t s = (uint32_t)(__popc((rb + j) & z0[k]) & 1) << 31;
+                        re[j] = flip_sign(c0r[k], s); im[j] = flip_sign(c0i[k], s);
+                    }
+                    for (uint32_t e = eb[k]; e < ee[k]; e++) {
+                        const uint32_t z = s_ez[e];
+                        const double2 c = s_ec[e];
+#pragma unroll
+                        for (uint32_t j = 0; j < RT; j++) {
+                            const uint32_t s = (uint32_t)(__popc((rb + j) & z) & 1) << 31;
+                            re[j] = __dadd_rn(re[j], flip_sign(c.x, s)); im[j] = __dadd_rn(im[j], flip_sign(c.y, s));
+                        }
+                    }
+#pragma unroll
+                    for (uint32_t j = 0; j < RT; j++) {
+                        uint32_t o = j * G + off[k];
+#pragma unroll
+                        for (int b = 0; b < Q; b++) if ((j >> b) & 1u) o += (uint32_t)sd[k][b];
+                        bd[o] = make_double2(re[j], im[j]);
+                        bi[o] = (uint64_t)((rb + j) ^ x[k]);
+                    }
+                }
+            }
+            // generic-proxy writes -> visible to the async proxy; the copy that last read the OTHER buffer
+            // (issued one batch ago) must have drained before anyone refills it after the barrier
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const uint64_t o = ((uint64_t)rb - row_lo) * G;
+                bulk_store_smem_to_global(data + o, bd, tile_n * 16u);
+                bulk_store_smem_to_global(indices + o, bi, tile_n * 8u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            parity ^= 1u;
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 }  // namespace qr

@@ -89,6 +89,9 @@ struct qr_plan {
     uint32_t block_s = 0, n_blocks = 0;    // blocked kernel: S and the number of subtree blocks
     // lanes kernel (large G, default): rows per run = 2^lanes_log2r, warps per CTA, heavy groups
     int lanes = 0, lanes_log2r = 0, lanes_warps = 0, lanes_resync = 2, lanes_persist = 0;
+    // rows kernel (large G, whole rows staged a few at a time): threads per CTA, groups per thread,
+    // log2(rows per batch), log2(rows per run); rows_th == 0: not used
+    int rows_th = 0, rows_ng = 0, rows_q = 0, rows_log2r = 0;
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -139,9 +142,34 @@ int blocked_strips(const qr_plan *pl)
     return pl->n_terms >= 3 * pl->n_groups ? 2 : 1;
 }
 
+// Rows kernel: eligible when two batches of 2^q whole rows plus the groups' extra terms fit in shared
+// memory and a thread keeps at most ROWS_MAX_NG groups.  QR_FILL_ROWS_TH / _Q / _R override the shape.
+constexpr int ROWS_MAX_NG_1024 = 3, ROWS_MAX_NG_512 = 6;
+size_t rows_smem(uint64_t G, uint64_t n_extra, int q) { return (size_t)((G << q) * 48 + n_extra * 20); }
+
+bool choose_rows(qr_plan *pl)
+{
+    const uint64_t G = pl->n_groups, n_extra = pl->n_terms_canonical - G;
+    int th = G > 512 ? 1024 : 512, q = 0, r = 7;
+    if (const char *env = getenv("QR_FILL_ROWS_TH")) { int v = atoi(env); if (v == 512 || v == 1024) th = v; }
+    int ng = (int)((G + th - 1) / th);
+    if (th == 1024 && ng > ROWS_MAX_NG_1024) { th = 512; ng = (int)((G + th - 1) / th); }
+    if (ng > (th == 1024 ? ROWS_MAX_NG_1024 : ROWS_MAX_NG_512)) return false;
+    if (const char *env = getenv("QR_FILL_ROWS_Q")) { int v = atoi(env); if (v == 1 || v == 2) q = v; }
+    if (q == 0) q = rows_smem(G, n_extra, 2) <= MAX_SMEM ? 2 : 1;
+    if (q == 2 && rows_smem(G, n_extra, 2) > MAX_SMEM) q = 1;
+    if (rows_smem(G, n_extra, q) > MAX_SMEM) return false;
+    if ((G << q) * 16 >= (1ull << 31)) return false;
+    if (const char *env = getenv("QR_FILL_ROWS_R")) { int v = atoi(env); if (v >= q && v <= 16) r = v; }
+    pl->rows_th = th; pl->rows_ng = ng; pl->rows_q = q; pl->rows_log2r = r;
+    return true;
+}
+
 void choose_staged(qr_plan *pl)
 {
     pl->rw = pl->gw = 0;
+    pl->rows_th = 0;
+    if (const char *env = getenv("QR_FILL_ROWS")) if (env[0] == '1') choose_rows(pl);   // force (tests, sweeps)
     const uint64_t G = pl->n_groups;
     pl->block_s = 0;
     pl->lanes = 0;
@@ -177,6 +205,11 @@ void choose_staged(qr_plan *pl)
         // shared memory (profiles/r01_fill_sweep_largeG.jsonl: C3 4.52 TB/s at S=32, 3.73 at 64).
         pl->lanes = 1;
         if (const char *env = getenv("QR_FILL_LANES")) if (env[0] == '0') { pl->lanes = 0; pl->block_s = 32; }
+        // G >= 400 with rows that fit shared memory two batches at a time: whole rows through the TMA
+        // (fill_rows_kernel); the lanes kernel stays the path for everything else and for the ragged
+        // cases build_rows cannot align
+        const char *env = getenv("QR_FILL_ROWS");
+        if (!(env && env[0] == '0') && G >= 400) choose_rows(pl);
     }
 }
 
@@ -331,6 +364,16 @@ extern "C" int qr_plan_canonical_terms(const qr_plan *pl, uint64_t *count)
     return QR_OK;
 }
 
+extern "C" const char *qr_plan_fill_kernel(const qr_plan *pl)
+{
+    if (!pl) return "";
+    if (pl->rows_th) return "fill_rows_kernel";
+    if (pl->lanes) return "fill_lanes_kernel";
+    if (pl->block_s) return "fill_blocked_kernel";
+    if (pl->rw) return "fill_staged_kernel";
+    return "fill_direct_kernel";
+}
+
 extern "C" int qr_plan_canonicalise_async(qr_plan *pl, void *stream)
 {
     if (!pl) return fail(QR_ERR_INVALID, "qr_plan_canonicalise_async: NULL plan");
@@ -365,6 +408,40 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
     const uint64_t G = pl->n_groups;
     const uint64_t indptr_base = (flags & QR_INDPTR_GLOBAL) ? row_lo * G : 0;
     uint64_t lo = row_lo, hi = row_hi;
+    if (!(flags & QR_FILL_DIRECT) && pl->rows_th) {
+        const int q = pl->rows_q;
+        int k = std::max(pl->rows_log2r, q);
+        while (k > q && align_up(row_lo, 1ull << k) + (1ull << k) > row_hi) k--;      // short windows: shorter runs
+        const uint64_t R = 1ull << k;
+        const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
+        // the bulk copies need 16-byte aligned global addresses: indices + (s0 - row_lo) * G * 8
+        const bool aligned = (((s0 - row_lo) * G) & 1) == 0;
+        if (s1 > s0 && aligned && (s1 - s0) / R <= 0xffffffffull) {
+            const uint64_t n_runs = (s1 - s0) / R, n_extra = pl->n_terms_canonical - G;
+            const size_t smem = rows_smem(G, n_extra, q);
+            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t,
+                                    uint64_t *, uint64_t *, double2 *, uint64_t);
+            RowsFn kern = nullptr;
+#define QR_ROWS_CASE(NG_, TH_) \
+            if (pl->rows_ng == NG_ && pl->rows_th == TH_) kern = q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_>;
+            QR_ROWS_CASE(1, 1024) QR_ROWS_CASE(2, 1024) QR_ROWS_CASE(3, 1024)
+            QR_ROWS_CASE(1, 512) QR_ROWS_CASE(2, 512) QR_ROWS_CASE(3, 512) QR_ROWS_CASE(4, 512) QR_ROWS_CASE(5, 512) QR_ROWS_CASE(6, 512)
+#undef QR_ROWS_CASE
+            if (!kern) return fail(QR_ERR_UNSUPPORTED, "fill_rows: no kernel instance for this plan");
+            QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0, n_sm = 0;
+            QR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl->rows_th, smem));
+            QR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pl->device));
+            if (per_sm < 1) return fail(QR_ERR_CUDA, "fill_rows: kernel does not fit on an SM");
+            const uint64_t ctas = std::min<uint64_t>(n_runs, (uint64_t)per_sm * (uint64_t)n_sm);   // persistent CTAs
+            int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+            if (rc != QR_OK) return rc;
+            kern<<<(unsigned)ctas, pl->rows_th, smem, st>>>(pl->dev, (uint32_t)G, (uint32_t)n_extra, (uint32_t)k, (uint32_t)n_runs,
+                                                           s0, row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo);
+            QR_LAUNCH_CHECK("fill_rows_kernel");
+            return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+        }
+    }
     if (!(flags & QR_FILL_DIRECT) && pl->lanes) {
         int k = pl->lanes_log2r;
         while (k > 5 && align_up(row_lo, 1ull << k) + (1ull << k) > row_hi) k--;     // short windows: shorter runs

@@ -241,15 +241,77 @@ def test_lanes_kernel_clusters(monkeypatch, W):
     labels, coeffs = H.random_pauli_sum(12, 1500, 1100, 50, 5)
     n, params = O.make_params(labels, coeffs)
     ref = O.build_csr(params, n)
+    monkeypatch.setenv("QR_FILL_ROWS", "0")
     for R in (5, 8):
         monkeypatch.setenv("QR_FILL_LANES_R", str(R))
         monkeypatch.setenv("QR_FILL_LANES_W", str(W))
         plan = make_op(labels, coeffs).plan()
-        assert plan.n_groups == 1100
+        assert plan.n_groups == 1100 and plan.fill_kernel == "fill_lanes_kernel"
         assert_same(device_build(plan, 0, 1 << n), ref, f"G=1100 W={W} R={R}")
         lo, hi = 100, 4000
         ip, ix, dt = device_build(plan, lo, hi)
         assert np.array_equal(ix, ref[1][lo * 1100:hi * 1100]) and np.array_equal(u64(dt), u64(ref[2][lo * 1100:hi * 1100]))
+
+
+@pytest.mark.parametrize("TH,Q,R", [(512, 1, 1), (512, 2, 5), (1024, 1, 7), (1024, 2, 3), (512, 1, 4), (1024, 2, 8)])
+@pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
+def test_rows_kernel(fixtures, monkeypatch, name, TH, Q, R):
+    """Rows kernel (fill_rows_kernel: persistent CTAs own whole rows, thread <-> group, batches of 2^Q rows
+    in Gray-code order through two shared-memory buffers and the TMA) forced on every case: whole matrix
+    and ragged windows (edge rows go through the direct kernel, misaligned windows through the default path)."""
+    monkeypatch.setenv("QR_FILL_ROWS", "1")
+    monkeypatch.setenv("QR_FILL_ROWS_TH", str(TH))
+    monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
+    monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    assert plan.fill_kernel == "fill_rows_kernel"
+    G, dim = plan.n_groups, 1 << n
+    assert_same(device_build(plan, 0, dim), ref, f"{name} TH={TH} Q={Q} R={R}")
+    if dim >= 128:
+        for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 33), (6, dim - 2)]:
+            ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
+            assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G])), (lo, hi)
+            assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
+
+
+@pytest.mark.parametrize("G,T,TH,Q", [(1100, 1500, 1024, 1), (1100, 1500, 1024, 2), (1100, 1500, 512, 1), (2200, 2600, 1024, 1),
+                                      (2200, 2600, 512, 1), (600, 2400, 512, 2), (450, 500, 0, 0)])
+def test_rows_kernel_large_G(monkeypatch, G, T, TH, Q):
+    """The shapes the rows kernel is chosen for by default (G >= 400): 2..5 groups per thread, extras in
+    shared memory (T - G of them, up to 4 per group on average), 2- and 4-row batches, runs of 8 and 128 rows,
+    several runs per persistent CTA (a 2^12-row matrix on 148 CTAs has 512 runs of 8 rows)."""
+    labels, coeffs = H.random_pauli_sum(12, T, G, 50, 5)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    if TH:
+        monkeypatch.setenv("QR_FILL_ROWS_TH", str(TH))
+        monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
+    for R in (3, 7):
+        monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
+        plan = make_op(labels, coeffs).plan()
+        assert plan.n_groups == G and plan.fill_kernel == "fill_rows_kernel"
+        assert_same(device_build(plan, 0, 1 << n), ref, f"G={G} TH={TH} Q={Q} R={R}")
+        lo, hi = 100, 4000
+        ip, ix, dt = device_build(plan, lo, hi)
+        assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G]))
+        assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
+
+
+def test_rows_kernel_selection(fixtures, monkeypatch):
+    """Default choice: staged for rows that fit a 32-row tile, lanes for 150 < G < 400 and for rows too long for
+    two shared-memory batches, rows in between; QR_FILL_ROWS=0 restores the lanes kernel."""
+    def kernel_of(labels, coeffs):
+        return make_op(labels, coeffs).plan().fill_kernel
+    assert kernel_of(*H.xxz_chain(10, 1.0, 0.7)) == "fill_staged_kernel"
+    assert kernel_of(*fixtures["H6"]) == "fill_lanes_kernel"                       # G = 286
+    big = H.random_pauli_sum(12, 1500, 1100, 50, 5)
+    assert kernel_of(*big) == "fill_rows_kernel"
+    assert kernel_of(*H.random_pauli_sum(13, 3500, 3000, 50, 5)) == "fill_lanes_kernel"    # 3000 * 96 B > 227 KB
+    monkeypatch.setenv("QR_FILL_ROWS", "0")
+    assert kernel_of(*big) == "fill_lanes_kernel"
 
 
 def test_lanes_kernel_is_the_large_G_default(fixtures):
@@ -703,7 +765,8 @@ def test_multi_gpu_single_process(fixtures):
 @pytest.mark.parametrize("n,n_masks", [(32, 20), (32, 300), (31, 24), (30, 1100)])
 def test_row_windows_at_the_top_of_32_bit_row_space(n, n_masks):
     """n = 30..32 qubits: windows that end at row 2^n, straddle 2^31, or sit in the middle -- row ids and
-    column ids use every bit of a u32, offsets are 64-bit.  Staged (G = 20, 24), lanes (G = 300, 1100)."""
+    column ids use every bit of a u32, offsets are 64-bit.  Staged (G = 20, 24), lanes (G = 300), rows (G = 1100;
+    its misaligned windows fall through to the lanes kernel)."""
     labels, coeffs = H.random_pauli_sum(n, n_masks + n_masks // 2, n_masks, 5, 1000 + n_masks)
     nq, params = O.make_params(labels, coeffs)
     plan = make_op(labels, coeffs).plan()

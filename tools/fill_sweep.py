@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Times the fill kernel (events on the launching stream) for one workload under several
 (RW,GW) tile configurations, the direct kernel, and a row window size.  GPU box only.
-  python tools/fill_sweep.py C2 | C4 | C3 | xxz<n> | H8 ...   [--rows LOG2] [--cfgs "2,4 1,8 direct lanes:8:8 blocked:32:1"]
+  python tools/fill_sweep.py C2 | C4 | C3 | xxz<n> | H8 ...   [--rows LOG2] [--cfgs "2,4 1,8 direct lanes:8:8 blocked:32:1 rows:1024:1:7"]
 """
 import argparse, ctypes as C, gzip, json, os, sys
 from pathlib import Path
@@ -40,10 +40,17 @@ def main():
     for cfg in a.cfgs.split():
         flags = 0
         for k in ("QR_FILL_CFG", "QR_FILL_LANES", "QR_FILL_LANES_R", "QR_FILL_LANES_W", "QR_FILL_LANES_SYNC",
-                  "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E"):      # the ones a cfg string sets
+                  "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E", "QR_FILL_ROWS", "QR_FILL_ROWS_TH",
+                  "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R"):      # the ones a cfg string sets
             os.environ.pop(k, None)
         if cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
+        elif cfg.startswith("rows"):                  # rows[:threads[:log2(rows per batch)[:log2(rows per run)]]]
+            parts = cfg.split(":")
+            os.environ["QR_FILL_ROWS"] = "1"
+            if len(parts) > 1: os.environ["QR_FILL_ROWS_TH"] = parts[1]
+            if len(parts) > 2: os.environ["QR_FILL_ROWS_Q"] = parts[2]
+            if len(parts) > 3: os.environ["QR_FILL_ROWS_R"] = parts[3]
         elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:sync[:persist]]]]
             parts = cfg.split(":")
             os.environ["QR_FILL_LANES"] = "1"
@@ -79,7 +86,7 @@ def main():
         ms = C.c_float(); call("qr_event_elapsed_ms", e0, e1, C.byref(ms))
         t = ms.value / a.reps
         nbytes = rows * G * 24 + (rows + 1) * 8
-        print(json.dumps({"workload": a.workload, "cfg": cfg, "n": n, "T": len(labels), "G": G, "rows": rows,
+        print(json.dumps({"workload": a.workload, "cfg": cfg, "kernel": plan.fill_kernel, "n": n, "T": len(labels), "G": G, "rows": rows,
                           "ms": round(t, 5), "GBps": round(nbytes / t / 1e6, 1), "Gnnz_s": round(rows * G / t / 1e6, 2)}), flush=True)
 
 
