@@ -621,13 +621,33 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
 // handed to the TMA as two bulk copies (RT*G*16 B of data, RT*G*8 B of column ids) while the
 // CTA fills the other buffer.  One barrier per batch.
 //
+// Groups with more than hv_thr terms ("heavy": the Z-only group of a molecular Hamiltonian and a
+// few dozen others) would make their owner's warp the critical path of every batch.  They are
+// evaluated by the whole CTA instead, lane <-> row, for an aligned strip of 32 rows at a time
+// (the next 32 / RT batches stay inside that strip), into a side buffer s_hv[heavy][32] their
+// owners read back.
+//
 // Values: sign flips and __dadd_rn in original term order, first term taken as is: the fold
 // of accel.rs:191-205, bit for bit (same helpers as the other fill kernels).
 // ---------------------------------------------------------------------------------
+// +-1.0 whose sign is bit 0 of p (the other bits of p are ignored)
+__device__ __forceinline__ double pm_one(uint32_t p)
+{
+    return __hiloint2double((int)(0x3ff00000u + (p << 31)), 0);
+}
+// bit 0 of the result: parity of popc((rb + j) & z) given p = popc(rb & z), for rb with no bits below Q and j < 2^Q
+template <int Q>
+__device__ __forceinline__ uint32_t rows_parity(uint32_t p, uint32_t z, uint32_t j)
+{
+#pragma unroll
+    for (int b = 0; b < Q; b++) if ((j >> b) & 1u) p ^= z >> b;
+    return p;
+}
+
 template <int NG, int Q, int TH>
 __global__ void __launch_bounds__(TH, 1)
 fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32_t n_runs,
-                 uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
+                 uint32_t hv_thr, uint32_t hv_cap, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
                  uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
                  double2 *__restrict__ data, uint64_t indptr_last_row)
 {
@@ -639,10 +659,16 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)tile_n * 32u);      // [2][tile_n]
     double2 *s_ec = reinterpret_cast<double2 *>(smem_raw + (size_t)tile_n * 48u);        // [n_extra]
     uint32_t *s_ez = reinterpret_cast<uint32_t *>(s_ec + n_extra);                       // [n_extra]
+    double2 *s_hv = reinterpret_cast<double2 *>(smem_raw + (((size_t)tile_n * 48u + (size_t)n_extra * 20u + 15u) & ~(size_t)15u));   // [hv_cap][32]
+    uint32_t *s_hg = reinterpret_cast<uint32_t *>(s_hv + (size_t)hv_cap * 32u);          // [hv_cap]
+    __shared__ uint32_t s_nheavy;
     const uint32_t T = p.n_terms, nq = (uint32_t)p.n_qubits;
+    constexpr uint32_t NOT_HEAVY = 0xffffffffu;
+    if (threadIdx.x == 0) s_nheavy = 0;
+    __syncthreads();
 
     // ---- once per CTA: this thread's groups ------------------------------------------------------
-    uint32_t x[NG], z0[NG], eb[NG], ee[NG], off[NG];
+    uint32_t x[NG], z0[NG], eb[NG], ee[NG], off[NG], hidx[NG];
     int32_t sd[NG][NS];
     double c0r[NG], c0i[NG];
 #pragma unroll
@@ -657,6 +683,13 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
         eb[k] = t0 - gg; ee[k] = t1 - gg - 1u;                     // sorted term t > t0 of group g is extra t - g - 1
         if (g < G)
             for (uint32_t t = t0 + 1u; t < t1; t++) { s_ez[t - gg - 1u] = __ldg(&p.tz[t]); s_ec[t - gg - 1u] = __ldg(&p.tc[t]); }
+        // heavy groups (more than hv_thr terms: the Z-only group of a molecular Hamiltonian, a few dozen others)
+        // are evaluated lane <-> row for 32 rows at a time by the whole CTA, not inside their owner's lane
+        hidx[k] = NOT_HEAVY;
+        if (g < G && t1 - t0 > hv_thr) {
+            const uint32_t h = atomicAdd(&s_nheavy, 1u);
+            if (h < hv_cap) { hidx[k] = h; s_hg[h] = g; }
+        }
 #pragma unroll
         for (int b = 0; b < NS; b++) {
             const int32_t cb = (int32_t)__ldg(&p.cnt_t[(uint32_t)b * T + gg]);
@@ -667,6 +700,9 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     __syncthreads();
 
     const uint32_t R = 1u << log2R, n_batches = R >> Q;
+    const uint32_t n_heavy = min(s_nheavy, hv_cap);
+    const uint32_t HS = R < 32u ? R : 32u, SB = HS >> Q;           // rows / batches per heavy strip
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t parity = 0;                                           // buffer of the current batch
     for (uint32_t run = blockIdx.x; run < n_runs; run += gridDim.x) {
         const uint64_t r0_64 = tile_row0 + ((uint64_t)run << log2R);   // first row of the run (aligned to R)
@@ -707,24 +743,59 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                     off[k] += (uint32_t)(up ? s : -s);
                 }
             }
+            if (n_heavy != 0u && (i & (SB - 1u)) == 0u) {
+                // the next SB batches stay inside the aligned strip of HS rows that holds rb: every warp takes heavy
+                // groups round-robin, lane <-> row, warp-uniform term loop (extras broadcast from shared memory).
+                // The barrier that ended the previous batch also retired the last reader of s_hv.
+                const uint32_t r = (rb & ~(HS - 1u)) + lane;
+                for (uint32_t q = warp; q < n_heavy; q += TH / 32u) {
+                    const uint32_t g = s_hg[q], t0 = __ldg(&p.goff[g]), t1 = __ldg(&p.goff[g + 1]);
+                    const double2 c0 = __ldg(&p.tc[t0]);
+                    uint32_t s = (uint32_t)(__popc(r & __ldg(&p.tz[t0])) & 1) << 31;
+                    double hre = flip_sign(c0.x, s), him = flip_sign(c0.y, s);
+#pragma unroll 4
+                    for (uint32_t e = t0 - g; e < t1 - g - 1u; e++) {
+                        const double2 c = s_ec[e];
+                        const double sg = pm_one((uint32_t)__popc(r & s_ez[e]));
+                        hre = __fma_rn(sg, c.x, hre); him = __fma_rn(sg, c.y, him);
+                    }
+                    s_hv[q * 32u + lane] = make_double2(hre, him);
+                }
+                __syncthreads();
+            }
             double2 *bd = sdat + parity * tile_n;
             uint64_t *bi = sidx + parity * tile_n;
 #pragma unroll
             for (int k = 0; k < NG; k++) {
                 if (threadIdx.x + (uint32_t)k * TH < G) {
                     double re[RT], im[RT];
-#pragma unroll
-                    for (uint32_t j = 0; j < RT; j++) {
-                        const uint32_t s = (uint32_t)(__popc((rb + j) & z0[k]) & 1) << 31;
-                        re[j] = flip_sign(c0r[k], s); im[j] = flip_sign(c0i[k], s);
-                    }
-                    for (uint32_t e = eb[k]; e < ee[k]; e++) {
-                        const uint32_t z = s_ez[e];
-                        const double2 c = s_ec[e];
+                    if (hidx[k] != NOT_HEAVY) {
 #pragma unroll
                         for (uint32_t j = 0; j < RT; j++) {
-                            const uint32_t s = (uint32_t)(__popc((rb + j) & z) & 1) << 31;
-                            re[j] = __dadd_rn(re[j], flip_sign(c.x, s)); im[j] = __dadd_rn(im[j], flip_sign(c.y, s));
+                            const double2 v = s_hv[hidx[k] * 32u + ((rb + j) & (HS - 1u))];
+                            re[j] = v.x; im[j] = v.y;
+                        }
+                    } else {
+                        // rb has no bits below Q, so popc((rb + j) & z) = popc(rb & z) + popc(j & z): one POPC per term
+                        // serves the RT rows; bit 0 of p0 ^ (z >> b) ^ ... is row j's parity
+                        const uint32_t p0 = (uint32_t)__popc(rb & z0[k]);
+#pragma unroll
+                        for (uint32_t j = 0; j < RT; j++) {
+                            const uint32_t s = rows_parity<Q>(p0, z0[k], j) << 31;
+                            re[j] = flip_sign(c0r[k], s); im[j] = flip_sign(c0i[k], s);
+                        }
+                        // later terms: fma(+-1.0, c', acc) is the sign flip and the __dadd_rn of the fold in one
+                        // instruction per component (the product is exact, signed zeros included)
+#pragma unroll 1
+                        for (uint32_t e = eb[k]; e < ee[k]; e++) {
+                            const uint32_t z = s_ez[e];
+                            const double2 c = s_ec[e];
+                            const uint32_t p = (uint32_t)__popc(rb & z);
+#pragma unroll
+                            for (uint32_t j = 0; j < RT; j++) {
+                                const double sg = pm_one(rows_parity<Q>(p, z, j));
+                                re[j] = __fma_rn(sg, c.x, re[j]); im[j] = __fma_rn(sg, c.y, im[j]);
+                            }
                         }
                     }
 #pragma unroll

@@ -92,6 +92,8 @@ struct qr_plan {
     // rows kernel (large G, whole rows staged a few at a time): threads per CTA, groups per thread,
     // log2(rows per batch), log2(rows per run); rows_th == 0: not used
     int rows_th = 0, rows_ng = 0, rows_q = 0, rows_log2r = 0;
+    uint32_t rows_hv_thr = 0xffffffffu, rows_hv_cap = 0;   // heavy groups: more than hv_thr terms, hv_cap of them
+    size_t rows_smem_bytes = 0;
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -145,24 +147,49 @@ int blocked_strips(const qr_plan *pl)
 // Rows kernel: eligible when two batches of 2^q whole rows plus the groups' extra terms fit in shared
 // memory and a thread keeps at most ROWS_MAX_NG groups.  QR_FILL_ROWS_TH / _Q / _R override the shape.
 constexpr int ROWS_MAX_NG_1024 = 3, ROWS_MAX_NG_512 = 6;
-size_t rows_smem(uint64_t G, uint64_t n_extra, int q) { return (size_t)((G << q) * 48 + n_extra * 20); }
+constexpr uint32_t ROWS_HEAVY_TERMS = 6;                 // groups with more terms than this are "heavy"
+size_t rows_smem(uint64_t G, uint64_t n_extra, int q, uint64_t n_heavy = 0)
+{
+    return (size_t)align_up((G << q) * 48 + n_extra * 20, 16) + (size_t)n_heavy * (32 * 16 + 4);
+}
 
 bool choose_rows(qr_plan *pl)
 {
     const uint64_t G = pl->n_groups, n_extra = pl->n_terms_canonical - G;
-    int th = G > 512 ? 1024 : 512, q = 0, r = 7;
+    // 1024 threads (32 warps hide the shared-memory and FP64 latency of the term loops) while a thread's groups fit
+    // its 64 registers: C3 6.63 vs 6.34 TB/s at 512, H8 3.88 vs 3.68 (profiles/r03_rows_sweep.jsonl)
+    int th = G <= 1024 * (uint64_t)ROWS_MAX_NG_1024 ? 1024 : 512, q_forced = 0, r = 0;
     if (const char *env = getenv("QR_FILL_ROWS_TH")) { int v = atoi(env); if (v == 512 || v == 1024) th = v; }
     int ng = (int)((G + th - 1) / th);
     if (th == 1024 && ng > ROWS_MAX_NG_1024) { th = 512; ng = (int)((G + th - 1) / th); }
     if (ng > (th == 1024 ? ROWS_MAX_NG_1024 : ROWS_MAX_NG_512)) return false;
-    if (const char *env = getenv("QR_FILL_ROWS_Q")) { int v = atoi(env); if (v == 1 || v == 2) q = v; }
-    if (q == 0) q = rows_smem(G, n_extra, 2) <= MAX_SMEM ? 2 : 1;
-    if (q == 2 && rows_smem(G, n_extra, 2) > MAX_SMEM) q = 1;
-    if (rows_smem(G, n_extra, q) > MAX_SMEM) return false;
-    if ((G << q) * 16 >= (1ull << 31)) return false;
-    if (const char *env = getenv("QR_FILL_ROWS_R")) { int v = atoi(env); if (v >= q && v <= 16) r = v; }
-    pl->rows_th = th; pl->rows_ng = ng; pl->rows_q = q; pl->rows_log2r = r;
-    return true;
+    if ((G << 2) * 16 >= (1ull << 31)) return false;
+    if (const char *env = getenv("QR_FILL_ROWS_Q")) { int v = atoi(env); if (v == 1 || v == 2) q_forced = v; }
+    // group sizes decide which groups leave their owner's lane for the CTA-wide heavy path
+    std::vector<uint32_t> goff(G + 1);
+    if (cudaMemcpy(goff.data(), pl->dev.goff, (G + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; }
+    uint32_t thr0 = ROWS_HEAVY_TERMS;
+    if (const char *env = getenv("QR_FILL_ROWS_HV")) { int v = atoi(env); thr0 = v <= 0 ? 0xffffffffu : (uint32_t)v; }
+    auto heavy_count = [&](uint32_t thr) { uint64_t n = 0; for (uint64_t g = 0; g < G; g++) n += goff[g + 1] - goff[g] > thr; return n; };
+    for (int q = q_forced ? q_forced : 2; q >= (q_forced ? q_forced : 1); q--) {
+        if (rows_smem(G, n_extra, q) > MAX_SMEM) continue;
+        uint32_t thr = thr0;
+        uint64_t nh = heavy_count(thr);
+        // 4-row batches only if every heavy group fits beside them; 2-row batches shed heavy groups (raise
+        // the threshold) until the side buffer fits
+        while (nh != 0 && rows_smem(G, n_extra, q, nh) > MAX_SMEM) {
+            if (q == 2 && !q_forced) break;
+            thr = thr > 0x7fffffffu ? 0xffffffffu : thr * 2;
+            nh = thr == 0xffffffffu ? 0 : heavy_count(thr);
+        }
+        if (rows_smem(G, n_extra, q, nh) > MAX_SMEM) continue;
+        if (const char *env = getenv("QR_FILL_ROWS_R")) { int v = atoi(env); if (v >= q && v <= 16) r = v; }
+        pl->rows_th = th; pl->rows_ng = ng; pl->rows_q = q; pl->rows_log2r = r ? std::max(r, q) : 0;   // 0: per window
+        pl->rows_hv_thr = nh ? thr : 0xffffffffu; pl->rows_hv_cap = (uint32_t)nh;
+        pl->rows_smem_bytes = rows_smem(G, n_extra, q, nh);
+        return true;
+    }
+    return false;
 }
 
 void choose_staged(qr_plan *pl)
@@ -410,7 +437,18 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
     uint64_t lo = row_lo, hi = row_hi;
     if (!(flags & QR_FILL_DIRECT) && pl->rows_th) {
         const int q = pl->rows_q;
-        int k = std::max(pl->rows_log2r, q);
+        // rows per run: 256 (C3 6.27 TB/s; 128: 6.04, 64: 5.66), shorter when the window does not hold enough runs
+        // to spread evenly over the persistent CTAs (2^16 rows of H8: 32-row runs 3.28 TB/s, 128-row runs 3.02)
+        int k = pl->rows_log2r ? pl->rows_log2r : 8;
+        if (!pl->rows_log2r) {
+            const uint64_t span = row_hi - row_lo;
+            while (k > 5 && k > q) {
+                const uint64_t runs = span >> k;
+                if (runs >= 148 && (runs + 147) / 148 * 148 * 100 <= runs * 104) break;    // <= 4 % idle tail on 148 CTAs
+                k--;
+            }
+        }
+        k = std::max(k, q);
         while (k > q && align_up(row_lo, 1ull << k) + (1ull << k) > row_hi) k--;      // short windows: shorter runs
         const uint64_t R = 1ull << k;
         const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
@@ -418,9 +456,9 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         const bool aligned = (((s0 - row_lo) * G) & 1) == 0;
         if (s1 > s0 && aligned && (s1 - s0) / R <= 0xffffffffull) {
             const uint64_t n_runs = (s1 - s0) / R, n_extra = pl->n_terms_canonical - G;
-            const size_t smem = rows_smem(G, n_extra, q);
-            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t,
-                                    uint64_t *, uint64_t *, double2 *, uint64_t);
+            const size_t smem = pl->rows_smem_bytes;
+            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t,
+                                    uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
             RowsFn kern = nullptr;
 #define QR_ROWS_CASE(NG_, TH_) \
             if (pl->rows_ng == NG_ && pl->rows_th == TH_) kern = q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_>;
@@ -437,7 +475,8 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
             kern<<<(unsigned)ctas, pl->rows_th, smem, st>>>(pl->dev, (uint32_t)G, (uint32_t)n_extra, (uint32_t)k, (uint32_t)n_runs,
-                                                           s0, row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo);
+                                                           pl->rows_hv_thr, pl->rows_hv_cap, s0, row_lo, indptr_base, d_indptr,
+                                                           d_indices, d_data, row_hi - row_lo);
             QR_LAUNCH_CHECK("fill_rows_kernel");
             return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
         }

@@ -254,12 +254,16 @@ def test_lanes_kernel_clusters(monkeypatch, W):
 
 
 @pytest.mark.parametrize("TH,Q,R", [(512, 1, 1), (512, 2, 5), (1024, 1, 7), (1024, 2, 3), (512, 1, 4), (1024, 2, 8)])
+@pytest.mark.parametrize("HV", [None, "0", "2"])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
-def test_rows_kernel(fixtures, monkeypatch, name, TH, Q, R):
+def test_rows_kernel(fixtures, monkeypatch, name, TH, Q, R, HV):
     """Rows kernel (fill_rows_kernel: persistent CTAs own whole rows, thread <-> group, batches of 2^Q rows
     in Gray-code order through two shared-memory buffers and the TMA) forced on every case: whole matrix
-    and ragged windows (edge rows go through the direct kernel, misaligned windows through the default path)."""
+    and ragged windows (edge rows go through the direct kernel, misaligned windows through the default path).
+    HV: threshold of the CTA-wide heavy-group path (default: more than 6 terms; "0": off; "2": nearly every group)."""
     monkeypatch.setenv("QR_FILL_ROWS", "1")
+    if HV is not None:
+        monkeypatch.setenv("QR_FILL_ROWS_HV", HV)
     monkeypatch.setenv("QR_FILL_ROWS_TH", str(TH))
     monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
     monkeypatch.setenv("QR_FILL_ROWS_R", str(R))

@@ -41,16 +41,17 @@ def main():
         flags = 0
         for k in ("QR_FILL_CFG", "QR_FILL_LANES", "QR_FILL_LANES_R", "QR_FILL_LANES_W", "QR_FILL_LANES_SYNC",
                   "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E", "QR_FILL_ROWS", "QR_FILL_ROWS_TH",
-                  "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R"):      # the ones a cfg string sets
+                  "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R", "QR_FILL_ROWS_HV"):      # the ones a cfg string sets
             os.environ.pop(k, None)
         if cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
-        elif cfg.startswith("rows"):                  # rows[:threads[:log2(rows per batch)[:log2(rows per run)]]]
+        elif cfg.startswith("rows"):                  # rows[:threads[:log2(rows per batch)[:log2(rows per run)[:heavy threshold]]]]
             parts = cfg.split(":")
             os.environ["QR_FILL_ROWS"] = "1"
             if len(parts) > 1: os.environ["QR_FILL_ROWS_TH"] = parts[1]
             if len(parts) > 2: os.environ["QR_FILL_ROWS_Q"] = parts[2]
             if len(parts) > 3: os.environ["QR_FILL_ROWS_R"] = parts[3]
+            if len(parts) > 4: os.environ["QR_FILL_ROWS_HV"] = parts[4]
         elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:sync[:persist]]]]
             parts = cfg.split(":")
             os.environ["QR_FILL_LANES"] = "1"
