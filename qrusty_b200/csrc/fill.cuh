@@ -623,9 +623,10 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
 //
 // Groups with more than hv_thr terms ("heavy": the Z-only group of a molecular Hamiltonian and a
 // few dozen others) would make their owner's warp the critical path of every batch.  They are
-// evaluated by the whole CTA instead, lane <-> row, for an aligned strip of 32 rows at a time
-// (the next 32 / RT batches stay inside that strip), into a side buffer s_hv[heavy][32] their
-// owners read back.
+// evaluated by the whole CTA instead, lane <-> row, for an aligned strip of 2^hv_log2 = 32..128
+// rows at a time (the next batches stay inside that strip), into a side buffer s_hv[heavy][strip]
+// their owners read back; a lane folds up to 4 rows at once, which is what hides the latency of
+// the one dependent FP64 chain per (group, row).
 //
 // Values: sign flips and __dadd_rn in original term order, first term taken as is: the fold
 // of accel.rs:191-205, bit for bit (same helpers as the other fill kernels).
@@ -644,51 +645,127 @@ __device__ __forceinline__ uint32_t rows_parity(uint32_t p, uint32_t z, uint32_t
     return p;
 }
 
-template <int NG, int Q, int TH>
+// Folds terms [0, n) of (zs, cs) into HE rows per lane: r, r + 32, ...
+template <int HE>
+__device__ __forceinline__ void rows_heavy_fold(const uint32_t *zs, const double2 *cs, uint32_t n, uint32_t r,
+                                                double (&hre)[4], double (&him)[4])
+{
+#pragma unroll 2
+    for (uint32_t t = 0; t < n; t++) {
+        const uint32_t z = zs[t];                                  // shared memory, warp-uniform (broadcast)
+        const double2 c = cs[t];
+#pragma unroll
+        for (int e = 0; e < HE; e++) {
+            const double sg = pm_one((uint32_t)__popc((r + 32u * e) & z));
+            hre[e] = __fma_rn(sg, c.x, hre[e]); him[e] = __fma_rn(sg, c.y, him[e]);
+        }
+    }
+}
+
+// The CTA-wide heavy phase for the strip of HS rows that starts at row `sbase`.  s_hd[q] = {offset of the group's
+// terms 1.. in the shared term table, their number, z of term 0, group}; s_h0c[q] = c' of term 0.
+template <int TH>
+__device__ __forceinline__ void rows_heavy_phase(const uint4 *s_hd, const double2 *s_h0c, double2 *s_hv, const uint32_t *s_ez,
+                                                 const double2 *s_ec, uint32_t n_heavy, uint32_t HS, uint32_t hv_log2,
+                                                 uint32_t sbase)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t r = sbase + lane;
+    for (uint32_t q = warp; q < n_heavy; q += TH / 32u) {
+        const uint4 d = s_hd[q];
+        const double2 c0 = s_h0c[q];
+        double hre[4], him[4];
+#pragma unroll
+        for (uint32_t e = 0; e < 4u; e++) {
+            const uint32_t s = (uint32_t)(__popc((r + 32u * e) & d.z) & 1) << 31;
+            hre[e] = flip_sign(c0.x, s); him[e] = flip_sign(c0.y, s);
+        }
+        if (HS > 64u) rows_heavy_fold<4>(s_ez + d.x, s_ec + d.x, d.y, r, hre, him);
+        else if (HS > 32u) rows_heavy_fold<2>(s_ez + d.x, s_ec + d.x, d.y, r, hre, him);
+        else rows_heavy_fold<1>(s_ez + d.x, s_ec + d.x, d.y, r, hre, him);
+#pragma unroll
+        for (uint32_t e = 0; e < 4u; e++)
+            if (lane + 32u * e < HS) s_hv[(q << hv_log2) + lane + 32u * e] = make_double2(hre[e], him[e]);
+    }
+}
+
+// REGT = false: terms 1.. of every group ("extras", n_extra = T - G of them) live in shared memory.
+// REGT = true : a thread keeps up to NT = LANE_TERMS (z, c') of each of its groups in registers (the lanes
+//               kernel's SoA tables, padded with (0, -0.0): x + (-0.0) == x for every x, signed zeros included,
+//               so padding needs no predicate); the term loop runs to the warp's longest light group; groups
+//               with more terms must all be heavy (hv_thr == NT); the shared term table holds the heavy groups'
+//               terms only (n_extra = their number).  For term-rich operators (molecular Hamiltonians: 5-6
+//               terms per group) this removes two thirds of the kernel's shared-memory traffic.
+// HEAVY = false: the plan has no heavy group; the heavy path is compiled out (its 4-rows-per-lane fold costs the
+//               1024-thread instances registers they do not have: C3 6.6 TB/s without, 5.6 with).
+template <int NG, int Q, int TH, bool REGT, bool HEAVY>
 __global__ void __launch_bounds__(TH, 1)
 fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32_t n_runs,
-                 uint32_t hv_thr, uint32_t hv_cap, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
+                 uint32_t hv_thr, uint32_t hv_cap, uint32_t hv_log2, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
                  uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
                  double2 *__restrict__ data, uint64_t indptr_last_row)
 {
     constexpr uint32_t RT = 1u << Q;
     constexpr int NS = Q + 2;                                      // row bits whose slot step lives in a register
+    constexpr int NT = REGT ? LANE_TERMS : 1;                      // terms of a group kept in registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t tile_n = RT * G;                                // entries of one batch
     double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                               // [2][tile_n]
     uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)tile_n * 32u);      // [2][tile_n]
     double2 *s_ec = reinterpret_cast<double2 *>(smem_raw + (size_t)tile_n * 48u);        // [n_extra]
     uint32_t *s_ez = reinterpret_cast<uint32_t *>(s_ec + n_extra);                       // [n_extra]
-    double2 *s_hv = reinterpret_cast<double2 *>(smem_raw + (((size_t)tile_n * 48u + (size_t)n_extra * 20u + 15u) & ~(size_t)15u));   // [hv_cap][32]
-    uint32_t *s_hg = reinterpret_cast<uint32_t *>(s_hv + (size_t)hv_cap * 32u);          // [hv_cap]
-    __shared__ uint32_t s_nheavy;
+    double2 *s_hv = reinterpret_cast<double2 *>(smem_raw + (((size_t)tile_n * 48u + (size_t)n_extra * 20u + 15u) & ~(size_t)15u));   // [hv_cap][2^hv_log2]
+    double2 *s_h0c = s_hv + ((size_t)hv_cap << hv_log2);                                 // [hv_cap]
+    uint4 *s_hd = reinterpret_cast<uint4 *>(s_h0c + hv_cap);                             // [hv_cap]
+    __shared__ uint32_t s_nheavy, s_hterms;
     const uint32_t T = p.n_terms, nq = (uint32_t)p.n_qubits;
     constexpr uint32_t NOT_HEAVY = 0xffffffffu;
-    if (threadIdx.x == 0) s_nheavy = 0;
+    if (threadIdx.x == 0) { s_nheavy = 0; s_hterms = 0; }
     __syncthreads();
 
     // ---- once per CTA: this thread's groups ------------------------------------------------------
-    uint32_t x[NG], z0[NG], eb[NG], ee[NG], off[NG], hidx[NG];
+    uint32_t x[NG], z[NG][NT], eb[NG], ee[NG], off[NG], hidx[NG];
     int32_t sd[NG][NS];
-    double c0r[NG], c0i[NG];
+    double cr[NG][NT], ci[NG][NT];
 #pragma unroll
     for (int k = 0; k < NG; k++) {
         const uint32_t g = threadIdx.x + (uint32_t)k * TH;
         const uint32_t gg = g < G ? g : G - 1u;
         const uint32_t t0 = __ldg(&p.goff[gg]), t1 = __ldg(&p.goff[gg + 1]);
         x[k] = __ldg(&p.gx[gg]);
-        z0[k] = __ldg(&p.tz[t0]);
-        const double2 c = __ldg(&p.tc[t0]);
-        c0r[k] = c.x; c0i[k] = c.y;
-        eb[k] = t0 - gg; ee[k] = t1 - gg - 1u;                     // sorted term t > t0 of group g is extra t - g - 1
-        if (g < G)
-            for (uint32_t t = t0 + 1u; t < t1; t++) { s_ez[t - gg - 1u] = __ldg(&p.tz[t]); s_ec[t - gg - 1u] = __ldg(&p.tc[t]); }
         // heavy groups (more than hv_thr terms: the Z-only group of a molecular Hamiltonian, a few dozen others)
-        // are evaluated lane <-> row for 32 rows at a time by the whole CTA, not inside their owner's lane
+        // are evaluated lane <-> row for a strip of rows at a time by the whole CTA, not inside their owner's lane
         hidx[k] = NOT_HEAVY;
-        if (g < G && t1 - t0 > hv_thr) {
+        if (HEAVY && g < G && t1 - t0 > hv_thr) {
             const uint32_t h = atomicAdd(&s_nheavy, 1u);
-            if (h < hv_cap) { hidx[k] = h; s_hg[h] = g; }
+            if (h < hv_cap) {
+                hidx[k] = h;
+                uint32_t o = t0 - gg;                              // shared-memory variant: its slice of the extras table
+                if constexpr (REGT) {                              // register variant: the table holds heavy groups only
+                    o = atomicAdd(&s_hterms, t1 - t0 - 1u);
+                    for (uint32_t t = t0 + 1u; t < t1; t++) { s_ez[o + t - t0 - 1u] = __ldg(&p.tz[t]); s_ec[o + t - t0 - 1u] = __ldg(&p.tc[t]); }
+                }
+                s_hd[h] = make_uint4(o, t1 - t0 - 1u, __ldg(&p.tz[t0]), g);
+                s_h0c[h] = __ldg(&p.tc[t0]);
+            }
+        }
+        if constexpr (REGT) {
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                z[k][t] = __ldg(&p.lt_z[(uint32_t)t * T + gg]);
+                const double2 c = __ldg(&p.lt_c[(uint32_t)t * T + gg]);
+                cr[k][t] = c.x; ci[k][t] = c.y;
+            }
+            // ee: terms the warp folds for this group slot = its longest light group (warp-uniform)
+            const uint32_t nt = (g < G && hidx[k] == NOT_HEAVY) ? min(t1 - t0, (uint32_t)NT) : 1u;
+            eb[k] = 0; ee[k] = __reduce_max_sync(0xffffffffu, nt);
+        } else {
+            z[k][0] = __ldg(&p.tz[t0]);
+            const double2 c = __ldg(&p.tc[t0]);
+            cr[k][0] = c.x; ci[k][0] = c.y;
+            eb[k] = t0 - gg; ee[k] = t1 - gg - 1u;                 // sorted term t > t0 of group g is extra t - g - 1
+            if (g < G)
+                for (uint32_t t = t0 + 1u; t < t1; t++) { s_ez[t - gg - 1u] = __ldg(&p.tz[t]); s_ec[t - gg - 1u] = __ldg(&p.tc[t]); }
         }
 #pragma unroll
         for (int b = 0; b < NS; b++) {
@@ -700,9 +777,8 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     __syncthreads();
 
     const uint32_t R = 1u << log2R, n_batches = R >> Q;
-    const uint32_t n_heavy = min(s_nheavy, hv_cap);
-    const uint32_t HS = R < 32u ? R : 32u, SB = HS >> Q;           // rows / batches per heavy strip
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_heavy = HEAVY ? min(s_nheavy, hv_cap) : 0u;
+    const uint32_t HS = min(R, 1u << hv_log2), SB = HS >> Q;       // rows / batches per heavy strip
     uint32_t parity = 0;                                           // buffer of the current batch
     for (uint32_t run = blockIdx.x; run < n_runs; run += gridDim.x) {
         const uint64_t r0_64 = tile_row0 + ((uint64_t)run << log2R);   // first row of the run (aligned to R)
@@ -743,24 +819,13 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                     off[k] += (uint32_t)(up ? s : -s);
                 }
             }
-            if (n_heavy != 0u && (i & (SB - 1u)) == 0u) {
+            if (HEAVY && n_heavy != 0u && (i & (SB - 1u)) == 0u) {
                 // the next SB batches stay inside the aligned strip of HS rows that holds rb: every warp takes heavy
-                // groups round-robin, lane <-> row, warp-uniform term loop (extras broadcast from shared memory).
+                // groups round-robin, lane <-> row, warp-uniform term loop (terms broadcast to the warp).
                 // The barrier that ended the previous batch also retired the last reader of s_hv.
-                const uint32_t r = (rb & ~(HS - 1u)) + lane;
-                for (uint32_t q = warp; q < n_heavy; q += TH / 32u) {
-                    const uint32_t g = s_hg[q], t0 = __ldg(&p.goff[g]), t1 = __ldg(&p.goff[g + 1]);
-                    const double2 c0 = __ldg(&p.tc[t0]);
-                    uint32_t s = (uint32_t)(__popc(r & __ldg(&p.tz[t0])) & 1) << 31;
-                    double hre = flip_sign(c0.x, s), him = flip_sign(c0.y, s);
-#pragma unroll 4
-                    for (uint32_t e = t0 - g; e < t1 - g - 1u; e++) {
-                        const double2 c = s_ec[e];
-                        const double sg = pm_one((uint32_t)__popc(r & s_ez[e]));
-                        hre = __fma_rn(sg, c.x, hre); him = __fma_rn(sg, c.y, him);
-                    }
-                    s_hv[q * 32u + lane] = make_double2(hre, him);
-                }
+                // A lane folds rows lane, lane + 32, ... of the strip together: the fold is one dependent chain per
+                // row, so the rows of a lane are what hides the FP64 latency of the longest group.
+                rows_heavy_phase<TH>(s_hd, s_h0c, s_hv, s_ez, s_ec, n_heavy, HS, hv_log2, rb & ~(HS - 1u));
                 __syncthreads();
             }
             double2 *bd = sdat + parity * tile_n;
@@ -769,32 +834,46 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
             for (int k = 0; k < NG; k++) {
                 if (threadIdx.x + (uint32_t)k * TH < G) {
                     double re[RT], im[RT];
-                    if (hidx[k] != NOT_HEAVY) {
+                    if (HEAVY && hidx[k] != NOT_HEAVY) {
 #pragma unroll
                         for (uint32_t j = 0; j < RT; j++) {
-                            const double2 v = s_hv[hidx[k] * 32u + ((rb + j) & (HS - 1u))];
+                            const double2 v = s_hv[(hidx[k] << hv_log2) + ((rb + j) & (HS - 1u))];
                             re[j] = v.x; im[j] = v.y;
                         }
                     } else {
                         // rb has no bits below Q, so popc((rb + j) & z) = popc(rb & z) + popc(j & z): one POPC per term
                         // serves the RT rows; bit 0 of p0 ^ (z >> b) ^ ... is row j's parity
-                        const uint32_t p0 = (uint32_t)__popc(rb & z0[k]);
+                        const uint32_t p0 = (uint32_t)__popc(rb & z[k][0]);
 #pragma unroll
                         for (uint32_t j = 0; j < RT; j++) {
-                            const uint32_t s = rows_parity<Q>(p0, z0[k], j) << 31;
-                            re[j] = flip_sign(c0r[k], s); im[j] = flip_sign(c0i[k], s);
+                            const uint32_t s = rows_parity<Q>(p0, z[k][0], j) << 31;
+                            re[j] = flip_sign(cr[k][0], s); im[j] = flip_sign(ci[k][0], s);
                         }
                         // later terms: fma(+-1.0, c', acc) is the sign flip and the __dadd_rn of the fold in one
                         // instruction per component (the product is exact, signed zeros included)
-#pragma unroll 1
-                        for (uint32_t e = eb[k]; e < ee[k]; e++) {
-                            const uint32_t z = s_ez[e];
-                            const double2 c = s_ec[e];
-                            const uint32_t p = (uint32_t)__popc(rb & z);
+                        if constexpr (REGT) {
 #pragma unroll
-                            for (uint32_t j = 0; j < RT; j++) {
-                                const double sg = pm_one(rows_parity<Q>(p, z, j));
-                                re[j] = __fma_rn(sg, c.x, re[j]); im[j] = __fma_rn(sg, c.y, im[j]);
+                            for (int t = 1; t < NT; t++) {
+                                if ((uint32_t)t < ee[k]) {             // warp-uniform
+                                    const uint32_t pt = (uint32_t)__popc(rb & z[k][t]);
+#pragma unroll
+                                    for (uint32_t j = 0; j < RT; j++) {
+                                        const double sg = pm_one(rows_parity<Q>(pt, z[k][t], j));
+                                        re[j] = __fma_rn(sg, cr[k][t], re[j]); im[j] = __fma_rn(sg, ci[k][t], im[j]);
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll 1
+                            for (uint32_t e = eb[k]; e < ee[k]; e++) {
+                                const uint32_t ze = s_ez[e];
+                                const double2 c = s_ec[e];
+                                const uint32_t pe = (uint32_t)__popc(rb & ze);
+#pragma unroll
+                                for (uint32_t j = 0; j < RT; j++) {
+                                    const double sg = pm_one(rows_parity<Q>(pe, ze, j));
+                                    re[j] = __fma_rn(sg, c.x, re[j]); im[j] = __fma_rn(sg, c.y, im[j]);
+                                }
                             }
                         }
                     }

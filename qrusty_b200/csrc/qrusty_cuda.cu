@@ -93,7 +93,10 @@ struct qr_plan {
     // log2(rows per batch), log2(rows per run); rows_th == 0: not used
     int rows_th = 0, rows_ng = 0, rows_q = 0, rows_log2r = 0;
     uint32_t rows_hv_thr = 0xffffffffu, rows_hv_cap = 0;   // heavy groups: more than hv_thr terms, hv_cap of them
+    int rows_hv_log2 = 5;                                  // log2(rows per heavy strip)
+    int rows_regt = 0;                                     // 1: terms in registers (fill_rows_kernel<.., REGT = true>)
     size_t rows_smem_bytes = 0;
+    uint64_t rows_table_terms = 0;                         // entries of the kernel's shared term table
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -144,33 +147,61 @@ int blocked_strips(const qr_plan *pl)
     return pl->n_terms >= 3 * pl->n_groups ? 2 : 1;
 }
 
-// Rows kernel: eligible when two batches of 2^q whole rows plus the groups' extra terms fit in shared
-// memory and a thread keeps at most ROWS_MAX_NG groups.  QR_FILL_ROWS_TH / _Q / _R override the shape.
-constexpr int ROWS_MAX_NG_1024 = 3, ROWS_MAX_NG_512 = 6;
+// Rows kernel: eligible when two batches of 2^q whole rows (plus, variant (b), the groups' extra terms) fit in
+// shared memory and a thread keeps at most 2 (a) / 3 (b) groups.  QR_FILL_ROWS_REGT / _Q / _R / _HV / _HVS override
+// the variant, the batch, the run length, the heavy threshold and the heavy strip (tests, sweeps).
+constexpr int ROWS_MAX_NG_1024 = 3;
 constexpr uint32_t ROWS_HEAVY_TERMS = 6;                 // groups with more terms than this are "heavy"
-size_t rows_smem(uint64_t G, uint64_t n_extra, int q, uint64_t n_heavy = 0)
+size_t rows_smem(uint64_t G, uint64_t n_extra, int q, uint64_t n_heavy = 0, int hv_log2 = 5)
 {
-    return (size_t)align_up((G << q) * 48 + n_extra * 20, 16) + (size_t)n_heavy * (32 * 16 + 4);
+    return (size_t)align_up((G << q) * 48 + n_extra * 20, 16) + (size_t)n_heavy * ((16ull << hv_log2) + 32);
 }
 
 bool choose_rows(qr_plan *pl)
 {
     const uint64_t G = pl->n_groups, n_extra = pl->n_terms_canonical - G;
-    // 1024 threads (32 warps hide the shared-memory and FP64 latency of the term loops) while a thread's groups fit
-    // its 64 registers: C3 6.63 vs 6.34 TB/s at 512, H8 3.88 vs 3.68 (profiles/r03_rows_sweep.jsonl)
-    int th = G <= 1024 * (uint64_t)ROWS_MAX_NG_1024 ? 1024 : 512, q_forced = 0, r = 0;
-    if (const char *env = getenv("QR_FILL_ROWS_TH")) { int v = atoi(env); if (v == 512 || v == 1024) th = v; }
-    int ng = (int)((G + th - 1) / th);
-    if (th == 1024 && ng > ROWS_MAX_NG_1024) { th = 512; ng = (int)((G + th - 1) / th); }
-    if (ng > (th == 1024 ? ROWS_MAX_NG_1024 : ROWS_MAX_NG_512)) return false;
+    int q_forced = 0, r = 0;
     if ((G << 2) * 16 >= (1ull << 31)) return false;
     if (const char *env = getenv("QR_FILL_ROWS_Q")) { int v = atoi(env); if (v == 1 || v == 2) q_forced = v; }
+    if (const char *env = getenv("QR_FILL_ROWS_R")) { int v = atoi(env); if (v >= 1 && v <= 16) r = v; }
     // group sizes decide which groups leave their owner's lane for the CTA-wide heavy path
     std::vector<uint32_t> goff(G + 1);
     if (cudaMemcpy(goff.data(), pl->dev.goff, (G + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; }
     uint32_t thr0 = ROWS_HEAVY_TERMS;
     if (const char *env = getenv("QR_FILL_ROWS_HV")) { int v = atoi(env); thr0 = v <= 0 ? 0xffffffffu : (uint32_t)v; }
     auto heavy_count = [&](uint32_t thr) { uint64_t n = 0; for (uint64_t g = 0; g < G; g++) n += goff[g + 1] - goff[g] > thr; return n; };
+    auto strip_log2 = [&](uint64_t extra, int q, uint64_t nh) {
+        // strips of 128 / 64 rows (4 / 2 rows per lane in the heavy fold) when the side buffer still fits
+        int hl = 5;
+        while (hl < 7 && nh != 0 && rows_smem(G, extra, q, nh, hl + 1) <= MAX_SMEM) hl++;
+        if (const char *env = getenv("QR_FILL_ROWS_HVS")) { int v = atoi(env); if (v >= 5 && v <= 7 && rows_smem(G, extra, q, nh, v) <= MAX_SMEM) hl = v; }
+        return hl;
+    };
+
+    // (a) terms in registers: 512 threads x <= 2 groups x <= 6 terms; every longer group must fit the heavy path.
+    //     Chosen for term-rich operators (molecular Hamiltonians, 5-6 terms per group), where the extras table of
+    //     variant (b) makes shared memory the busiest unit (ncu: l1tex 59 %, issue 44 %, H12).
+    int regt = (G <= 1024 && n_extra >= G && thr0 == (uint32_t)qr::LANE_TERMS) ? 1 : 0;
+    if (const char *env = getenv("QR_FILL_ROWS_REGT")) regt = (env[0] == '1' && G <= 1024 && thr0 == (uint32_t)qr::LANE_TERMS) ? 1 : 0;
+    if (regt) {
+        const uint64_t nh = heavy_count(thr0);
+        uint64_t hx = 0;                                           // terms 1.. of the heavy groups: the shared term table
+        for (uint64_t g = 0; g < G; g++) if (goff[g + 1] - goff[g] > thr0) hx += goff[g + 1] - goff[g] - 1;
+        for (int q = q_forced ? q_forced : 2; q >= (q_forced ? q_forced : 1); q--) {
+            if (rows_smem(G, hx, q, nh) > MAX_SMEM) continue;
+            const int hl = strip_log2(hx, q, nh);
+            pl->rows_th = 512; pl->rows_ng = (int)((G + 511) / 512); pl->rows_q = q; pl->rows_log2r = r ? std::max(r, q) : 0;
+            pl->rows_hv_thr = thr0; pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = hl; pl->rows_regt = 1;
+            pl->rows_smem_bytes = rows_smem(G, hx, q, nh, hl); pl->rows_table_terms = hx;
+            return true;
+        }
+    }
+
+    // (b) first term in registers, the others in shared memory.  1024 threads (32 warps hide the shared-memory and
+    //     FP64 latency of the term loops), up to 3 groups per thread in its 64 registers: C3 6.63 TB/s against 6.34
+    //     with 512 threads (profiles/r03_rows_sweep.jsonl)
+    const int th = 1024, ng = (int)((G + th - 1) / th);
+    if (ng > ROWS_MAX_NG_1024) return false;
     for (int q = q_forced ? q_forced : 2; q >= (q_forced ? q_forced : 1); q--) {
         if (rows_smem(G, n_extra, q) > MAX_SMEM) continue;
         uint32_t thr = thr0;
@@ -183,10 +214,10 @@ bool choose_rows(qr_plan *pl)
             nh = thr == 0xffffffffu ? 0 : heavy_count(thr);
         }
         if (rows_smem(G, n_extra, q, nh) > MAX_SMEM) continue;
-        if (const char *env = getenv("QR_FILL_ROWS_R")) { int v = atoi(env); if (v >= q && v <= 16) r = v; }
+        const int hl = strip_log2(n_extra, q, nh);
         pl->rows_th = th; pl->rows_ng = ng; pl->rows_q = q; pl->rows_log2r = r ? std::max(r, q) : 0;   // 0: per window
-        pl->rows_hv_thr = nh ? thr : 0xffffffffu; pl->rows_hv_cap = (uint32_t)nh;
-        pl->rows_smem_bytes = rows_smem(G, n_extra, q, nh);
+        pl->rows_hv_thr = nh ? thr : 0xffffffffu; pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = hl; pl->rows_regt = 0;
+        pl->rows_smem_bytes = rows_smem(G, n_extra, q, nh, hl); pl->rows_table_terms = n_extra;
         return true;
     }
     return false;
@@ -455,15 +486,19 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         // the bulk copies need 16-byte aligned global addresses: indices + (s0 - row_lo) * G * 8
         const bool aligned = (((s0 - row_lo) * G) & 1) == 0;
         if (s1 > s0 && aligned && (s1 - s0) / R <= 0xffffffffull) {
-            const uint64_t n_runs = (s1 - s0) / R, n_extra = pl->n_terms_canonical - G;
+            const uint64_t n_runs = (s1 - s0) / R, n_extra = pl->rows_table_terms;
             const size_t smem = pl->rows_smem_bytes;
-            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t,
-                                    uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
+            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t,
+                                    uint64_t, uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
             RowsFn kern = nullptr;
-#define QR_ROWS_CASE(NG_, TH_) \
-            if (pl->rows_ng == NG_ && pl->rows_th == TH_) kern = q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_>;
-            QR_ROWS_CASE(1, 1024) QR_ROWS_CASE(2, 1024) QR_ROWS_CASE(3, 1024)
-            QR_ROWS_CASE(1, 512) QR_ROWS_CASE(2, 512) QR_ROWS_CASE(3, 512) QR_ROWS_CASE(4, 512) QR_ROWS_CASE(5, 512) QR_ROWS_CASE(6, 512)
+#define QR_ROWS_Q(NG_, TH_, RG_, HV_) \
+            (q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_, RG_, HV_> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_, RG_, HV_>)
+#define QR_ROWS_CASE(NG_, TH_, RG_) \
+            if (pl->rows_ng == NG_ && pl->rows_th == TH_ && pl->rows_regt == (RG_ ? 1 : 0)) \
+                kern = pl->rows_hv_cap ? QR_ROWS_Q(NG_, TH_, RG_, true) : QR_ROWS_Q(NG_, TH_, RG_, false);
+            QR_ROWS_CASE(1, 1024, false) QR_ROWS_CASE(2, 1024, false) QR_ROWS_CASE(3, 1024, false)
+            QR_ROWS_CASE(1, 512, true) QR_ROWS_CASE(2, 512, true)
+#undef QR_ROWS_Q
 #undef QR_ROWS_CASE
             if (!kern) return fail(QR_ERR_UNSUPPORTED, "fill_rows: no kernel instance for this plan");
             QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -475,7 +510,7 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
             kern<<<(unsigned)ctas, pl->rows_th, smem, st>>>(pl->dev, (uint32_t)G, (uint32_t)n_extra, (uint32_t)k, (uint32_t)n_runs,
-                                                           pl->rows_hv_thr, pl->rows_hv_cap, s0, row_lo, indptr_base, d_indptr,
+                                                           pl->rows_hv_thr, pl->rows_hv_cap, (uint32_t)pl->rows_hv_log2, s0, row_lo, indptr_base, d_indptr,
                                                            d_indices, d_data, row_hi - row_lo);
             QR_LAUNCH_CHECK("fill_rows_kernel");
             return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);

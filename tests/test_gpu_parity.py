@@ -253,18 +253,20 @@ def test_lanes_kernel_clusters(monkeypatch, W):
         assert np.array_equal(ix, ref[1][lo * 1100:hi * 1100]) and np.array_equal(u64(dt), u64(ref[2][lo * 1100:hi * 1100]))
 
 
-@pytest.mark.parametrize("TH,Q,R", [(512, 1, 1), (512, 2, 5), (1024, 1, 7), (1024, 2, 3), (512, 1, 4), (1024, 2, 8)])
+@pytest.mark.parametrize("REGT,Q,R", [(1, 1, 1), (1, 2, 5), (0, 1, 7), (0, 2, 3), (1, 1, 4), (0, 2, 8), (1, 1, 6), (1, 2, 7), (0, 1, 5)])
 @pytest.mark.parametrize("HV", [None, "0", "2"])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
-def test_rows_kernel(fixtures, monkeypatch, name, TH, Q, R, HV):
+def test_rows_kernel(fixtures, monkeypatch, name, REGT, Q, R, HV):
     """Rows kernel (fill_rows_kernel: persistent CTAs own whole rows, thread <-> group, batches of 2^Q rows
     in Gray-code order through two shared-memory buffers and the TMA) forced on every case: whole matrix
     and ragged windows (edge rows go through the direct kernel, misaligned windows through the default path).
-    HV: threshold of the CTA-wide heavy-group path (default: more than 6 terms; "0": off; "2": nearly every group)."""
+    REGT: 1 = up to 6 terms of a group in registers (512 threads), 0 = first term in registers, the others in shared
+    memory (1024 threads).  HV: threshold of the CTA-wide heavy-group path (default: more than 6 terms; "0": off;
+    "2": nearly every group is heavy; both force the shared-memory variant)."""
     monkeypatch.setenv("QR_FILL_ROWS", "1")
     if HV is not None:
         monkeypatch.setenv("QR_FILL_ROWS_HV", HV)
-    monkeypatch.setenv("QR_FILL_ROWS_TH", str(TH))
+    monkeypatch.setenv("QR_FILL_ROWS_REGT", str(REGT))
     monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
     monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
     labels, coeffs = SMALL[name](fixtures)
@@ -273,7 +275,7 @@ def test_rows_kernel(fixtures, monkeypatch, name, TH, Q, R, HV):
     plan = make_op(labels, coeffs).plan()
     assert plan.fill_kernel == "fill_rows_kernel"
     G, dim = plan.n_groups, 1 << n
-    assert_same(device_build(plan, 0, dim), ref, f"{name} TH={TH} Q={Q} R={R}")
+    assert_same(device_build(plan, 0, dim), ref, f"{name} REGT={REGT} Q={Q} R={R} HV={HV}")
     if dim >= 128:
         for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 33), (6, dim - 2)]:
             ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
@@ -281,23 +283,24 @@ def test_rows_kernel(fixtures, monkeypatch, name, TH, Q, R, HV):
             assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
 
 
-@pytest.mark.parametrize("G,T,TH,Q", [(1100, 1500, 1024, 1), (1100, 1500, 1024, 2), (1100, 1500, 512, 1), (2200, 2600, 1024, 1),
-                                      (2200, 2600, 512, 1), (600, 2400, 512, 2), (450, 500, 0, 0)])
-def test_rows_kernel_large_G(monkeypatch, G, T, TH, Q):
-    """The shapes the rows kernel is chosen for by default (G >= 400): 2..5 groups per thread, extras in
-    shared memory (T - G of them, up to 4 per group on average), 2- and 4-row batches, runs of 8 and 128 rows,
-    several runs per persistent CTA (a 2^12-row matrix on 148 CTAs has 512 runs of 8 rows)."""
+@pytest.mark.parametrize("G,T,REGT,Q", [(1100, 1500, 0, 1), (1100, 1500, 0, 2), (2200, 2600, 0, 1), (600, 2400, 0, 2), (600, 2400, 1, 2),
+                                        (1000, 3000, 1, 1), (1000, 3000, 0, 1), (450, 500, None, 0), (700, 3000, None, 0)])
+def test_rows_kernel_large_G(monkeypatch, G, T, REGT, Q):
+    """The shapes the rows kernel is chosen for by default (G >= 400): 1..3 groups per thread, terms in registers
+    or in shared memory (T - G extras, up to 4 per group on average, so some groups are heavy), 2- and 4-row
+    batches, runs of 8 and 128 rows, several runs per persistent CTA (a 2^12-row matrix on 148 CTAs has 512 runs
+    of 8 rows).  REGT None: the library's own choice (registers for the term-rich case)."""
     labels, coeffs = H.random_pauli_sum(12, T, G, 50, 5)
     n, params = O.make_params(labels, coeffs)
     ref = O.build_csr(params, n)
-    if TH:
-        monkeypatch.setenv("QR_FILL_ROWS_TH", str(TH))
+    if REGT is not None:
+        monkeypatch.setenv("QR_FILL_ROWS_REGT", str(REGT))
         monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
     for R in (3, 7):
         monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
         plan = make_op(labels, coeffs).plan()
         assert plan.n_groups == G and plan.fill_kernel == "fill_rows_kernel"
-        assert_same(device_build(plan, 0, 1 << n), ref, f"G={G} TH={TH} Q={Q} R={R}")
+        assert_same(device_build(plan, 0, 1 << n), ref, f"G={G} REGT={REGT} Q={Q} R={R}")
         lo, hi = 100, 4000
         ip, ix, dt = device_build(plan, lo, hi)
         assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G]))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Times the fill kernel (events on the launching stream) for one workload under several
 (RW,GW) tile configurations, the direct kernel, and a row window size.  GPU box only.
-  python tools/fill_sweep.py C2 | C4 | C3 | xxz<n> | H8 ...   [--rows LOG2] [--cfgs "2,4 1,8 direct lanes:8:8 blocked:32:1 rows:1024:1:7"]
+  python tools/fill_sweep.py C2 | C4 | C3 | xxz<n> | H8 ...   [--rows LOG2] [--cfgs "2,4 1,8 direct lanes:8:8 blocked:32:1 rows:1:1:7"]
 """
 import argparse, ctypes as C, gzip, json, os, sys
 from pathlib import Path
@@ -19,6 +19,9 @@ def get_workload(name):
         return H.CONFIGS[name][1]()
     if name.startswith("xxz"):
         return H.xxz_chain(int(name[3:]), 1.0, 0.7)
+    if name.startswith("rand:"):                      # rand:<n>:<T>:<G>  (C3's generator at another shape)
+        n, T, G = (int(v) for v in name.split(":")[1:4])
+        return H.random_pauli_sum(n, T, G, min(100, (T - G) // 2), 24)
     fx = json.load(gzip.open(ROOT / "tests/golden/h_fixtures.json.gz"))
     return fx[name]["labels"], [complex(a, b) for a, b in fx[name]["coeffs"]]
 
@@ -40,18 +43,16 @@ def main():
     for cfg in a.cfgs.split():
         flags = 0
         for k in ("QR_FILL_CFG", "QR_FILL_LANES", "QR_FILL_LANES_R", "QR_FILL_LANES_W", "QR_FILL_LANES_SYNC",
-                  "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E", "QR_FILL_ROWS", "QR_FILL_ROWS_TH",
+                  "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E", "QR_FILL_ROWS", "QR_FILL_ROWS_REGT", "QR_FILL_ROWS_HVS",
                   "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R", "QR_FILL_ROWS_HV"):      # the ones a cfg string sets
             os.environ.pop(k, None)
         if cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
-        elif cfg.startswith("rows"):                  # rows[:threads[:log2(rows per batch)[:log2(rows per run)[:heavy threshold]]]]
+        elif cfg.startswith("rows"):                  # rows[:regt 0|1[:log2(rows per batch)[:log2(rows per run)[:heavy threshold[:log2 heavy strip]]]]], "" = default
             parts = cfg.split(":")
             os.environ["QR_FILL_ROWS"] = "1"
-            if len(parts) > 1: os.environ["QR_FILL_ROWS_TH"] = parts[1]
-            if len(parts) > 2: os.environ["QR_FILL_ROWS_Q"] = parts[2]
-            if len(parts) > 3: os.environ["QR_FILL_ROWS_R"] = parts[3]
-            if len(parts) > 4: os.environ["QR_FILL_ROWS_HV"] = parts[4]
+            for i, key in enumerate(("QR_FILL_ROWS_REGT", "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R", "QR_FILL_ROWS_HV", "QR_FILL_ROWS_HVS")):
+                if len(parts) > i + 1 and parts[i + 1] != "": os.environ[key] = parts[i + 1]
         elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:sync[:persist]]]]
             parts = cfg.split(":")
             os.environ["QR_FILL_LANES"] = "1"
