@@ -427,6 +427,23 @@ def run_b200(args, rank, local_rank, world):
                              "achieved_GBps": cbytes / ms / 1e6, "frac_of_peak": cbytes / ms / 1e6 / peak}
         del c_ip, c_ix, c_dt, cplan
 
+        # (1b) a molecular Hamiltonian from the reference's own fixtures (H12: 24 qubits, T = 4497, G = 811, 5.5 terms
+        #      per group, one group of 301 terms), 2^18-row window: the term-rich side of the large-G path
+        fx_path = Path(__file__).resolve().parent / "tests" / "golden" / "h_fixtures.json.gz"
+        if fx_path.exists():
+            import gzip
+            fx = json.load(gzip.open(fx_path))["H12"]
+            mplan = Q.SparsePauliOp([Q.Pauli(l) for l in fx["labels"]], [complex(a, b) for a, b in fx["coeffs"]]).plan(device)
+            mrow, mG = 1 << 18, mplan.n_groups
+            m_ip, m_ix, m_dt = DeviceBuffer((mrow + 1) * 8, device), DeviceBuffer(mrow * mG * 8, device), DeviceBuffer(mrow * mG * 16, device)
+            mlo = mplan.dim // 2
+            ms = timed(lambda: call("qr_build_rows_device", mplan.handle, mlo, mlo + mrow, m_ip.ptr, m_ix.ptr, m_dt.ptr, 0, stream), 5)
+            mbytes = mrow * mG * 24 + (mrow + 1) * 8
+            extras["molecular"] = {"workload": "H12 fixture (qrusty H_fixtures.py), rows [2^23, 2^23 + 2^18)", "n_terms": mplan.n_terms,
+                                   "n_groups": mG, "kernel": mplan.fill_kernel, "ms": ms, "nnz_per_s": mrow * mG / ms * 1e3,
+                                   "achieved_GBps": mbytes / ms / 1e6, "frac_of_peak": mbytes / ms / 1e6 / peak}
+            del m_ip, m_ix, m_dt, mplan
+
         # (2) fused drop-zeros build of the bench operator: count_rows + scan + fill_compact
         kept = C.c_uint64()
         z_ip = DeviceBuffer((rows + 1) * 8, device)

@@ -621,6 +621,10 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
 // handed to the TMA as two bulk copies (RT*G*16 B of data, RT*G*8 B of column ids) while the
 // CTA fills the other buffer.  One barrier per batch.
 //
+// Small G (one group per thread, G <= TH / 2): the CTA's threads split into 2^sl sub-batches of TH >> sl
+// threads, sub-batch s taking rows s*RT .. s*RT + RT - 1 of a batch of RT << sl rows, so that all threads
+// work and a batch stays tens of KB however short the rows are.
+//
 // Groups with more than hv_thr terms ("heavy": the Z-only group of a molecular Hamiltonian and a
 // few dozen others) would make their owner's warp the critical path of every batch.  They are
 // evaluated by the whole CTA instead, lane <-> row, for an aligned strip of 2^hv_log2 = 32..128
@@ -700,7 +704,7 @@ __device__ __forceinline__ void rows_heavy_phase(const uint4 *s_hd, const double
 //               1024-thread instances registers they do not have: C3 6.6 TB/s without, 5.6 with).
 template <int NG, int Q, int TH, bool REGT, bool HEAVY>
 __global__ void __launch_bounds__(TH, 1)
-fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32_t n_runs,
+fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32_t sl, uint32_t n_runs,
                  uint32_t hv_thr, uint32_t hv_cap, uint32_t hv_log2, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
                  uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
                  double2 *__restrict__ data, uint64_t indptr_last_row)
@@ -709,7 +713,10 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     constexpr int NS = Q + 2;                                      // row bits whose slot step lives in a register
     constexpr int NT = REGT ? LANE_TERMS : 1;                      // terms of a group kept in registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t tile_n = RT * G;                                // entries of one batch
+    const uint32_t QB = (uint32_t)Q + sl;                          // log2(rows per batch): 2^sl sub-batches of RT rows
+    const uint32_t tile_n = (RT << sl) * G;                        // entries of one batch
+    const uint32_t GP = (uint32_t)TH >> sl;                        // threads per sub-batch (>= G when sl > 0; host-checked)
+    const uint32_t tg = threadIdx.x & (GP - 1u), sub = threadIdx.x / GP;   // this thread's group slot and sub-batch
     double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                               // [2][tile_n]
     uint64_t *sidx = reinterpret_cast<uint64_t *>(smem_raw + (size_t)tile_n * 32u);      // [2][tile_n]
     double2 *s_ec = reinterpret_cast<double2 *>(smem_raw + (size_t)tile_n * 48u);        // [n_extra]
@@ -729,14 +736,14 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     double cr[NG][NT], ci[NG][NT];
 #pragma unroll
     for (int k = 0; k < NG; k++) {
-        const uint32_t g = threadIdx.x + (uint32_t)k * TH;
+        const uint32_t g = tg + (uint32_t)k * GP;
         const uint32_t gg = g < G ? g : G - 1u;
         const uint32_t t0 = __ldg(&p.goff[gg]), t1 = __ldg(&p.goff[gg + 1]);
         x[k] = __ldg(&p.gx[gg]);
         // heavy groups (more than hv_thr terms: the Z-only group of a molecular Hamiltonian, a few dozen others)
         // are evaluated lane <-> row for a strip of rows at a time by the whole CTA, not inside their owner's lane
         hidx[k] = NOT_HEAVY;
-        if (HEAVY && g < G && t1 - t0 > hv_thr) {
+        if (HEAVY && g < G && sub == 0u && t1 - t0 > hv_thr) {
             const uint32_t h = atomicAdd(&s_nheavy, 1u);
             if (h < hv_cap) {
                 hidx[k] = h;
@@ -757,7 +764,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                 cr[k][t] = c.x; ci[k][t] = c.y;
             }
             // ee: terms the warp folds for this group slot = its longest light group (warp-uniform)
-            const uint32_t nt = (g < G && hidx[k] == NOT_HEAVY) ? min(t1 - t0, (uint32_t)NT) : 1u;
+            const uint32_t nt = (g < G && !(HEAVY && t1 - t0 > hv_thr)) ? min(t1 - t0, (uint32_t)NT) : 1u;
             eb[k] = 0; ee[k] = __reduce_max_sync(0xffffffffu, nt);
         } else {
             z[k][0] = __ldg(&p.tz[t0]);
@@ -768,17 +775,28 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                 for (uint32_t t = t0 + 1u; t < t1; t++) { s_ez[t - gg - 1u] = __ldg(&p.tz[t]); s_ec[t - gg - 1u] = __ldg(&p.tc[t]); }
         }
 #pragma unroll
-        for (int b = 0; b < NS; b++) {
-            const int32_t cb = (int32_t)__ldg(&p.cnt_t[(uint32_t)b * T + gg]);
-            sd[k][b] = ((x[k] >> b) & 1u) ? -cb : cb;
+        for (int b = 0; b < NS; b++) {                             // bits 0..Q-1 (rows of the thread), then QB and QB + 1
+            const uint32_t bit = b < Q ? (uint32_t)b : QB + (uint32_t)(b - Q);
+            const int32_t cb = (int32_t)__ldg(&p.cnt_t[bit * T + gg]);
+            sd[k][b] = ((x[k] >> bit) & 1u) ? -cb : cb;
         }
         off[k] = 0;
     }
     __syncthreads();
 
-    const uint32_t R = 1u << log2R, n_batches = R >> Q;
+    if (HEAVY && sl != 0u) {
+        // sub-batches > 0 own the same groups as sub-batch 0: look the heavy index up in the descriptor table
+        const uint32_t nh = min(s_nheavy, hv_cap);
+#pragma unroll
+        for (int k = 0; k < NG; k++)
+            if (sub != 0u) {
+                hidx[k] = NOT_HEAVY;
+                for (uint32_t h = 0; h < nh; h++) if (s_hd[h].w == tg + (uint32_t)k * GP) hidx[k] = h;
+            }
+    }
+    const uint32_t R = 1u << log2R, n_batches = R >> QB;
     const uint32_t n_heavy = HEAVY ? min(s_nheavy, hv_cap) : 0u;
-    const uint32_t HS = min(R, 1u << hv_log2), SB = HS >> Q;       // rows / batches per heavy strip
+    const uint32_t HS = min(R, 1u << hv_log2), SB = HS >> QB;      // rows / batches per heavy strip (HS >= 2^QB; host-checked)
     uint32_t parity = 0;                                           // buffer of the current batch
     for (uint32_t run = blockIdx.x; run < n_runs; run += gridDim.x) {
         const uint64_t r0_64 = tile_row0 + ((uint64_t)run << log2R);   // first row of the run (aligned to R)
@@ -789,10 +807,10 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                 indptr[lr] = indptr_base + lr * G;
                 if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
             }
-        // slot of every group in the run's first row
+        // slot of every group in the first row this thread handles in the run's first batch
 #pragma unroll
         for (int k = 0; k < NG; k++) {
-            const uint32_t g = threadIdx.x + (uint32_t)k * TH, gg = g < G ? g : G - 1u, xr = x[k] ^ r0;
+            const uint32_t g = tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u, xr = x[k] ^ (r0 + (sub << Q));   // the thread's first row
             uint32_t o = 0;
             for (uint32_t b = 0; b < nq; b++) {
                 const uint32_t cb = __ldg(&p.cnt_t[b * T + gg]);
@@ -800,19 +818,19 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
             }
             off[k] = o;
         }
-        uint32_t rb = r0;                                          // first row of the batch (bits < Q are 0)
+        uint32_t rb = r0;                                          // first row of the batch (bits < QB are 0)
         for (uint32_t i = 0; i < n_batches; i++) {
-            if (i != 0u) {                                         // Gray code over batches: step i flips row bit Q + ctz(i)
-                const uint32_t b = (uint32_t)Q + (uint32_t)__ffs((int)i) - 1u;
+            if (i != 0u) {                                         // Gray code over batches: step i flips row bit QB + ctz(i)
+                const uint32_t b = QB + (uint32_t)__ffs((int)i) - 1u;
                 rb ^= 1u << b;
                 const bool up = (rb >> b) & 1u;                    // CTA-uniform
 #pragma unroll
                 for (int k = 0; k < NG; k++) {
                     int32_t s;
-                    if (b == (uint32_t)Q) s = sd[k][Q];
-                    else if (b == (uint32_t)Q + 1u) s = sd[k][Q + 1];
+                    if (b == QB) s = sd[k][Q];
+                    else if (b == QB + 1u) s = sd[k][Q + 1];
                     else {
-                        const uint32_t g = threadIdx.x + (uint32_t)k * TH, gg = g < G ? g : G - 1u;
+                        const uint32_t g = tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u;
                         const int32_t cb = (int32_t)__ldg(&p.cnt_t[b * T + gg]);
                         s = ((x[k] >> b) & 1u) ? -cb : cb;
                     }
@@ -830,20 +848,21 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
             }
             double2 *bd = sdat + parity * tile_n;
             uint64_t *bi = sidx + parity * tile_n;
+            const uint32_t rt = rb + (sub << Q);                   // first of this thread's RT rows (bits < Q are 0)
 #pragma unroll
             for (int k = 0; k < NG; k++) {
-                if (threadIdx.x + (uint32_t)k * TH < G) {
+                if (tg + (uint32_t)k * GP < G) {
                     double re[RT], im[RT];
                     if (HEAVY && hidx[k] != NOT_HEAVY) {
 #pragma unroll
                         for (uint32_t j = 0; j < RT; j++) {
-                            const double2 v = s_hv[(hidx[k] << hv_log2) + ((rb + j) & (HS - 1u))];
+                            const double2 v = s_hv[(hidx[k] << hv_log2) + ((rt + j) & (HS - 1u))];
                             re[j] = v.x; im[j] = v.y;
                         }
                     } else {
-                        // rb has no bits below Q, so popc((rb + j) & z) = popc(rb & z) + popc(j & z): one POPC per term
+                        // rt has no bits below Q, so popc((rt + j) & z) = popc(rt & z) + popc(j & z): one POPC per term
                         // serves the RT rows; bit 0 of p0 ^ (z >> b) ^ ... is row j's parity
-                        const uint32_t p0 = (uint32_t)__popc(rb & z[k][0]);
+                        const uint32_t p0 = (uint32_t)__popc(rt & z[k][0]);
 #pragma unroll
                         for (uint32_t j = 0; j < RT; j++) {
                             const uint32_t s = rows_parity<Q>(p0, z[k][0], j) << 31;
@@ -855,7 +874,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
 #pragma unroll
                             for (int t = 1; t < NT; t++) {
                                 if ((uint32_t)t < ee[k]) {             // warp-uniform
-                                    const uint32_t pt = (uint32_t)__popc(rb & z[k][t]);
+                                    const uint32_t pt = (uint32_t)__popc(rt & z[k][t]);
 #pragma unroll
                                     for (uint32_t j = 0; j < RT; j++) {
                                         const double sg = pm_one(rows_parity<Q>(pt, z[k][t], j));
@@ -868,7 +887,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                             for (uint32_t e = eb[k]; e < ee[k]; e++) {
                                 const uint32_t ze = s_ez[e];
                                 const double2 c = s_ec[e];
-                                const uint32_t pe = (uint32_t)__popc(rb & ze);
+                                const uint32_t pe = (uint32_t)__popc(rt & ze);
 #pragma unroll
                                 for (uint32_t j = 0; j < RT; j++) {
                                     const double sg = pm_one(rows_parity<Q>(pe, ze, j));
@@ -879,11 +898,11 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                     }
 #pragma unroll
                     for (uint32_t j = 0; j < RT; j++) {
-                        uint32_t o = j * G + off[k];
+                        uint32_t o = ((sub << Q) + j) * G + off[k];
 #pragma unroll
                         for (int b = 0; b < Q; b++) if ((j >> b) & 1u) o += (uint32_t)sd[k][b];
                         bd[o] = make_double2(re[j], im[j]);
-                        bi[o] = (uint64_t)((rb + j) ^ x[k]);
+                        bi[o] = (uint64_t)((rt + j) ^ x[k]);
                     }
                 }
             }

@@ -95,6 +95,7 @@ struct qr_plan {
     uint32_t rows_hv_thr = 0xffffffffu, rows_hv_cap = 0;   // heavy groups: more than hv_thr terms, hv_cap of them
     int rows_hv_log2 = 5;                                  // log2(rows per heavy strip)
     int rows_regt = 0;                                     // 1: terms in registers (fill_rows_kernel<.., REGT = true>)
+    int rows_sl = 0;                                       // log2(sub-batches): a batch holds 2^(rows_q + rows_sl) rows
     size_t rows_smem_bytes = 0;
     uint64_t rows_table_terms = 0;                         // entries of the kernel's shared term table
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
@@ -162,7 +163,7 @@ bool choose_rows(qr_plan *pl)
     const uint64_t G = pl->n_groups, n_extra = pl->n_terms_canonical - G;
     int q_forced = 0, r = 0;
     if ((G << 2) * 16 >= (1ull << 31)) return false;
-    if (const char *env = getenv("QR_FILL_ROWS_Q")) { int v = atoi(env); if (v == 1 || v == 2) q_forced = v; }
+    if (const char *env = getenv("QR_FILL_ROWS_Q")) { int v = atoi(env); if (v >= 1 && v <= 3) q_forced = v; }
     if (const char *env = getenv("QR_FILL_ROWS_R")) { int v = atoi(env); if (v >= 1 && v <= 16) r = v; }
     // group sizes decide which groups leave their owner's lane for the CTA-wide heavy path
     std::vector<uint32_t> goff(G + 1);
@@ -181,20 +182,35 @@ bool choose_rows(qr_plan *pl)
     // (a) terms in registers: 512 threads x <= 2 groups x <= 6 terms; every longer group must fit the heavy path.
     //     Chosen for term-rich operators (molecular Hamiltonians, 5-6 terms per group), where the extras table of
     //     variant (b) makes shared memory the busiest unit (ncu: l1tex 59 %, issue 44 %, H12).
-    int regt = (G <= 1024 && n_extra >= G && thr0 == (uint32_t)qr::LANE_TERMS) ? 1 : 0;
+    //     Also for every G <= 512 (one group per thread): measured 6.67 vs 5.52 TB/s at G = 300, equal at G = 400;
+    //     at G = 1000 with 1.3 terms per group variant (b) is ahead, 6.36 vs 6.20 (profiles/r03_rows_sweep.jsonl).
+    int regt = ((G <= 512 || (G <= 1024 && n_extra >= G)) && thr0 == (uint32_t)qr::LANE_TERMS) ? 1 : 0;
     if (const char *env = getenv("QR_FILL_ROWS_REGT")) regt = (env[0] == '1' && G <= 1024 && thr0 == (uint32_t)qr::LANE_TERMS) ? 1 : 0;
     if (regt) {
         const uint64_t nh = heavy_count(thr0);
         uint64_t hx = 0;                                           // terms 1.. of the heavy groups: the shared term table
         for (uint64_t g = 0; g < G; g++) if (goff[g + 1] - goff[g] > thr0) hx += goff[g + 1] - goff[g] - 1;
-        for (int q = q_forced ? q_forced : 2; q >= (q_forced ? q_forced : 1); q--) {
-            if (rows_smem(G, hx, q, nh) > MAX_SMEM) continue;
-            const int hl = strip_log2(hx, q, nh);
-            pl->rows_th = 512; pl->rows_ng = (int)((G + 511) / 512); pl->rows_q = q; pl->rows_log2r = r ? std::max(r, q) : 0;
-            pl->rows_hv_thr = thr0; pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = hl; pl->rows_regt = 1;
-            pl->rows_smem_bytes = rows_smem(G, hx, q, nh, hl); pl->rows_table_terms = hx;
-            return true;
-        }
+        // 8-row batches (one group per thread only) pay while a 4-row batch is small: G = 160 / 200: 6.7 TB/s against
+        // 5.3 / 5.7; G = 300: 6.3 against 6.7; equal from 400 up
+        const int q_hi = (G <= 256 || (q_forced == 3 && G <= 512)) ? 3 : 2;
+        if (q_forced > q_hi) q_forced = q_hi;
+        // small G: 2^sl sub-batches of 512 >> sl >= G threads each, so that every thread has a group (G = 64: 8 sub-
+        // batches of 8 rows = 64-row batches of 98 KB)
+        int sl_hi = 0;
+        while (sl_hi < 4 && (512u >> (sl_hi + 1)) >= G) sl_hi++;
+        if (const char *env = getenv("QR_FILL_ROWS_SL")) { int v = atoi(env); if (v >= 0 && v <= sl_hi) sl_hi = v; }
+        for (int sl = sl_hi; sl >= 0; sl--)
+            for (int q = q_forced ? q_forced : q_hi; q >= (q_forced ? q_forced : 1); q--) {
+                const int qb = q + sl;
+                if (rows_smem(G, hx, qb, nh) > MAX_SMEM) continue;
+                int hl = std::max(strip_log2(hx, qb, nh), qb);             // a heavy strip holds whole batches
+                if (hl > 7 || rows_smem(G, hx, qb, nh, hl) > MAX_SMEM) continue;
+                pl->rows_th = 512; pl->rows_ng = (int)((G + 511) / 512); pl->rows_q = q; pl->rows_sl = sl;
+                pl->rows_log2r = r ? std::max(r, qb) : 0;
+                pl->rows_hv_thr = thr0; pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = hl; pl->rows_regt = 1;
+                pl->rows_smem_bytes = rows_smem(G, hx, qb, nh, hl); pl->rows_table_terms = hx;
+                return true;
+            }
     }
 
     // (b) first term in registers, the others in shared memory.  1024 threads (32 warps hide the shared-memory and
@@ -202,6 +218,7 @@ bool choose_rows(qr_plan *pl)
     //     with 512 threads (profiles/r03_rows_sweep.jsonl)
     const int th = 1024, ng = (int)((G + th - 1) / th);
     if (ng > ROWS_MAX_NG_1024) return false;
+    if (q_forced > 2) q_forced = 2;
     for (int q = q_forced ? q_forced : 2; q >= (q_forced ? q_forced : 1); q--) {
         if (rows_smem(G, n_extra, q) > MAX_SMEM) continue;
         uint32_t thr = thr0;
@@ -215,7 +232,7 @@ bool choose_rows(qr_plan *pl)
         }
         if (rows_smem(G, n_extra, q, nh) > MAX_SMEM) continue;
         const int hl = strip_log2(n_extra, q, nh);
-        pl->rows_th = th; pl->rows_ng = ng; pl->rows_q = q; pl->rows_log2r = r ? std::max(r, q) : 0;   // 0: per window
+        pl->rows_th = th; pl->rows_ng = ng; pl->rows_q = q; pl->rows_sl = 0; pl->rows_log2r = r ? std::max(r, q) : 0;   // 0: per window
         pl->rows_hv_thr = nh ? thr : 0xffffffffu; pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = hl; pl->rows_regt = 0;
         pl->rows_smem_bytes = rows_smem(G, n_extra, q, nh, hl); pl->rows_table_terms = n_extra;
         return true;
@@ -257,17 +274,27 @@ void choose_staged(qr_plan *pl)
     if (G < 8 && 64 * row_bytes <= MAX_SMEM)  { pl->rw = 2; pl->gw = 4; }
     else if (64 * row_bytes <= 113 * 1024)    { pl->rw = 2; pl->gw = 8; }   // 2+ CTAs/SM
     else if (32 * row_bytes <= 113 * 1024)    { pl->rw = 1; pl->gw = 8; }
-    else {
+    if (pl->rw) {
+        // The staged kernel (lane <-> row) is at its best on short rows with a long diagonal group (spin chains and
+        // lattices: G = n + 1, 97-100 % of peak).  On operators without such a group it pays per-group overheads and,
+        // from G = 76, runs one 8-warp CTA per SM: 2.3-4.4 TB/s for G = 32..150, where the rows kernel (thread <->
+        // group, sub-batches) holds 6.2-6.9 TB/s (profiles/r03_rows_sweep.jsonl).  With heavy groups the rows kernel
+        // takes over from G = 76 only (C2 / C4 / XXZ chains: 3.4-4.0 TB/s against 4.6-6.6 staged).
+        const char *env = getenv("QR_FILL_ROWS");
+        if (G >= 32 && !(env && (env[0] == '0' || env[0] == '1')) && choose_rows(pl))
+            if (!(pl->rows_regt && (pl->rows_hv_cap == 0 || G > 75))) pl->rows_th = 0;
+    } else {
         // whole rows do not fit (twice) in shared memory: the lanes kernel (lane <-> group, rows in
         // Gray-code order).  QR_FILL_LANES=0 falls back to subtree blocks of <= 32 groups through
         // shared memory (profiles/r01_fill_sweep_largeG.jsonl: C3 4.52 TB/s at S=32, 3.73 at 64).
         pl->lanes = 1;
         if (const char *env = getenv("QR_FILL_LANES")) if (env[0] == '0') { pl->lanes = 0; pl->block_s = 32; }
-        // G >= 400 with rows that fit shared memory two batches at a time: whole rows through the TMA
-        // (fill_rows_kernel); the lanes kernel stays the path for everything else and for the ragged
-        // cases build_rows cannot align
+        // rows that fit shared memory two batches at a time (G <= ~2400 unless the term table is huge): whole
+        // rows through the TMA (fill_rows_kernel), measured ahead of the lanes kernel for every G from 160 up
+        // (profiles/r03_rows_sweep.jsonl); the lanes kernel stays the path for everything else and for the
+        // ragged windows build_rows cannot align
         const char *env = getenv("QR_FILL_ROWS");
-        if (!(env && env[0] == '0') && G >= 400) choose_rows(pl);
+        if (!(env && env[0] == '0')) choose_rows(pl);
     }
 }
 
@@ -467,20 +494,20 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
     const uint64_t indptr_base = (flags & QR_INDPTR_GLOBAL) ? row_lo * G : 0;
     uint64_t lo = row_lo, hi = row_hi;
     if (!(flags & QR_FILL_DIRECT) && pl->rows_th) {
-        const int q = pl->rows_q;
+        const int q = pl->rows_q, qb = pl->rows_q + pl->rows_sl;   // log2 rows per thread / per batch
         // rows per run: 256 (C3 6.27 TB/s; 128: 6.04, 64: 5.66), shorter when the window does not hold enough runs
         // to spread evenly over the persistent CTAs (2^16 rows of H8: 32-row runs 3.28 TB/s, 128-row runs 3.02)
         int k = pl->rows_log2r ? pl->rows_log2r : 8;
         if (!pl->rows_log2r) {
             const uint64_t span = row_hi - row_lo;
-            while (k > 5 && k > q) {
+            while (k > 5 && k > qb) {
                 const uint64_t runs = span >> k;
                 if (runs >= 148 && (runs + 147) / 148 * 148 * 100 <= runs * 104) break;    // <= 4 % idle tail on 148 CTAs
                 k--;
             }
         }
-        k = std::max(k, q);
-        while (k > q && align_up(row_lo, 1ull << k) + (1ull << k) > row_hi) k--;      // short windows: shorter runs
+        k = std::max(k, qb);
+        while (k > qb && align_up(row_lo, 1ull << k) + (1ull << k) > row_hi) k--;     // short windows: shorter runs
         const uint64_t R = 1ull << k;
         const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
         // the bulk copies need 16-byte aligned global addresses: indices + (s0 - row_lo) * G * 8
@@ -488,16 +515,18 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         if (s1 > s0 && aligned && (s1 - s0) / R <= 0xffffffffull) {
             const uint64_t n_runs = (s1 - s0) / R, n_extra = pl->rows_table_terms;
             const size_t smem = pl->rows_smem_bytes;
-            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint64_t,
-                                    uint64_t, uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
+            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                                    uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
             RowsFn kern = nullptr;
 #define QR_ROWS_Q(NG_, TH_, RG_, HV_) \
             (q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_, RG_, HV_> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_, RG_, HV_>)
 #define QR_ROWS_CASE(NG_, TH_, RG_) \
-            if (pl->rows_ng == NG_ && pl->rows_th == TH_ && pl->rows_regt == (RG_ ? 1 : 0)) \
+            if (q <= 2 && pl->rows_ng == NG_ && pl->rows_th == TH_ && pl->rows_regt == (RG_ ? 1 : 0)) \
                 kern = pl->rows_hv_cap ? QR_ROWS_Q(NG_, TH_, RG_, true) : QR_ROWS_Q(NG_, TH_, RG_, false);
             QR_ROWS_CASE(1, 1024, false) QR_ROWS_CASE(2, 1024, false) QR_ROWS_CASE(3, 1024, false)
             QR_ROWS_CASE(1, 512, true) QR_ROWS_CASE(2, 512, true)
+            if (q == 3 && pl->rows_ng == 1 && pl->rows_regt)
+                kern = pl->rows_hv_cap ? (RowsFn)qr::fill_rows_kernel<1, 3, 512, true, true> : (RowsFn)qr::fill_rows_kernel<1, 3, 512, true, false>;
 #undef QR_ROWS_Q
 #undef QR_ROWS_CASE
             if (!kern) return fail(QR_ERR_UNSUPPORTED, "fill_rows: no kernel instance for this plan");
@@ -509,7 +538,7 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             const uint64_t ctas = std::min<uint64_t>(n_runs, (uint64_t)per_sm * (uint64_t)n_sm);   // persistent CTAs
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
-            kern<<<(unsigned)ctas, pl->rows_th, smem, st>>>(pl->dev, (uint32_t)G, (uint32_t)n_extra, (uint32_t)k, (uint32_t)n_runs,
+            kern<<<(unsigned)ctas, pl->rows_th, smem, st>>>(pl->dev, (uint32_t)G, (uint32_t)n_extra, (uint32_t)k, (uint32_t)pl->rows_sl, (uint32_t)n_runs,
                                                            pl->rows_hv_thr, pl->rows_hv_cap, (uint32_t)pl->rows_hv_log2, s0, row_lo, indptr_base, d_indptr,
                                                            d_indices, d_data, row_hi - row_lo);
             QR_LAUNCH_CHECK("fill_rows_kernel");

@@ -253,15 +253,17 @@ def test_lanes_kernel_clusters(monkeypatch, W):
         assert np.array_equal(ix, ref[1][lo * 1100:hi * 1100]) and np.array_equal(u64(dt), u64(ref[2][lo * 1100:hi * 1100]))
 
 
-@pytest.mark.parametrize("REGT,Q,R", [(1, 1, 1), (1, 2, 5), (0, 1, 7), (0, 2, 3), (1, 1, 4), (0, 2, 8), (1, 1, 6), (1, 2, 7), (0, 1, 5)])
+@pytest.mark.parametrize("REGT,Q,R,SL", [(1, 1, 1, 0), (1, 2, 5, 0), (0, 1, 7, 0), (0, 2, 3, 0), (1, 1, 4, 0), (0, 2, 8, 0), (1, 1, 6, 0), (1, 2, 7, 0),
+                                         (0, 1, 5, 0), (1, 3, 7, 0), (1, 3, 3, 0), (1, 3, 7, None), (1, 1, 6, 2), (1, 2, 7, 1), (1, 3, 8, 4), (1, 1, 3, 1)])
 @pytest.mark.parametrize("HV", [None, "0", "2"])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
-def test_rows_kernel(fixtures, monkeypatch, name, REGT, Q, R, HV):
+def test_rows_kernel(fixtures, monkeypatch, name, REGT, Q, R, SL, HV):
     """Rows kernel (fill_rows_kernel: persistent CTAs own whole rows, thread <-> group, batches of 2^Q rows
     in Gray-code order through two shared-memory buffers and the TMA) forced on every case: whole matrix
     and ragged windows (edge rows go through the direct kernel, misaligned windows through the default path).
     REGT: 1 = up to 6 terms of a group in registers (512 threads), 0 = first term in registers, the others in shared
-    memory (1024 threads).  HV: threshold of the CTA-wide heavy-group path (default: more than 6 terms; "0": off;
+    memory (1024 threads).  SL: log2 of the sub-batches the threads split into when G <= 256 (None: as many as fit; the
+    library lowers it when 512 >> SL < G).  HV: threshold of the CTA-wide heavy-group path (default: more than 6 terms; "0": off;
     "2": nearly every group is heavy; both force the shared-memory variant)."""
     monkeypatch.setenv("QR_FILL_ROWS", "1")
     if HV is not None:
@@ -269,13 +271,15 @@ def test_rows_kernel(fixtures, monkeypatch, name, REGT, Q, R, HV):
     monkeypatch.setenv("QR_FILL_ROWS_REGT", str(REGT))
     monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
     monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
+    if SL is not None:
+        monkeypatch.setenv("QR_FILL_ROWS_SL", str(SL))
     labels, coeffs = SMALL[name](fixtures)
     n, params = O.make_params(labels, coeffs)
     ref = O.build_csr(params, n)
     plan = make_op(labels, coeffs).plan()
     assert plan.fill_kernel == "fill_rows_kernel"
     G, dim = plan.n_groups, 1 << n
-    assert_same(device_build(plan, 0, dim), ref, f"{name} REGT={REGT} Q={Q} R={R} HV={HV}")
+    assert_same(device_build(plan, 0, dim), ref, f"{name} REGT={REGT} Q={Q} R={R} SL={SL} HV={HV}")
     if dim >= 128:
         for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 33), (6, dim - 2)]:
             ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
@@ -284,7 +288,8 @@ def test_rows_kernel(fixtures, monkeypatch, name, REGT, Q, R, HV):
 
 
 @pytest.mark.parametrize("G,T,REGT,Q", [(1100, 1500, 0, 1), (1100, 1500, 0, 2), (2200, 2600, 0, 1), (600, 2400, 0, 2), (600, 2400, 1, 2),
-                                        (1000, 3000, 1, 1), (1000, 3000, 0, 1), (450, 500, None, 0), (700, 3000, None, 0)])
+                                        (1000, 3000, 1, 1), (1000, 3000, 0, 1), (450, 500, None, 0), (700, 3000, None, 0), (400, 900, 1, 3),
+                                        (200, 300, None, 0), (160, 700, None, 0), (100, 250, 1, 3), (60, 200, 1, 2)])
 def test_rows_kernel_large_G(monkeypatch, G, T, REGT, Q):
     """The shapes the rows kernel is chosen for by default (G >= 400): 1..3 groups per thread, terms in registers
     or in shared memory (T - G extras, up to 4 per group on average, so some groups are heavy), 2- and 4-row
@@ -296,6 +301,8 @@ def test_rows_kernel_large_G(monkeypatch, G, T, REGT, Q):
     if REGT is not None:
         monkeypatch.setenv("QR_FILL_ROWS_REGT", str(REGT))
         monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
+    if G <= 150:
+        monkeypatch.setenv("QR_FILL_ROWS", "1")          # the staged kernel's range: force
     for R in (3, 7):
         monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
         plan = make_op(labels, coeffs).plan()
@@ -308,12 +315,16 @@ def test_rows_kernel_large_G(monkeypatch, G, T, REGT, Q):
 
 
 def test_rows_kernel_selection(fixtures, monkeypatch):
-    """Default choice: staged for rows that fit a 32-row tile, lanes for 150 < G < 400 and for rows too long for
-    two shared-memory batches, rows in between; QR_FILL_ROWS=0 restores the lanes kernel."""
+    """Default choice: staged for rows that fit a 32-row tile, lanes for rows too long for two shared-memory
+    batches, rows in between; QR_FILL_ROWS=0 restores the lanes kernel."""
     def kernel_of(labels, coeffs):
         return make_op(labels, coeffs).plan().fill_kernel
     assert kernel_of(*H.xxz_chain(10, 1.0, 0.7)) == "fill_staged_kernel"
-    assert kernel_of(*fixtures["H6"]) == "fill_lanes_kernel"                       # G = 286
+    assert kernel_of(*H.tfim_lattice(5, 6, 1.0, 3.0)) == "fill_staged_kernel"      # G = 31
+    assert kernel_of(*H.random_pauli_sum(12, 60, 40, 5, 5)) == "fill_rows_kernel"  # G = 40, no long group
+    assert kernel_of(*H.random_pauli_sum(12, 30, 20, 5, 5)) == "fill_staged_kernel"
+    assert kernel_of(*fixtures["H4"]) == "fill_staged_kernel"                      # G = 51 with heavy groups
+    assert kernel_of(*fixtures["H6"]) == "fill_rows_kernel"                        # G = 286
     big = H.random_pauli_sum(12, 1500, 1100, 50, 5)
     assert kernel_of(*big) == "fill_rows_kernel"
     assert kernel_of(*H.random_pauli_sum(13, 3500, 3000, 50, 5)) == "fill_lanes_kernel"    # 3000 * 96 B > 227 KB
@@ -321,16 +332,16 @@ def test_rows_kernel_selection(fixtures, monkeypatch):
     assert kernel_of(*big) == "fill_lanes_kernel"
 
 
-def test_lanes_kernel_is_the_large_G_default(fixtures):
-    """G = 286 rows do not fit the staged kernel's shared-memory tile: the default path must be the
-    lanes kernel, and it must agree with the shared-memory blocked kernel and the oracle."""
+def test_large_G_default_is_one_launch(fixtures):
+    """G = 286 rows do not fit the staged kernel's shared-memory tile: the default path must be one launch of a
+    large-G kernel (rows; lanes with QR_FILL_ROWS=0), and it must agree with the oracle."""
     labels, coeffs = fixtures["H6"]
     n, params = O.make_params(labels, coeffs)
     ref = O.build_csr(params, n)
     plan = make_op(labels, coeffs).plan()
     before = _ffi.kernel_launches()
     assert_same(device_build(plan, 0, 1 << n), ref, "H6 default")
-    assert _ffi.kernel_launches() - before == 1          # one fill_lanes_kernel, no edge launches
+    assert _ffi.kernel_launches() - before == 1          # one fill kernel, no edge launches
 
 
 def test_build_host_windows(fixtures):
