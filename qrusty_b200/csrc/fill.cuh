@@ -668,28 +668,68 @@ __device__ __forceinline__ void rows_heavy_fold(const uint32_t *zs, const double
 
 // The CTA-wide heavy phase for the strip of HS rows that starts at row `sbase`.  s_hd[q] = {offset of the group's
 // terms 1.. in the shared term table, their number, z of term 0, group}; s_h0c[q] = c' of term 0.
+template <int HE>
+__device__ __forceinline__ void rows_heavy_item(const uint4 d, const double2 c0, double2 *hv, const uint32_t *s_ez,
+                                                const double2 *s_ec, uint32_t r, uint32_t lane)
+{
+    double hre[4], him[4];
+#pragma unroll
+    for (int e = 0; e < HE; e++) {
+        const uint32_t s = (uint32_t)(__popc((r + 32u * e) & d.z) & 1) << 31;
+        hre[e] = flip_sign(c0.x, s); him[e] = flip_sign(c0.y, s);
+    }
+    rows_heavy_fold<HE>(s_ez + d.x, s_ec + d.x, d.y, r, hre, him);
+#pragma unroll
+    for (int e = 0; e < HE; e++) hv[lane + 32u * e] = make_double2(hre[e], him[e]);
+}
+
+// Heavy groups round-robin over the warps, lane <-> row, up to 4 rows per lane (the rows of a lane are independent FP64
+// chains that hide the latency of the group's one dependent chain per row); when there are fewer heavy groups than half
+// the warps, (group, 32 rows) items are spread over the warps instead.
 template <int TH>
 __device__ __forceinline__ void rows_heavy_phase(const uint4 *s_hd, const double2 *s_h0c, double2 *s_hv, const uint32_t *s_ez,
                                                  const double2 *s_ec, uint32_t n_heavy, uint32_t HS, uint32_t hv_log2,
                                                  uint32_t sbase)
 {
+    constexpr uint32_t NW = TH / 32u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t r = sbase + lane;
-    for (uint32_t q = warp; q < n_heavy; q += TH / 32u) {
-        const uint4 d = s_hd[q];
-        const double2 c0 = s_h0c[q];
-        double hre[4], him[4];
-#pragma unroll
-        for (uint32_t e = 0; e < 4u; e++) {
-            const uint32_t s = (uint32_t)(__popc((r + 32u * e) & d.z) & 1) << 31;
-            hre[e] = flip_sign(c0.x, s); him[e] = flip_sign(c0.y, s);
+    if (HS < 32u) {                                                // runs shorter than a warp (tiny matrices)
+        for (uint32_t q = warp; q < n_heavy; q += NW) {
+            const uint4 d = s_hd[q];
+            const double2 c0 = s_h0c[q];
+            double hre[4], him[4];
+            const uint32_t sg = (uint32_t)(__popc((sbase + lane) & d.z) & 1) << 31;
+            hre[0] = flip_sign(c0.x, sg); him[0] = flip_sign(c0.y, sg);
+            rows_heavy_fold<1>(s_ez + d.x, s_ec + d.x, d.y, sbase + lane, hre, him);
+            if (lane < HS) s_hv[(q << hv_log2) + lane] = make_double2(hre[0], him[0]);
         }
-        if (HS > 64u) rows_heavy_fold<4>(s_ez + d.x, s_ec + d.x, d.y, r, hre, him);
-        else if (HS > 32u) rows_heavy_fold<2>(s_ez + d.x, s_ec + d.x, d.y, r, hre, him);
-        else rows_heavy_fold<1>(s_ez + d.x, s_ec + d.x, d.y, r, hre, him);
+        return;
+    }
+    if (2u * n_heavy >= NW) {
+        // at least half as many heavy groups as warps: one group per warp visit, up to 4 rows per lane
+        for (uint32_t q = warp; q < n_heavy; q += NW) {
+            const uint4 d = s_hd[q];
+            const double2 c0 = s_h0c[q];
+            double hre[4], him[4];
 #pragma unroll
-        for (uint32_t e = 0; e < 4u; e++)
-            if (lane + 32u * e < HS) s_hv[(q << hv_log2) + lane + 32u * e] = make_double2(hre[e], him[e]);
+            for (uint32_t e = 0; e < 4u; e++) {
+                const uint32_t s = (uint32_t)(__popc((sbase + lane + 32u * e) & d.z) & 1) << 31;
+                hre[e] = flip_sign(c0.x, s); him[e] = flip_sign(c0.y, s);
+            }
+            if (HS > 64u) rows_heavy_fold<4>(s_ez + d.x, s_ec + d.x, d.y, sbase + lane, hre, him);
+            else if (HS > 32u) rows_heavy_fold<2>(s_ez + d.x, s_ec + d.x, d.y, sbase + lane, hre, him);
+            else rows_heavy_fold<1>(s_ez + d.x, s_ec + d.x, d.y, sbase + lane, hre, him);
+#pragma unroll
+            for (uint32_t e = 0; e < 4u; e++)
+                if (lane + 32u * e < HS) s_hv[(q << hv_log2) + lane + 32u * e] = make_double2(hre[e], him[e]);
+        }
+        return;
+    }
+    // a few heavy groups (one long diagonal group: spin chains): (group, 32 rows) items spread over the warps
+    const uint32_t n_chunks = HS >> 5;
+    for (uint32_t item = warp; item < n_heavy * n_chunks; item += NW) {
+        const uint32_t q = item / n_chunks, ch = item - q * n_chunks;
+        rows_heavy_item<1>(s_hd[q], s_h0c[q], s_hv + (q << hv_log2) + (ch << 5), s_ez, s_ec, sbase + (ch << 5) + lane, lane);
     }
 }
 
@@ -702,11 +742,12 @@ __device__ __forceinline__ void rows_heavy_phase(const uint4 *s_hd, const double
 //               terms per group) this removes two thirds of the kernel's shared-memory traffic.
 // HEAVY = false: the plan has no heavy group; the heavy path is compiled out (its 4-rows-per-lane fold costs the
 //               1024-thread instances registers they do not have: C3 6.6 TB/s without, 5.6 with).
-template <int NG, int Q, int TH, bool REGT, bool HEAVY>
+// CS = true   : the rank-table columns are staged in shared memory (short rows; instantiated for NG = 1, REGT only).
+template <int NG, int Q, int TH, bool REGT, bool HEAVY, bool CS>
 __global__ void __launch_bounds__(TH, 1)
 fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32_t sl, uint32_t n_runs,
-                 uint32_t hv_thr, uint32_t hv_cap, uint32_t hv_log2, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
-                 uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
+                 uint32_t hv_thr, uint32_t hv_cap, uint32_t hv_log2, uint64_t tile_row0, uint64_t row_lo,
+                 uint64_t indptr_base, uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
                  double2 *__restrict__ data, uint64_t indptr_last_row)
 {
     constexpr uint32_t RT = 1u << Q;
@@ -724,10 +765,15 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     double2 *s_hv = reinterpret_cast<double2 *>(smem_raw + (((size_t)tile_n * 48u + (size_t)n_extra * 20u + 15u) & ~(size_t)15u));   // [hv_cap][2^hv_log2]
     double2 *s_h0c = s_hv + ((size_t)hv_cap << hv_log2);                                 // [hv_cap]
     uint4 *s_hd = reinterpret_cast<uint4 *>(s_h0c + hv_cap);                             // [hv_cap]
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_hd + hv_cap);                       // [n_qubits][G] when CS
     __shared__ uint32_t s_nheavy, s_hterms;
     const uint32_t T = p.n_terms, nq = (uint32_t)p.n_qubits;
     constexpr uint32_t NOT_HEAVY = 0xffffffffu;
     if (threadIdx.x == 0) { s_nheavy = 0; s_hterms = 0; }
+    // short rows: the rank-table columns (n_qubits * G words) fit in shared memory, so neither the slot of a run's
+    // first row (n_qubits reads per group and run) nor a Gray step waits on L2
+    if constexpr (CS)
+        for (uint32_t i = threadIdx.x; i < nq * G; i += TH) { const uint32_t b = i / G; s_cnt[i] = __ldg(&p.cnt_t[b * T + (i - b * G)]); }
     __syncthreads();
 
     // ---- once per CTA: this thread's groups ------------------------------------------------------
@@ -813,7 +859,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
             const uint32_t g = tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u, xr = x[k] ^ (r0 + (sub << Q));   // the thread's first row
             uint32_t o = 0;
             for (uint32_t b = 0; b < nq; b++) {
-                const uint32_t cb = __ldg(&p.cnt_t[b * T + gg]);
+                const uint32_t cb = CS ? s_cnt[b * G + gg] : __ldg(&p.cnt_t[b * T + gg]);
                 o += ((xr >> b) & 1u) ? cb : 0u;
             }
             off[k] = o;
@@ -831,7 +877,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                     else if (b == QB + 1u) s = sd[k][Q + 1];
                     else {
                         const uint32_t g = tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u;
-                        const int32_t cb = (int32_t)__ldg(&p.cnt_t[b * T + gg]);
+                        const int32_t cb = (int32_t)(CS ? s_cnt[b * G + gg] : __ldg(&p.cnt_t[b * T + gg]));
                         s = ((x[k] >> b) & 1u) ? -cb : cb;
                     }
                     off[k] += (uint32_t)(up ? s : -s);

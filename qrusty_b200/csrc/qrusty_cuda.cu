@@ -98,6 +98,7 @@ struct qr_plan {
     int rows_sl = 0;                                       // log2(sub-batches): a batch holds 2^(rows_q + rows_sl) rows
     size_t rows_smem_bytes = 0;
     uint64_t rows_table_terms = 0;                         // entries of the kernel's shared term table
+    uint32_t rows_cnt_smem = 0;                            // 1: rank-table columns staged in shared memory
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -158,7 +159,24 @@ size_t rows_smem(uint64_t G, uint64_t n_extra, int q, uint64_t n_heavy = 0, int 
     return (size_t)align_up((G << q) * 48 + n_extra * 20, 16) + (size_t)n_heavy * ((16ull << hv_log2) + 32);
 }
 
+bool choose_rows_shape(qr_plan *pl);
+
+// choose_rows_shape picks the variant; the rank-table columns are staged in shared memory on top when they are small
+// (short rows: G * n_qubits words <= 24 KB) and still fit
 bool choose_rows(qr_plan *pl)
+{
+    pl->rows_cnt_smem = 0;
+    if (!choose_rows_shape(pl)) return false;
+    const size_t cnt_bytes = (size_t)pl->n_groups * pl->n_qubits * 4;
+    const char *env = getenv("QR_FILL_ROWS_CNT");
+    if (pl->rows_regt && pl->rows_ng == 1 && cnt_bytes <= 24 * 1024 && pl->rows_smem_bytes + cnt_bytes <= MAX_SMEM && !(env && env[0] == '0')) {
+        pl->rows_cnt_smem = 1;
+        pl->rows_smem_bytes += cnt_bytes;
+    }
+    return true;
+}
+
+bool choose_rows_shape(qr_plan *pl)
 {
     const uint64_t G = pl->n_groups, n_extra = pl->n_terms_canonical - G;
     int q_forced = 0, r = 0;
@@ -279,10 +297,14 @@ void choose_staged(qr_plan *pl)
         // lattices: G = n + 1, 97-100 % of peak).  On operators without such a group it pays per-group overheads and,
         // from G = 76, runs one 8-warp CTA per SM: 2.3-4.4 TB/s for G = 32..150, where the rows kernel (thread <->
         // group, sub-batches) holds 6.2-6.9 TB/s (profiles/r03_rows_sweep.jsonl).  With heavy groups the rows kernel
-        // takes over from G = 76 only (C2 / C4 / XXZ chains: 3.4-4.0 TB/s against 4.6-6.6 staged).
+        // takes over from G = 76 only (C2 / C4 / XXZ n = 24: 4.8-5.1 TB/s against 6.0-6.6 staged).
         const char *env = getenv("QR_FILL_ROWS");
-        if (G >= 32 && !(env && (env[0] == '0' || env[0] == '1')) && choose_rows(pl))
-            if (!(pl->rows_regt && (pl->rows_hv_cap == 0 || G > 75))) pl->rows_th = 0;
+        // Chains whose G = n + 1 is a multiple of 4 hit 4- and 8-way bank conflicts in the staged tile (lanes G * 16 B
+        // apart): XXZ n = 23 / 27 (G = 24 / 28) 4.66 / 4.98 TB/s staged, 5.24 / 5.76 rows; G = 20 still favours staged (4.73 / 4.16).
+        if (G >= 24 && !(env && (env[0] == '0' || env[0] == '1')) && choose_rows(pl)) {
+            const bool no_long_group = G >= 32 && pl->rows_hv_cap == 0, long_rows = G > 75, conflicts = G % 4 == 0;
+            if (!(pl->rows_regt && (no_long_group || long_rows || conflicts))) pl->rows_th = 0;
+        }
     } else {
         // whole rows do not fit (twice) in shared memory: the lanes kernel (lane <-> group, rows in
         // Gray-code order).  QR_FILL_LANES=0 falls back to subtree blocks of <= 32 groups through
@@ -497,7 +519,7 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         const int q = pl->rows_q, qb = pl->rows_q + pl->rows_sl;   // log2 rows per thread / per batch
         // rows per run: 256 (C3 6.27 TB/s; 128: 6.04, 64: 5.66), shorter when the window does not hold enough runs
         // to spread evenly over the persistent CTAs (2^16 rows of H8: 32-row runs 3.28 TB/s, 128-row runs 3.02)
-        int k = pl->rows_log2r ? pl->rows_log2r : 8;
+        int k = pl->rows_log2r ? pl->rows_log2r : std::max(8, qb + 3);   // big batches (short rows): 8 batches per run
         if (!pl->rows_log2r) {
             const uint64_t span = row_hi - row_lo;
             while (k > 5 && k > qb) {
@@ -519,14 +541,20 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
                                     uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
             RowsFn kern = nullptr;
 #define QR_ROWS_Q(NG_, TH_, RG_, HV_) \
-            (q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_, RG_, HV_> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_, RG_, HV_>)
+            (q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_, RG_, HV_, false> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_, RG_, HV_, false>)
 #define QR_ROWS_CASE(NG_, TH_, RG_) \
-            if (q <= 2 && pl->rows_ng == NG_ && pl->rows_th == TH_ && pl->rows_regt == (RG_ ? 1 : 0)) \
+            if (q <= 2 && !pl->rows_cnt_smem && pl->rows_ng == NG_ && pl->rows_th == TH_ && pl->rows_regt == (RG_ ? 1 : 0)) \
                 kern = pl->rows_hv_cap ? QR_ROWS_Q(NG_, TH_, RG_, true) : QR_ROWS_Q(NG_, TH_, RG_, false);
             QR_ROWS_CASE(1, 1024, false) QR_ROWS_CASE(2, 1024, false) QR_ROWS_CASE(3, 1024, false)
             QR_ROWS_CASE(1, 512, true) QR_ROWS_CASE(2, 512, true)
-            if (q == 3 && pl->rows_ng == 1 && pl->rows_regt)
-                kern = pl->rows_hv_cap ? (RowsFn)qr::fill_rows_kernel<1, 3, 512, true, true> : (RowsFn)qr::fill_rows_kernel<1, 3, 512, true, false>;
+            // one group per thread, terms in registers: 8-row batches and the rank table in shared memory exist here only
+#define QR_ROWS_ONE(Q_, HV_, CS_) \
+            if (pl->rows_ng == 1 && pl->rows_regt && q == Q_ && (pl->rows_hv_cap != 0) == HV_ && (pl->rows_cnt_smem != 0) == CS_) \
+                kern = (RowsFn)qr::fill_rows_kernel<1, Q_, 512, true, HV_, CS_>;
+            QR_ROWS_ONE(3, false, false) QR_ROWS_ONE(3, true, false)
+            QR_ROWS_ONE(1, false, true) QR_ROWS_ONE(1, true, true) QR_ROWS_ONE(2, false, true) QR_ROWS_ONE(2, true, true)
+            QR_ROWS_ONE(3, false, true) QR_ROWS_ONE(3, true, true)
+#undef QR_ROWS_ONE
 #undef QR_ROWS_Q
 #undef QR_ROWS_CASE
             if (!kern) return fail(QR_ERR_UNSUPPORTED, "fill_rows: no kernel instance for this plan");

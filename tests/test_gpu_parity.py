@@ -174,6 +174,7 @@ def test_direct_equals_staged(fixtures):
 def test_staged_padded_tiles(fixtures, monkeypatch, name, force):
     """fill_staged_kernel<.,.,PAD>: G a multiple of 4 (xxz n=11/15/7: G = 12/16/8, H2: 4) takes the padded
     shared-memory pitch and one TMA copy per row automatically; QR_FILL_PAD=1 forces it for any even G."""
+    monkeypatch.setenv("QR_FILL_ROWS", "0")              # this test is about the staged kernel
     if force:
         monkeypatch.setenv("QR_FILL_PAD", "1")
     labels, coeffs = H.xxz_chain(int(name[3:]), 1.0, 0.7) if name.startswith("xxz") else SMALL[name](fixtures)
@@ -321,6 +322,8 @@ def test_rows_kernel_selection(fixtures, monkeypatch):
         return make_op(labels, coeffs).plan().fill_kernel
     assert kernel_of(*H.xxz_chain(10, 1.0, 0.7)) == "fill_staged_kernel"
     assert kernel_of(*H.tfim_lattice(5, 6, 1.0, 3.0)) == "fill_staged_kernel"      # G = 31
+    assert kernel_of(*H.xxz_chain(23, 1.0, 0.7)) == "fill_rows_kernel"             # G = 24: bank conflicts in the staged tile
+    assert kernel_of(*H.xxz_chain(19, 1.0, 0.7)) == "fill_staged_kernel"           # G = 20
     assert kernel_of(*H.random_pauli_sum(12, 60, 40, 5, 5)) == "fill_rows_kernel"  # G = 40, no long group
     assert kernel_of(*H.random_pauli_sum(12, 30, 20, 5, 5)) == "fill_staged_kernel"
     assert kernel_of(*fixtures["H4"]) == "fill_staged_kernel"                      # G = 51 with heavy groups
