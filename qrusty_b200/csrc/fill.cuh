@@ -635,6 +635,32 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
 // Values: sign flips and __dadd_rn in original term order, first term taken as is: the fold
 // of accel.rs:191-205, bit for bit (same helpers as the other fill kernels).
 // ---------------------------------------------------------------------------------
+// ---- thread-block cluster helpers (rows kernel, CL > 1) ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier()           // arrive has release, wait has acquire semantics
+{
+    asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank)    // same offset in CTA `rank`'s shared memory
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f64x2(uint32_t addr, double a, double b)
+{
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t addr, uint64_t v)
+{
+    asm volatile("st.shared::cluster.u64 [%0], %1;" :: "r"(addr), "l"(v) : "memory");
+}
+
 // +-1.0 whose sign is bit 0 of p (the other bits of p are ignored)
 __device__ __forceinline__ double pm_one(uint32_t p)
 {
@@ -743,19 +769,56 @@ __device__ __forceinline__ void rows_heavy_phase(const uint4 *s_hd, const double
 // HEAVY = false: the plan has no heavy group; the heavy path is compiled out (its 4-rows-per-lane fold costs the
 //               1024-thread instances registers they do not have: C3 6.6 TB/s without, 5.6 with).
 // CS = true   : the rank-table columns are staged in shared memory (short rows; instantiated for NG = 1, REGT only).
-template <int NG, int Q, int TH, bool REGT, bool HEAVY, bool CS>
+// CL > 1      : rows too long for one CTA's shared memory.  The CTAs of a thread-block cluster of CL split the GROUPS
+//               (CTA c: groups [c*Gc, (c+1)*Gc), terms in registers) and the ROWS of a batch (CTA c owns rows
+//               c*RT/CL .. of every batch): each thread folds its groups for all RT rows and stores row j's entry into
+//               the batch buffer of the CTA that owns row j through distributed shared memory (mapa + st.shared::cluster);
+//               a cluster barrier per batch; every CTA hands its own whole rows to the TMA.  REGT, sl = 0 only.
+//               (Measured slower than one CTA per row wherever both apply: distributed shared memory moves 17-21 B
+//               per cycle and SM, about the SM's share of HBM; kept for term-rich operators with 1024 < G <= 2048.)
+// CL == 0     : SPLIT mode, rows of any length.  The sorted masks are cut into trie subtrees of <= 1024 groups (K1b,
+//               partition_kernel); a subtree's groups fill one contiguous slot range [base(r), base(r) + Gs) in every row
+//               (XOR never splits a subtree), base(r) = sum_{b >= level} cnt[g0][b] * bit_b(x_g0 ^ r).  A CTA owns one
+//               subtree (terms in registers) and assembles, per batch, the RT row SEGMENTS of its subtree, each handed to
+//               the TMA on its own (data: always 16-byte aligned; column ids: the buffer row is shifted by one entry when
+//               the segment starts at an odd entry, the aligned interior goes through the TMA and the one or two edge
+//               entries through plain stores).  CTAs are shared out among the subtrees in proportion to their size; the
+//               CTAs of a subtree share out the runs.  No exchange between CTAs.
+struct RowsSplit {
+    uint32_t n;                    // subtrees
+    uint32_t g0[33];               // subtree s = sorted groups [g0[s], g0[s + 1])
+    uint32_t level[32];            // its groups share the mask bits >= level[s]
+    uint32_t cta0[33];             // CTAs [cta0[s], cta0[s + 1]) work on subtree s
+};
+
+template <int NG, int Q, int TH, bool REGT, bool HEAVY, bool CS, int CL>
 __global__ void __launch_bounds__(TH, 1)
-fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32_t sl, uint32_t n_runs,
+fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t log2R, uint32_t sl, uint32_t n_runs,
                  uint32_t hv_thr, uint32_t hv_cap, uint32_t hv_log2, uint64_t tile_row0, uint64_t row_lo,
                  uint64_t indptr_base, uint64_t *__restrict__ indptr, uint64_t *__restrict__ indices,
-                 double2 *__restrict__ data, uint64_t indptr_last_row)
+                 double2 *__restrict__ data, uint64_t indptr_last_row, const __grid_constant__ RowsSplit sp)
 {
     constexpr uint32_t RT = 1u << Q;
+    constexpr bool SPLIT = CL == 0;
     constexpr int NS = Q + 2;                                      // row bits whose slot step lives in a register
     constexpr int NT = REGT ? LANE_TERMS : 1;                      // terms of a group kept in registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t QB = (uint32_t)Q + sl;                          // log2(rows per batch): 2^sl sub-batches of RT rows
-    const uint32_t tile_n = (RT << sl) * G;                        // entries of one batch
+    constexpr uint32_t CLD = CL > 1 ? CL : 1;
+    static_assert(CL <= 1 || (REGT && !CS && RT % CLD == 0), "cluster variant: terms in registers, whole rows per CTA");
+    static_assert(!SPLIT || (REGT && !CS), "split variant: terms in registers");
+    constexpr uint32_t ROWS_OWN = RT / CLD;                        // CL > 1: rows of a batch this CTA hands to the TMA
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    // this CTA's groups [gbase, gbase + Gn) and its share jcta, jcta + n_share, ... of the runs
+    uint32_t gbase = crank * Gc, Gn = Gc, jcta = blockIdx.x / CLD, n_share = gridDim.x / CLD, level = 32u, sid = 0u;
+    if constexpr (SPLIT) {
+        while (sid + 1u < sp.n && blockIdx.x >= sp.cta0[sid + 1u]) sid++;
+        gbase = sp.g0[sid]; Gn = sp.g0[sid + 1u] - gbase; level = sp.level[sid];
+        jcta = blockIdx.x - sp.cta0[sid]; n_share = sp.cta0[sid + 1u] - sp.cta0[sid];
+    }
+    const uint32_t GW = SPLIT ? Gn : G;                            // entries of one buffered row (segment)
+    const uint32_t SI = SPLIT ? ((Gn + 3u) & ~1u) : G;             // pitch of a buffered row of column ids (room for the shift)
+    const uint32_t tile_n = (CL > 1 ? ROWS_OWN : (RT << sl)) * (SPLIT ? SI : G);   // entries of one batch buffer (SPLIT: its id pitch)
     const uint32_t GP = (uint32_t)TH >> sl;                        // threads per sub-batch (>= G when sl > 0; host-checked)
     const uint32_t tg = threadIdx.x & (GP - 1u), sub = threadIdx.x / GP;   // this thread's group slot and sub-batch
     double2 *sdat = reinterpret_cast<double2 *>(smem_raw);                               // [2][tile_n]
@@ -767,9 +830,15 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     uint4 *s_hd = reinterpret_cast<uint4 *>(s_h0c + hv_cap);                             // [hv_cap]
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_hd + hv_cap);                       // [n_qubits][G] when CS
     __shared__ uint32_t s_nheavy, s_hterms;
+    __shared__ uint32_t s_cb[32];                                  // SPLIT: cnt[g0][b] for b >= level (else 0), x of g0 in s_cb_x
+    __shared__ uint32_t s_cb_x;
     const uint32_t T = p.n_terms, nq = (uint32_t)p.n_qubits;
     constexpr uint32_t NOT_HEAVY = 0xffffffffu;
     if (threadIdx.x == 0) { s_nheavy = 0; s_hterms = 0; }
+    if (SPLIT && threadIdx.x < 32u) {
+        s_cb[threadIdx.x] = (threadIdx.x >= level && threadIdx.x < nq) ? __ldg(&p.cnt_t[threadIdx.x * T + gbase]) : 0u;
+        if (threadIdx.x == 0) s_cb_x = __ldg(&p.gx[gbase]);
+    }
     // short rows: the rank-table columns (n_qubits * G words) fit in shared memory, so neither the slot of a run's
     // first row (n_qubits reads per group and run) nor a Gray step waits on L2
     if constexpr (CS)
@@ -782,14 +851,15 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     double cr[NG][NT], ci[NG][NT];
 #pragma unroll
     for (int k = 0; k < NG; k++) {
-        const uint32_t g = tg + (uint32_t)k * GP;
+        const uint32_t gl = tg + (uint32_t)k * GP, g = gbase + gl;          // slot inside the CTA, group
+        const bool mine = gl < Gn && g < G;
         const uint32_t gg = g < G ? g : G - 1u;
         const uint32_t t0 = __ldg(&p.goff[gg]), t1 = __ldg(&p.goff[gg + 1]);
         x[k] = __ldg(&p.gx[gg]);
         // heavy groups (more than hv_thr terms: the Z-only group of a molecular Hamiltonian, a few dozen others)
         // are evaluated lane <-> row for a strip of rows at a time by the whole CTA, not inside their owner's lane
         hidx[k] = NOT_HEAVY;
-        if (HEAVY && g < G && sub == 0u && t1 - t0 > hv_thr) {
+        if (HEAVY && mine && sub == 0u && t1 - t0 > hv_thr) {
             const uint32_t h = atomicAdd(&s_nheavy, 1u);
             if (h < hv_cap) {
                 hidx[k] = h;
@@ -810,14 +880,14 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                 cr[k][t] = c.x; ci[k][t] = c.y;
             }
             // ee: terms the warp folds for this group slot = its longest light group (warp-uniform)
-            const uint32_t nt = (g < G && !(HEAVY && t1 - t0 > hv_thr)) ? min(t1 - t0, (uint32_t)NT) : 1u;
+            const uint32_t nt = (mine && !(HEAVY && t1 - t0 > hv_thr)) ? min(t1 - t0, (uint32_t)NT) : 1u;
             eb[k] = 0; ee[k] = __reduce_max_sync(0xffffffffu, nt);
         } else {
             z[k][0] = __ldg(&p.tz[t0]);
             const double2 c = __ldg(&p.tc[t0]);
             cr[k][0] = c.x; ci[k][0] = c.y;
             eb[k] = t0 - gg; ee[k] = t1 - gg - 1u;                 // sorted term t > t0 of group g is extra t - g - 1
-            if (g < G)
+            if (mine)
                 for (uint32_t t = t0 + 1u; t < t1; t++) { s_ez[t - gg - 1u] = __ldg(&p.tz[t]); s_ec[t - gg - 1u] = __ldg(&p.tc[t]); }
         }
 #pragma unroll
@@ -830,6 +900,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
     }
     __syncthreads();
 
+    if constexpr (CL > 1) cluster_barrier();                       // every CTA of the cluster is resident before the first remote store
     if (HEAVY && sl != 0u) {
         // sub-batches > 0 own the same groups as sub-batch 0: look the heavy index up in the descriptor table
         const uint32_t nh = min(s_nheavy, hv_cap);
@@ -837,17 +908,17 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
         for (int k = 0; k < NG; k++)
             if (sub != 0u) {
                 hidx[k] = NOT_HEAVY;
-                for (uint32_t h = 0; h < nh; h++) if (s_hd[h].w == tg + (uint32_t)k * GP) hidx[k] = h;
+                for (uint32_t h = 0; h < nh; h++) if (s_hd[h].w == gbase + tg + (uint32_t)k * GP) hidx[k] = h;
             }
     }
     const uint32_t R = 1u << log2R, n_batches = R >> QB;
     const uint32_t n_heavy = HEAVY ? min(s_nheavy, hv_cap) : 0u;
     const uint32_t HS = min(R, 1u << hv_log2), SB = HS >> QB;      // rows / batches per heavy strip (HS >= 2^QB; host-checked)
     uint32_t parity = 0;                                           // buffer of the current batch
-    for (uint32_t run = blockIdx.x; run < n_runs; run += gridDim.x) {
+    for (uint32_t run = jcta; run < n_runs; run += n_share) {
         const uint64_t r0_64 = tile_row0 + ((uint64_t)run << log2R);   // first row of the run (aligned to R)
         const uint32_t r0 = (uint32_t)r0_64;
-        if (indptr != nullptr)
+        if (indptr != nullptr && crank == 0u && sid == 0u)
             for (uint32_t i = threadIdx.x; i < R; i += TH) {
                 const uint64_t lr = r0_64 + i - row_lo;
                 indptr[lr] = indptr_base + lr * G;
@@ -856,7 +927,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
         // slot of every group in the first row this thread handles in the run's first batch
 #pragma unroll
         for (int k = 0; k < NG; k++) {
-            const uint32_t g = tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u, xr = x[k] ^ (r0 + (sub << Q));   // the thread's first row
+            const uint32_t g = gbase + tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u, xr = x[k] ^ (r0 + (sub << Q));   // the thread's first row
             uint32_t o = 0;
             for (uint32_t b = 0; b < nq; b++) {
                 const uint32_t cb = CS ? s_cnt[b * G + gg] : __ldg(&p.cnt_t[b * T + gg]);
@@ -865,18 +936,24 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
             off[k] = o;
         }
         uint32_t rb = r0;                                          // first row of the batch (bits < QB are 0)
+        uint32_t base = 0;                                         // SPLIT: first slot of the subtree in the rows of the batch
+        if constexpr (SPLIT) {
+            const uint32_t xr = s_cb_x ^ r0;
+            for (uint32_t b = level; b < nq; b++) base += ((xr >> b) & 1u) ? s_cb[b] : 0u;
+        }
         for (uint32_t i = 0; i < n_batches; i++) {
             if (i != 0u) {                                         // Gray code over batches: step i flips row bit QB + ctz(i)
                 const uint32_t b = QB + (uint32_t)__ffs((int)i) - 1u;
                 rb ^= 1u << b;
                 const bool up = (rb >> b) & 1u;                    // CTA-uniform
+                if constexpr (SPLIT) base += (((s_cb_x ^ rb) >> b) & 1u) ? s_cb[b] : 0u - s_cb[b];   // 0 for b < level
 #pragma unroll
                 for (int k = 0; k < NG; k++) {
                     int32_t s;
                     if (b == QB) s = sd[k][Q];
                     else if (b == QB + 1u) s = sd[k][Q + 1];
                     else {
-                        const uint32_t g = tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u;
+                        const uint32_t g = gbase + tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u;
                         const int32_t cb = (int32_t)(CS ? s_cnt[b * G + gg] : __ldg(&p.cnt_t[b * T + gg]));
                         s = ((x[k] >> b) & 1u) ? -cb : cb;
                     }
@@ -897,7 +974,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
             const uint32_t rt = rb + (sub << Q);                   // first of this thread's RT rows (bits < Q are 0)
 #pragma unroll
             for (int k = 0; k < NG; k++) {
-                if (tg + (uint32_t)k * GP < G) {
+                if (tg + (uint32_t)k * GP < Gn && gbase + tg + (uint32_t)k * GP < G) {
                     double re[RT], im[RT];
                     if (HEAVY && hidx[k] != NOT_HEAVY) {
 #pragma unroll
@@ -944,21 +1021,50 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
                     }
 #pragma unroll
                     for (uint32_t j = 0; j < RT; j++) {
-                        uint32_t o = ((sub << Q) + j) * G + off[k];
+                        uint32_t o = (CL > 1 ? (j % ROWS_OWN) : ((sub << Q) + j)) * G + off[k];
 #pragma unroll
                         for (int b = 0; b < Q; b++) if ((j >> b) & 1u) o += (uint32_t)sd[k][b];
-                        bd[o] = make_double2(re[j], im[j]);
-                        bi[o] = (uint64_t)((rt + j) ^ x[k]);
+                        if constexpr (SPLIT) {                     // segment-local slot; ids shifted by the parity of the segment start
+                            const uint32_t local = o - j * G - base;
+                            const uint32_t par = (uint32_t)(((uint64_t)(rt + j) - row_lo) * G + base) & 1u;
+                            bd[j * GW + local] = make_double2(re[j], im[j]);
+                            bi[j * SI + par + local] = (uint64_t)((rt + j) ^ x[k]);
+                        } else if constexpr (CL > 1) {                    // row j belongs to CTA j / ROWS_OWN of the cluster
+                            const uint32_t owner = j / ROWS_OWN;
+                            st_cluster_f64x2(mapa_shared((uint32_t)__cvta_generic_to_shared(bd + o), owner), re[j], im[j]);
+                            st_cluster_u64(mapa_shared((uint32_t)__cvta_generic_to_shared(bi + o), owner), (uint64_t)((rt + j) ^ x[k]));
+                        } else {
+                            bd[o] = make_double2(re[j], im[j]);
+                            bi[o] = (uint64_t)((rt + j) ^ x[k]);
+                        }
                     }
                 }
             }
             // generic-proxy writes -> visible to the async proxy; the copy that last read the OTHER buffer
             // (issued one batch ago) must have drained before anyone refills it after the barrier
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const uint64_t o = ((uint64_t)rb - row_lo) * G;
+            if constexpr (CL > 1) {
+                asm volatile("fence.proxy.async;" ::: "memory");           // this thread's (remote) writes -> async proxy
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                cluster_barrier();                                         // release / acquire across the cluster
+            } else {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (threadIdx.x < (SPLIT ? RT : 1u)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            }
+            if constexpr (SPLIT) {
+                if (threadIdx.x < RT) {                            // one thread per row segment
+                    const uint32_t j = threadIdx.x;
+                    const uint64_t gs = ((uint64_t)(rb + j) - row_lo) * G + base;     // first entry of the segment in the outputs
+                    const uint32_t par = (uint32_t)gs & 1u, n_al = (Gn - par) & ~1u;
+                    bulk_store_smem_to_global(data + gs, bd + j * GW, Gn * 16u);
+                    if (n_al) bulk_store_smem_to_global(indices + gs + par, bi + j * SI + 2u * par, n_al * 8u);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (par) indices[gs] = bi[j * SI + 1u];
+                    if ((Gn - par) & 1u) indices[gs + Gn - 1u] = bi[j * SI + par + Gn - 1u];
+                }
+            } else if (threadIdx.x == 0) {
+                if constexpr (CL > 1) asm volatile("fence.proxy.async;" ::: "memory");
+                const uint64_t o = ((uint64_t)rb + crank * ROWS_OWN - row_lo) * G;
                 bulk_store_smem_to_global(data + o, bd, tile_n * 16u);
                 bulk_store_smem_to_global(indices + o, bi, tile_n * 8u);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -966,7 +1072,8 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t n_extra, uint32_t log2R, uint32
             parity ^= 1u;
         }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (threadIdx.x < (SPLIT ? RT : 1u)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if constexpr (CL > 1) cluster_barrier();                       // nobody leaves while a peer could still address its memory
 }
 
 }  // namespace qr

@@ -99,6 +99,9 @@ struct qr_plan {
     size_t rows_smem_bytes = 0;
     uint64_t rows_table_terms = 0;                         // entries of the kernel's shared term table
     uint32_t rows_cnt_smem = 0;                            // 1: rank-table columns staged in shared memory
+    int rows_cl = 1;                                       // > 1: thread-block cluster of rows_cl CTAs per run of rows; 0: split mode
+    qr::RowsSplit rows_split{};                            // split mode: trie subtrees of <= 1024 groups, CTAs per subtree
+    uint32_t rows_gc = 0;                                  // groups per CTA of the cluster
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -153,6 +156,7 @@ int blocked_strips(const qr_plan *pl)
 // shared memory and a thread keeps at most 2 (a) / 3 (b) groups.  QR_FILL_ROWS_REGT / _Q / _R / _HV / _HVS override
 // the variant, the batch, the run length, the heavy threshold and the heavy strip (tests, sweeps).
 constexpr int ROWS_MAX_NG_1024 = 3;
+constexpr size_t ROWS_SMEM_CAP = MAX_SMEM - 1024;           // the kernel's static __shared__ variables count too
 constexpr uint32_t ROWS_HEAVY_TERMS = 6;                 // groups with more terms than this are "heavy"
 size_t rows_smem(uint64_t G, uint64_t n_extra, int q, uint64_t n_heavy = 0, int hv_log2 = 5)
 {
@@ -165,11 +169,11 @@ bool choose_rows_shape(qr_plan *pl);
 // (short rows: G * n_qubits words <= 24 KB) and still fit
 bool choose_rows(qr_plan *pl)
 {
-    pl->rows_cnt_smem = 0;
+    pl->rows_cnt_smem = 0; pl->rows_cl = 1; pl->rows_gc = 0; pl->rows_split = qr::RowsSplit{};
     if (!choose_rows_shape(pl)) return false;
     const size_t cnt_bytes = (size_t)pl->n_groups * pl->n_qubits * 4;
     const char *env = getenv("QR_FILL_ROWS_CNT");
-    if (pl->rows_regt && pl->rows_ng == 1 && cnt_bytes <= 24 * 1024 && pl->rows_smem_bytes + cnt_bytes <= MAX_SMEM && !(env && env[0] == '0')) {
+    if (pl->rows_regt && pl->rows_ng == 1 && cnt_bytes <= 24 * 1024 && pl->rows_smem_bytes + cnt_bytes <= ROWS_SMEM_CAP && !(env && env[0] == '0')) {
         pl->rows_cnt_smem = 1;
         pl->rows_smem_bytes += cnt_bytes;
     }
@@ -192,8 +196,8 @@ bool choose_rows_shape(qr_plan *pl)
     auto strip_log2 = [&](uint64_t extra, int q, uint64_t nh) {
         // strips of 128 / 64 rows (4 / 2 rows per lane in the heavy fold) when the side buffer still fits
         int hl = 5;
-        while (hl < 7 && nh != 0 && rows_smem(G, extra, q, nh, hl + 1) <= MAX_SMEM) hl++;
-        if (const char *env = getenv("QR_FILL_ROWS_HVS")) { int v = atoi(env); if (v >= 5 && v <= 7 && rows_smem(G, extra, q, nh, v) <= MAX_SMEM) hl = v; }
+        while (hl < 7 && nh != 0 && rows_smem(G, extra, q, nh, hl + 1) <= ROWS_SMEM_CAP) hl++;
+        if (const char *env = getenv("QR_FILL_ROWS_HVS")) { int v = atoi(env); if (v >= 5 && v <= 7 && rows_smem(G, extra, q, nh, v) <= ROWS_SMEM_CAP) hl = v; }
         return hl;
     };
 
@@ -203,6 +207,8 @@ bool choose_rows_shape(qr_plan *pl)
     //     Also for every G <= 512 (one group per thread): measured 6.67 vs 5.52 TB/s at G = 300, equal at G = 400;
     //     at G = 1000 with 1.3 terms per group variant (b) is ahead, 6.36 vs 6.20 (profiles/r03_rows_sweep.jsonl).
     int regt = ((G <= 512 || (G <= 1024 && n_extra >= G)) && thr0 == (uint32_t)qr::LANE_TERMS) ? 1 : 0;
+    if (const char *env = getenv("QR_FILL_ROWS_CL")) if (atoi(env) > 1) regt = 0;
+    if (const char *env = getenv("QR_FILL_ROWS_SPLIT")) if (atoi(env) > 0) regt = 0;
     if (const char *env = getenv("QR_FILL_ROWS_REGT")) regt = (env[0] == '1' && G <= 1024 && thr0 == (uint32_t)qr::LANE_TERMS) ? 1 : 0;
     if (regt) {
         const uint64_t nh = heavy_count(thr0);
@@ -220,15 +226,131 @@ bool choose_rows_shape(qr_plan *pl)
         for (int sl = sl_hi; sl >= 0; sl--)
             for (int q = q_forced ? q_forced : q_hi; q >= (q_forced ? q_forced : 1); q--) {
                 const int qb = q + sl;
-                if (rows_smem(G, hx, qb, nh) > MAX_SMEM) continue;
+                if (rows_smem(G, hx, qb, nh) > ROWS_SMEM_CAP) continue;
                 int hl = std::max(strip_log2(hx, qb, nh), qb);             // a heavy strip holds whole batches
-                if (hl > 7 || rows_smem(G, hx, qb, nh, hl) > MAX_SMEM) continue;
+                if (hl > 7 || rows_smem(G, hx, qb, nh, hl) > ROWS_SMEM_CAP) continue;
                 pl->rows_th = 512; pl->rows_ng = (int)((G + 511) / 512); pl->rows_q = q; pl->rows_sl = sl;
                 pl->rows_log2r = r ? std::max(r, qb) : 0;
                 pl->rows_hv_thr = thr0; pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = hl; pl->rows_regt = 1;
                 pl->rows_smem_bytes = rows_smem(G, hx, qb, nh, hl); pl->rows_table_terms = hx;
                 return true;
             }
+    }
+
+    // (d) SPLIT: rows of any length.  K1b cuts the sorted masks into trie subtrees of <= 1024 groups; a CTA owns one subtree
+    //     (terms in registers) and writes its contiguous segment of every row.  Chosen when one CTA cannot hold whole rows
+    //     (G > ~2400, or (b)'s term table does not fit) and for term-rich operators with more than 1024 groups.
+    const bool b_fits = G <= 1024 * (uint64_t)ROWS_MAX_NG_1024 && rows_smem(G, n_extra, 1) <= ROWS_SMEM_CAP;
+    int want_split = (G > 1024 && thr0 == (uint32_t)qr::LANE_TERMS && (n_extra >= G || !b_fits)) ? 1 : 0;
+    uint32_t split_s = 1024;
+    if (const char *env = getenv("QR_FILL_ROWS_SPLIT")) {          // "0": never; "<S>": force, subtrees of <= S groups (tests)
+        const int v = atoi(env);
+        want_split = (v > 0 && thr0 == (uint32_t)qr::LANE_TERMS) ? 1 : 0;
+        if (v >= 32 && v <= 1024) split_s = (uint32_t)v;
+    }
+    if (const char *env = getenv("QR_FILL_ROWS_CL")) if (atoi(env) > 1) want_split = 0;
+    if (want_split) {
+        qr::partition_kernel<<<1, qr::K1_THREADS>>>(pl->dev, split_s);
+        uint32_t meta[8] = {0};
+        std::vector<uint32_t> bs, bp;
+        bool ok = cudaGetLastError() == cudaSuccess && cudaMemcpy(meta, pl->dev.meta, sizeof(meta), cudaMemcpyDeviceToHost) == cudaSuccess;
+        const uint32_t nb = meta[2];
+        ok = ok && nb >= 1 && nb <= 32;
+        if (ok) {
+            bs.resize(nb + 1); bp.resize(nb);
+            ok = cudaMemcpy(bs.data(), pl->dev.blk_start, (nb + 1) * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                 cudaMemcpy(bp.data(), pl->dev.blk_p, nb * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        if (!ok) cudaGetLastError();
+        int n_sm = 0;
+        if (ok) ok = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pl->device) == cudaSuccess && n_sm >= (int)nb;
+        if (ok) {
+            uint64_t gmax = 0, gmin = G, nh_max = 0, hx_max = 0, hx_all = 0;
+            for (uint32_t b = 0; b < nb; b++) {
+                uint64_t nh = 0, hx = 0;
+                for (uint64_t g = bs[b]; g < bs[b + 1]; g++)
+                    if (goff[g + 1] - goff[g] > thr0) { nh++; hx += goff[g + 1] - goff[g] - 1; }
+                gmax = std::max<uint64_t>(gmax, bs[b + 1] - bs[b]); gmin = std::min<uint64_t>(gmin, bs[b + 1] - bs[b]);
+                nh_max = std::max(nh_max, nh); hx_max = std::max(hx_max, hx); hx_all += hx;
+            }
+            // Where it pays (profiles/r03_rows_sweep.jsonl): balanced tries of light groups -- random operators with
+            // G = 1500..4000: 4.1-5.3 TB/s against 1.9-4.8 with the lanes kernel.  Molecular Hamiltonians keep their long
+            // groups in the subtree around mask 0 and have small side subtrees: a third of the CTAs then folds all the
+            // heavy terms of every row and 100-group subtrees make 10 KB batches (H10 1.9-2.2 TB/s against 2.5 lanes;
+            // H12 cut at 512: 1.4 against 4.9 whole) -- those stay where they were.
+            if (!getenv("QR_FILL_ROWS_SPLIT") && (gmin < 256 || hx_all * 100 > pl->n_terms_canonical * 20)) ok = false;
+        }
+        if (ok) {
+            uint64_t gmax = 0, nh_max = 0, hx_max = 0;
+            for (uint32_t b = 0; b < nb; b++) {
+                uint64_t nh = 0, hx = 0;
+                for (uint64_t g = bs[b]; g < bs[b + 1]; g++)
+                    if (goff[g + 1] - goff[g] > thr0) { nh++; hx += goff[g + 1] - goff[g] - 1; }
+                gmax = std::max<uint64_t>(gmax, bs[b + 1] - bs[b]); nh_max = std::max(nh_max, nh); hx_max = std::max(hx_max, hx);
+            }
+            const uint64_t si = (gmax + 3) & ~1ull;                // pitch of a buffered row of column ids
+            for (int q = q_forced ? std::min(q_forced, 2) : 2; ok && q >= (q_forced ? std::min(q_forced, 2) : 1); q--) {
+                auto smem_d = [&](int hl) { return (size_t)align_up((si << q) * 48 + hx_max * 20, 16) + (size_t)nh_max * ((16ull << hl) + 32); };
+                int hl = 5;
+                if (smem_d(hl) > ROWS_SMEM_CAP) continue;
+                while (hl < 7 && nh_max != 0 && smem_d(hl + 1) <= ROWS_SMEM_CAP) hl++;
+                qr::RowsSplit &sp = pl->rows_split;
+                sp = qr::RowsSplit{};
+                sp.n = nb;
+                // CTAs in proportion to the subtrees' work (terms folded + entries written per row), at least one each,
+                // n_sm in all
+                std::vector<uint64_t> w(nb);
+                uint64_t w_all = 0;
+                for (uint32_t b = 0; b < nb; b++) { w[b] = (uint64_t)(goff[bs[b + 1]] - goff[bs[b]]) + (bs[b + 1] - bs[b]); w_all += w[b]; }
+                uint32_t given = 0;
+                std::vector<uint32_t> cnt(nb);
+                for (uint32_t b = 0; b < nb; b++) { cnt[b] = std::max<uint32_t>(1, (uint32_t)(w[b] * n_sm / w_all)); given += cnt[b]; }
+                while (given > (uint32_t)n_sm) { uint32_t m = 0; for (uint32_t b = 1; b < nb; b++) if (cnt[b] > cnt[m]) m = b; cnt[m]--; given--; }
+                while (given < (uint32_t)n_sm) {                   // hand the rest to the subtrees with the most work per CTA
+                    uint32_t m = 0;
+                    for (uint32_t b = 1; b < nb; b++) if (w[b] * cnt[m] > w[m] * cnt[b]) m = b;
+                    cnt[m]++; given++;
+                }
+                sp.cta0[0] = 0;
+                for (uint32_t b = 0; b < nb; b++) { sp.g0[b] = bs[b]; sp.level[b] = bp[b]; sp.cta0[b + 1] = sp.cta0[b] + cnt[b]; }
+                sp.g0[nb] = bs[nb];
+                pl->rows_th = 512; pl->rows_ng = (int)((gmax + 511) / 512); pl->rows_q = q; pl->rows_sl = 0; pl->rows_log2r = r ? std::max(r, q) : 0;
+                pl->rows_hv_thr = thr0; pl->rows_hv_cap = (uint32_t)nh_max; pl->rows_hv_log2 = hl; pl->rows_regt = 1;
+                pl->rows_smem_bytes = smem_d(hl); pl->rows_table_terms = hx_max; pl->rows_cl = 0; pl->rows_gc = (uint32_t)gmax;
+                return true;
+            }
+        }
+    }
+
+    // (c) rows too long for one CTA (or term-rich with more than 1024 groups): a cluster of 2 or 4 CTAs splits the groups
+    //     (terms in registers, <= 2 groups per thread) and the rows of every 4-row batch; entries travel to the row's
+    //     owner through distributed shared memory.  Needs an even number of entries per owned row block (16-byte TMA
+    //     alignment of the column ids).
+    //     Measured slower than (b), (d) and mostly the lanes kernel (distributed shared memory moves 17-21 B per cycle and
+    //     SM, about an SM's share of HBM: C3 3.6 TB/s with a cluster of 2 against 6.6 alone; H10 2.0 against 2.5 lanes), so
+    //     it is only taken on request (QR_FILL_ROWS_CL=2|4; tests, sweeps).
+    int want_cl = 0;
+    if (const char *env = getenv("QR_FILL_ROWS_CL")) want_cl = (env[0] != '0' && thr0 == (uint32_t)qr::LANE_TERMS) ? atoi(env) : 0;
+    for (int cl = 2; want_cl && cl <= 4; cl *= 2) {
+        if (want_cl > 1 && cl != want_cl) continue;                // forced size (tests)
+        const uint64_t gc = align_up((G + cl - 1) / cl, 32);
+        const uint64_t rows_own = 4 / cl;
+        if (gc > 1024 || ((rows_own * G) & 1)) continue;
+        uint64_t nh_max = 0, hx_max = 0;
+        for (int c = 0; c < cl; c++) {
+            uint64_t nh = 0, hx = 0;
+            for (uint64_t g = c * gc; g < std::min<uint64_t>(G, (c + 1) * gc); g++)
+                if (goff[g + 1] - goff[g] > thr0) { nh++; hx += goff[g + 1] - goff[g] - 1; }
+            nh_max = std::max(nh_max, nh); hx_max = std::max(hx_max, hx);
+        }
+        auto smem_c = [&](int hl) { return (size_t)align_up(rows_own * G * 48 + hx_max * 20, 16) + (size_t)nh_max * ((16ull << hl) + 32); };
+        int hl = 5;
+        if (smem_c(hl) > ROWS_SMEM_CAP) continue;
+        while (hl < 7 && nh_max != 0 && smem_c(hl + 1) <= ROWS_SMEM_CAP) hl++;
+        pl->rows_th = 512; pl->rows_ng = (int)((gc + 511) / 512); pl->rows_q = 2; pl->rows_sl = 0; pl->rows_log2r = r ? std::max(r, 2) : 0;
+        pl->rows_hv_thr = thr0; pl->rows_hv_cap = (uint32_t)nh_max; pl->rows_hv_log2 = hl; pl->rows_regt = 1;
+        pl->rows_smem_bytes = smem_c(hl); pl->rows_table_terms = hx_max; pl->rows_cl = cl; pl->rows_gc = (uint32_t)gc;
+        return true;
     }
 
     // (b) first term in registers, the others in shared memory.  1024 threads (32 warps hide the shared-memory and
@@ -238,17 +360,17 @@ bool choose_rows_shape(qr_plan *pl)
     if (ng > ROWS_MAX_NG_1024) return false;
     if (q_forced > 2) q_forced = 2;
     for (int q = q_forced ? q_forced : 2; q >= (q_forced ? q_forced : 1); q--) {
-        if (rows_smem(G, n_extra, q) > MAX_SMEM) continue;
+        if (rows_smem(G, n_extra, q) > ROWS_SMEM_CAP) continue;
         uint32_t thr = thr0;
         uint64_t nh = heavy_count(thr);
         // 4-row batches only if every heavy group fits beside them; 2-row batches shed heavy groups (raise
         // the threshold) until the side buffer fits
-        while (nh != 0 && rows_smem(G, n_extra, q, nh) > MAX_SMEM) {
+        while (nh != 0 && rows_smem(G, n_extra, q, nh) > ROWS_SMEM_CAP) {
             if (q == 2 && !q_forced) break;
             thr = thr > 0x7fffffffu ? 0xffffffffu : thr * 2;
             nh = thr == 0xffffffffu ? 0 : heavy_count(thr);
         }
-        if (rows_smem(G, n_extra, q, nh) > MAX_SMEM) continue;
+        if (rows_smem(G, n_extra, q, nh) > ROWS_SMEM_CAP) continue;
         const int hl = strip_log2(n_extra, q, nh);
         pl->rows_th = th; pl->rows_ng = ng; pl->rows_q = q; pl->rows_sl = 0; pl->rows_log2r = r ? std::max(r, q) : 0;   // 0: per window
         pl->rows_hv_thr = nh ? thr : 0xffffffffu; pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = hl; pl->rows_regt = 0;
@@ -533,42 +655,77 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         const uint64_t R = 1ull << k;
         const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
         // the bulk copies need 16-byte aligned global addresses: indices + (s0 - row_lo) * G * 8
-        const bool aligned = (((s0 - row_lo) * G) & 1) == 0;
+        const bool aligned = pl->rows_cl == 0 || (((s0 - row_lo) * G) & 1) == 0;    // split mode handles odd segment starts itself
         if (s1 > s0 && aligned && (s1 - s0) / R <= 0xffffffffull) {
             const uint64_t n_runs = (s1 - s0) / R, n_extra = pl->rows_table_terms;
             const size_t smem = pl->rows_smem_bytes;
-            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
-                                    uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t);
+            using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                                    uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t, const qr::RowsSplit);
             RowsFn kern = nullptr;
 #define QR_ROWS_Q(NG_, TH_, RG_, HV_) \
-            (q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_, RG_, HV_, false> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_, RG_, HV_, false>)
+            (q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_, RG_, HV_, false, 1> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_, RG_, HV_, false, 1>)
 #define QR_ROWS_CASE(NG_, TH_, RG_) \
-            if (q <= 2 && !pl->rows_cnt_smem && pl->rows_ng == NG_ && pl->rows_th == TH_ && pl->rows_regt == (RG_ ? 1 : 0)) \
+            if (q <= 2 && pl->rows_cl == 1 && !pl->rows_cnt_smem && pl->rows_ng == NG_ && pl->rows_th == TH_ && pl->rows_regt == (RG_ ? 1 : 0)) \
                 kern = pl->rows_hv_cap ? QR_ROWS_Q(NG_, TH_, RG_, true) : QR_ROWS_Q(NG_, TH_, RG_, false);
             QR_ROWS_CASE(1, 1024, false) QR_ROWS_CASE(2, 1024, false) QR_ROWS_CASE(3, 1024, false)
             QR_ROWS_CASE(1, 512, true) QR_ROWS_CASE(2, 512, true)
             // one group per thread, terms in registers: 8-row batches and the rank table in shared memory exist here only
 #define QR_ROWS_ONE(Q_, HV_, CS_) \
-            if (pl->rows_ng == 1 && pl->rows_regt && q == Q_ && (pl->rows_hv_cap != 0) == HV_ && (pl->rows_cnt_smem != 0) == CS_) \
-                kern = (RowsFn)qr::fill_rows_kernel<1, Q_, 512, true, HV_, CS_>;
+            if (pl->rows_cl == 1 && pl->rows_ng == 1 && pl->rows_regt && q == Q_ && (pl->rows_hv_cap != 0) == HV_ && (pl->rows_cnt_smem != 0) == CS_) \
+                kern = (RowsFn)qr::fill_rows_kernel<1, Q_, 512, true, HV_, CS_, 1>;
             QR_ROWS_ONE(3, false, false) QR_ROWS_ONE(3, true, false)
             QR_ROWS_ONE(1, false, true) QR_ROWS_ONE(1, true, true) QR_ROWS_ONE(2, false, true) QR_ROWS_ONE(2, true, true)
             QR_ROWS_ONE(3, false, true) QR_ROWS_ONE(3, true, true)
 #undef QR_ROWS_ONE
+            // clusters: terms in registers, 4-row batches
+#define QR_ROWS_CL(NG_, HV_, CL_) \
+            if (pl->rows_cl == CL_ && pl->rows_ng == NG_ && (pl->rows_hv_cap != 0) == HV_) kern = (RowsFn)qr::fill_rows_kernel<NG_, 2, 512, true, HV_, false, CL_>;
+            QR_ROWS_CL(1, false, 2) QR_ROWS_CL(1, true, 2) QR_ROWS_CL(2, false, 2) QR_ROWS_CL(2, true, 2)
+            QR_ROWS_CL(1, false, 4) QR_ROWS_CL(1, true, 4) QR_ROWS_CL(2, false, 4) QR_ROWS_CL(2, true, 4)
+#undef QR_ROWS_CL
+            // split mode: a CTA per trie subtree of <= 1024 groups
+#define QR_ROWS_SPLIT(NG_, HV_) \
+            if (pl->rows_cl == 0 && pl->rows_ng == NG_ && (pl->rows_hv_cap != 0) == HV_) \
+                kern = q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, 512, true, HV_, false, 0> : (RowsFn)qr::fill_rows_kernel<NG_, 1, 512, true, HV_, false, 0>;
+            QR_ROWS_SPLIT(1, false) QR_ROWS_SPLIT(1, true) QR_ROWS_SPLIT(2, false) QR_ROWS_SPLIT(2, true)
+#undef QR_ROWS_SPLIT
 #undef QR_ROWS_Q
 #undef QR_ROWS_CASE
             if (!kern) return fail(QR_ERR_UNSUPPORTED, "fill_rows: no kernel instance for this plan");
             QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 0, n_sm = 0;
-            QR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl->rows_th, smem));
-            QR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pl->device));
-            if (per_sm < 1) return fail(QR_ERR_CUDA, "fill_rows: kernel does not fit on an SM");
-            const uint64_t ctas = std::min<uint64_t>(n_runs, (uint64_t)per_sm * (uint64_t)n_sm);   // persistent CTAs
+            const uint32_t cl = (uint32_t)pl->rows_cl, gc = cl != 1 ? pl->rows_gc : (uint32_t)G;
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3((unsigned)pl->rows_th, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            uint64_t ctas = 0;
+            if (cl > 1) {                                          // persistent clusters: as many as are resident at once
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                cfg.gridDim = dim3(cl, 1, 1);
+                int max_clusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+                    cudaGetLastError();
+                    return fail(QR_ERR_CUDA, "fill_rows: the cluster does not fit on the device");
+                }
+                ctas = std::min<uint64_t>(n_runs, (uint64_t)max_clusters) * cl;
+            } else if (cl == 0) {
+                ctas = pl->rows_split.cta0[pl->rows_split.n];      // fixed at plan creation: CTAs per subtree
+            } else {
+                int per_sm = 0, n_sm = 0;
+                QR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl->rows_th, smem));
+                QR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pl->device));
+                if (per_sm < 1) return fail(QR_ERR_CUDA, "fill_rows: kernel does not fit on an SM");
+                ctas = std::min<uint64_t>(n_runs, (uint64_t)per_sm * (uint64_t)n_sm);   // persistent CTAs
+            }
+            cfg.gridDim = dim3((unsigned)ctas, 1, 1);
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
-            kern<<<(unsigned)ctas, pl->rows_th, smem, st>>>(pl->dev, (uint32_t)G, (uint32_t)n_extra, (uint32_t)k, (uint32_t)pl->rows_sl, (uint32_t)n_runs,
-                                                           pl->rows_hv_thr, pl->rows_hv_cap, (uint32_t)pl->rows_hv_log2, s0, row_lo, indptr_base, d_indptr,
-                                                           d_indices, d_data, row_hi - row_lo);
+            QR_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->dev, (uint32_t)G, gc, (uint32_t)n_extra, (uint32_t)k, (uint32_t)pl->rows_sl, (uint32_t)n_runs,
+                                       pl->rows_hv_thr, pl->rows_hv_cap, (uint32_t)pl->rows_hv_log2, s0, row_lo, indptr_base, d_indptr,
+                                       d_indices, d_data, row_hi - row_lo, pl->rows_split));
             QR_LAUNCH_CHECK("fill_rows_kernel");
             return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
         }

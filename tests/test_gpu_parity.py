@@ -315,6 +315,69 @@ def test_rows_kernel_large_G(monkeypatch, G, T, REGT, Q):
         assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
 
 
+@pytest.mark.parametrize("CL", [2, 4])
+@pytest.mark.parametrize("R", [2, 7])
+@pytest.mark.parametrize("name", ["random_n10", "H6", "tfim_3x3", "H2", "H4", "C1"])
+def test_rows_kernel_clusters(fixtures, monkeypatch, name, R, CL):
+    """Cluster variant of the rows kernel forced on small cases: the CTAs of a cluster split the groups and the rows of a
+    4-row batch and exchange entries through distributed shared memory.  (Odd G with a cluster of 4 needs misaligned
+    single-row copies: the library falls back to the one-CTA variant there -- H4, C1 -- which must still be right.)"""
+    monkeypatch.setenv("QR_FILL_ROWS", "1")
+    monkeypatch.setenv("QR_FILL_ROWS_CL", str(CL))
+    monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    assert plan.fill_kernel == "fill_rows_kernel"
+    G, dim = plan.n_groups, 1 << n
+    assert_same(device_build(plan, 0, dim), ref, f"{name} CL={CL} R={R}")
+    if dim >= 128:
+        for lo, hi in [(6, dim - 2), (32, 64), (dim // 2 - 2, dim // 2 + 34)]:
+            ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
+            assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G])), (lo, hi)
+            assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
+
+
+@pytest.mark.parametrize("S", [32, 64, 1024])
+@pytest.mark.parametrize("R", [1, 2, 7])
+@pytest.mark.parametrize("name", ["random_n10", "H6", "tfim_3x3", "H2", "H4", "C1", "xxz_n10"])
+def test_rows_kernel_split(fixtures, monkeypatch, name, R, S):
+    """Split mode of the rows kernel forced on small cases: the sorted masks are cut into trie subtrees of <= S groups, a
+    CTA owns one subtree and writes its segment of every row (odd segment starts: shifted id buffer + edge stores)."""
+    monkeypatch.setenv("QR_FILL_ROWS", "1")
+    monkeypatch.setenv("QR_FILL_ROWS_SPLIT", str(S))
+    monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    assert plan.fill_kernel == "fill_rows_kernel"
+    G, dim = plan.n_groups, 1 << n
+    assert_same(device_build(plan, 0, dim), ref, f"{name} S={S} R={R}")
+    if dim >= 128:
+        for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 34)]:
+            ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
+            assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G])), (lo, hi)
+            assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
+
+
+@pytest.mark.parametrize("G,T,n", [(2600, 3900, 12), (3001, 3500, 12), (1500, 3600, 12), (2048, 4000, 12), (3998, 4090, 12), (5001, 9000, 13)])
+def test_rows_kernel_split_large_G(G, T, n):
+    """The shapes split mode is chosen for: more than 1024 groups with >= 2 terms per group on average, or rows too long
+    for one CTA's shared memory (any G, odd ones included).  n = 12 / 13: 4096 / 8192 rows of up to 5001 entries."""
+    labels, coeffs = H.random_pauli_sum(n, T, G, 50, 5)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    assert plan.n_groups == G and plan.fill_kernel == "fill_rows_kernel"
+    assert_same(device_build(plan, 0, 1 << n), ref, f"G={G} T={T}")
+    lo, hi = 101, 4000
+    ip, ix, dt = device_build(plan, lo, hi)
+    assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G]))
+    assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
+
+
 def test_rows_kernel_selection(fixtures, monkeypatch):
     """Default choice: staged for rows that fit a 32-row tile, lanes for rows too long for two shared-memory
     batches, rows in between; QR_FILL_ROWS=0 restores the lanes kernel."""
@@ -330,7 +393,11 @@ def test_rows_kernel_selection(fixtures, monkeypatch):
     assert kernel_of(*fixtures["H6"]) == "fill_rows_kernel"                        # G = 286
     big = H.random_pauli_sum(12, 1500, 1100, 50, 5)
     assert kernel_of(*big) == "fill_rows_kernel"
-    assert kernel_of(*H.random_pauli_sum(13, 3500, 3000, 50, 5)) == "fill_lanes_kernel"    # 3000 * 96 B > 227 KB
+    assert kernel_of(*H.random_pauli_sum(13, 3500, 3000, 50, 5)) == "fill_rows_kernel"     # split mode: a CTA per subtree of <= 1024 masks
+    assert kernel_of(*H.random_pauli_sum(13, 5501, 5001, 50, 5)) == "fill_rows_kernel"
+    monkeypatch.setenv("QR_FILL_ROWS_SPLIT", "0")
+    assert kernel_of(*H.random_pauli_sum(13, 5501, 5001, 50, 5)) == "fill_lanes_kernel"    # 5001 * 96 B > 227 KB
+    monkeypatch.delenv("QR_FILL_ROWS_SPLIT")
     monkeypatch.setenv("QR_FILL_ROWS", "0")
     assert kernel_of(*big) == "fill_lanes_kernel"
 

@@ -43,15 +43,15 @@ def main():
     for cfg in a.cfgs.split():
         flags = 0
         for k in ("QR_FILL_CFG", "QR_FILL_LANES", "QR_FILL_LANES_R", "QR_FILL_LANES_W", "QR_FILL_LANES_SYNC",
-                  "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E", "QR_FILL_ROWS", "QR_FILL_ROWS_REGT", "QR_FILL_ROWS_HVS", "QR_FILL_ROWS_SL",
+                  "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E", "QR_FILL_ROWS", "QR_FILL_ROWS_REGT", "QR_FILL_ROWS_HVS", "QR_FILL_ROWS_SL", "QR_FILL_ROWS_CL", "QR_FILL_ROWS_SPLIT",
                   "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R", "QR_FILL_ROWS_HV"):      # the ones a cfg string sets
             os.environ.pop(k, None)
         if cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
-        elif cfg.startswith("rows"):                  # rows[:regt 0|1[:log2(rows per batch)[:log2(rows per run)[:heavy threshold[:log2 heavy strip[:log2 sub-batches]]]]]], "" = default
+        elif cfg.startswith("rows"):                  # rows[:regt 0|1[:log2(rows per batch)[:log2(rows per run)[:heavy threshold[:log2 heavy strip[:log2 sub-batches[:cluster size[:split S]]]]]]]], "" = default
             parts = cfg.split(":")
             os.environ["QR_FILL_ROWS"] = "1"
-            for i, key in enumerate(("QR_FILL_ROWS_REGT", "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R", "QR_FILL_ROWS_HV", "QR_FILL_ROWS_HVS", "QR_FILL_ROWS_SL")):
+            for i, key in enumerate(("QR_FILL_ROWS_REGT", "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R", "QR_FILL_ROWS_HV", "QR_FILL_ROWS_HVS", "QR_FILL_ROWS_SL", "QR_FILL_ROWS_CL", "QR_FILL_ROWS_SPLIT")):
                 if len(parts) > i + 1 and parts[i + 1] != "": os.environ[key] = parts[i + 1]
         elif cfg.startswith("lanes"):                 # lanes[:log2R[:warps[:sync[:persist]]]]
             parts = cfg.split(":")
