@@ -810,7 +810,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
     constexpr uint32_t ROWS_OWN = RT / CLD;                        // CL > 1: rows of a batch this CTA hands to the TMA
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
     // this CTA's groups [gbase, gbase + Gn) and its share jcta, jcta + n_share, ... of the runs
-    uint32_t gbase = crank * Gc, Gn = Gc, jcta = blockIdx.x / CLD, n_share = gridDim.x / CLD, level = 32u, sid = 0u;
+    uint32_t gbase = crank * Gc, Gn = CL == 1 ? G : Gc, jcta = blockIdx.x / CLD, n_share = gridDim.x / CLD, level = 32u, sid = 0u;
     if constexpr (SPLIT) {
         while (sid + 1u < sp.n && blockIdx.x >= sp.cta0[sid + 1u]) sid++;
         gbase = sp.g0[sid]; Gn = sp.g0[sid + 1u] - gbase; level = sp.level[sid];
