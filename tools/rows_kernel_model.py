@@ -109,12 +109,13 @@ def check(name, labels, coeffs, NG, TH, Q, log2R, lo=None, hi=None):
     assert np.array_equal(dt[a:b].view(np.uint64), ref[2][s0 * G:s1 * G].view(np.uint64)), name
     print("ok", name, "G", G, NG, TH, Q, log2R, (lo, hi))
 
-fx = json.load(gzip.open(ROOT / "tests/golden/h_fixtures.json.gz"))
-def fxop(k): return fx[k]["labels"], [complex(a, b) for a, b in fx[k]["coeffs"]]
-check("C1", *H.tfim_chain(12)[:2], 1, 32, 1, 5)
-check("C1q2", *H.tfim_chain(12)[:2], 1, 32, 2, 6, 100, 4000)
-l, c = H.random_pauli_sum(8, 120, 70, 10, 7)
-check("rand", l, c, 3, 32, 1, 4)
-check("rand", l, c, 2, 64, 2, 6, 3, 250)
-check("H4", *fxop("H4"), 2, 32, 2, 5)
-check("H4", *fxop("H4"), 1, 64, 1, 3)
+if __name__ == "__main__" and "--no-run" not in sys.argv:
+    fx = json.load(gzip.open(ROOT / "tests/golden/h_fixtures.json.gz"))
+    def fxop(k): return fx[k]["labels"], [complex(a, b) for a, b in fx[k]["coeffs"]]
+    check("C1", *H.tfim_chain(12)[:2], 1, 32, 1, 5)
+    check("C1q2", *H.tfim_chain(12)[:2], 1, 32, 2, 6, 100, 4000)
+    l, c = H.random_pauli_sum(8, 120, 70, 10, 7)
+    check("rand", l, c, 3, 32, 1, 4)
+    check("rand", l, c, 2, 64, 2, 6, 3, 250)
+    check("H4", *fxop("H4"), 2, 32, 2, 5)
+    check("H4", *fxop("H4"), 1, 64, 1, 3)
