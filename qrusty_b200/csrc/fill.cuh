@@ -600,26 +600,26 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
 }
 
 // ---------------------------------------------------------------------------------
-// Rows kernel (large G whose rows still fit shared memory a few at a time: G <= ~3000).
+// Rows kernel: the default for every operator the staged kernel does not take (host: choose_rows, qrusty_cuda.cu).
 //
-// One persistent CTA owns WHOLE rows, so -- like the staged kernel, and unlike the lanes
-// kernel -- everything it sends to HBM is one sequential stream of full lines issued by the
+// A persistent CTA owns WHOLE rows (split mode: whole row segments), so -- like the staged kernel, and
+// unlike the lanes kernel -- everything it sends to HBM is a sequential stream of full lines issued by the
 // TMA; no LSU store instruction touches global memory and no sector is ever half-written.
 //
-// thread <-> group: thread t keeps groups t, t + TH, ... (<= NG of them) in registers for the
-// whole kernel: mask, first (z, c'), the first-flip slot steps of the lowest Q + 2 row bits.
-// The other terms of a group ("extras": T - G of them in all) sit in shared memory.
-// Rows are visited in batches of RT = 2^Q aligned consecutive rows; the batches of a run of
-// R = 2^log2R rows follow the Gray code of the batch index, so from one batch to the next
-// exactly one row bit b >= Q flips and the slot of group g moves by +-cnt[g][b] (plan.cuh):
+// thread <-> group: a thread keeps its groups (<= NG of them, TH apart) in registers for the whole kernel:
+// mask, slot steps of the lowest row bits, and either the first (z, c') -- the other terms ("extras", T - G of
+// them) sit in a shared-memory table -- or, REGT, up to six (z, c') per group (template parameters below).
+// Rows are visited in batches of RT = 2^Q aligned consecutive rows per thread; the batches of a run of
+// R = 2^log2R rows follow the Gray code of the batch index, so from one batch to the next exactly one row bit
+// b flips and the slot of group g moves by +-cnt[g][b] (plan.cuh):
 //     off(g) += (bit_b(row) just became 1) ? sd : -sd,     sd = bit_b(x_g) ? -cnt[g][b] : +cnt[g][b]
-// (sd for b < Q + 2 is a register, the rest one coalesced L1-resident load per 4 batches).
-// Within a batch the RT rows differ in bits < Q only: slot(row j) = off + sum_{b in j} sd_b.
-// A batch is assembled in one of two shared-memory buffers in final order -- the lanes of a
-// warp hold consecutive sorted groups, whose slots form a few contiguous runs (XOR never
-// splits a trie subtree), so the 16-byte shared stores are mostly conflict-free -- and is
-// handed to the TMA as two bulk copies (RT*G*16 B of data, RT*G*8 B of column ids) while the
-// CTA fills the other buffer.  One barrier per batch.
+// (sd of the two lowest batch bits is a register, the rest one coalesced L1- or shared-memory-resident load
+// per 4 batches).  Within a batch the RT rows differ in bits < Q only: slot(row j) = off + sum_{b in j} sd_b,
+// and popc((r + j) & z) = popc(r & z) + popc(j & z): one POPC per term serves the RT rows.
+// A batch is assembled in one of two shared-memory buffers in final order -- the lanes of a warp hold
+// consecutive sorted groups, whose slots form a few contiguous runs (XOR never splits a trie subtree), so the
+// 16-byte shared stores are mostly conflict-free -- and is handed to the TMA as two bulk copies (data, column
+// ids) while the CTA fills the other buffer.  One barrier per batch.
 //
 // Small G (one group per thread, G <= TH / 2): the CTA's threads split into 2^sl sub-batches of TH >> sl
 // threads, sub-batch s taking rows s*RT .. s*RT + RT - 1 of a batch of RT << sl rows, so that all threads
@@ -632,8 +632,11 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
 // their owners read back; a lane folds up to 4 rows at once, which is what hides the latency of
 // the one dependent FP64 chain per (group, row).
 //
-// Values: sign flips and __dadd_rn in original term order, first term taken as is: the fold
-// of accel.rs:191-205, bit for bit (same helpers as the other fill kernels).
+// Values: first term = sign-bit flip; later terms fma(+-1.0, c', acc) in original term order -- the product
+// is exact, so this is the __dadd_rn fold of accel.rs:191-205 bit for bit, signed zeros included.
+//
+// Dynamic shared memory (host: rows_smem): [2][tile] double2 data | [2][tile] u64 column ids | term table
+// (c' then z) | s_hv [hv_cap][2^hv_log2] double2 | s_h0c [hv_cap] double2 | s_hd [hv_cap] uint4 | s_cnt (CS).
 // ---------------------------------------------------------------------------------
 // ---- thread-block cluster helpers (rows kernel, CL > 1) ----
 __device__ __forceinline__ uint32_t cluster_ctarank()
