@@ -42,6 +42,8 @@ def lib():
         L.oracle_make_row.restype = C.c_size_t
         L.oracle_build_chunked.argtypes = [vp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, vp, vp, vp, u64p]
         L.oracle_build_chunked.restype = C.c_int
+        L.oracle_build_grouped.argtypes = [vp, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp, u64p]
+        L.oracle_build_grouped.restype = C.c_int
         L.oracle_single_pauli.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp]
         L.oracle_single_pauli.restype = None
         L.oracle_spmv.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.c_int]
@@ -132,6 +134,26 @@ def build_csr(params, n_qubits, row_lo=0, row_hi=None, step=1000, n_threads=None
     if rc != 0:
         raise MemoryError("oracle_build_chunked")
     assert nnz.value == cap, (nnz.value, cap)
+    return indptr, indices, data
+
+
+def build_csr_grouped(params, n_qubits, row_lo=0, row_hi=None, n_threads=None, groups=None):
+    """Tuned CPU variant (NOT the reference's algorithm; see oracle_build_grouped): same bytes as build_csr."""
+    params = np.ascontiguousarray(params)
+    dim = 1 << n_qubits
+    row_hi = dim if row_hi is None else row_hi
+    rows = row_hi - row_lo
+    if groups is None:
+        groups = len(np.unique(params["x"]))
+    indptr = np.zeros(rows + 1, np.uint64)
+    indices = np.zeros(rows * groups, np.uint64)
+    data = np.zeros(rows * groups, np.complex128)
+    nnz = C.c_uint64()
+    rc = lib().oracle_build_grouped(_p(params), len(params), n_qubits, row_lo, row_hi, n_threads or hardware_threads(),
+                                    _p(indptr), _p(indices), _p(data), C.byref(nnz))
+    if rc != 0:
+        raise MemoryError("oracle_build_grouped")
+    assert nnz.value == rows * groups
     return indptr, indices, data
 
 

@@ -260,3 +260,25 @@ def test_rawio_layout():
 
 def test_pair_t_layout():
     assert O.PARAM_DTYPE.itemsize == 32
+
+
+def test_tuned_cpu_variant_matches_the_restatement(fixtures):
+    """oracle_build_grouped (the fairness line of bench.py: group-first, closed-form slots, no per-row sort) is not the
+    reference's algorithm, but it must produce the same bytes as the restatement of accel.rs:267-336."""
+    from qrusty_b200 import hamiltonians as H
+    cases = [fixtures["H2"], fixtures["H4"], fixtures["H6"], H.tfim_chain(12), H.xxz_chain(10, 1.0, 0.7),
+             H.random_pauli_sum(10, 300, 200, 30, 7)]
+    for labels, coeffs in cases:
+        n, params = O.make_params(labels, coeffs)
+        ref = O.build_csr(params, n)
+        for threads in (1, 3):
+            got = O.build_csr_grouped(params, n, n_threads=threads)
+            for a, b in zip(got, ref):
+                assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
+        dim = 1 << n
+        if dim >= 64:
+            lo, hi = 5, dim - 3
+            got = O.build_csr_grouped(params, n, lo, hi)
+            want = O.build_csr(params, n, lo, hi)
+            for a, b in zip(got, want):
+                assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
