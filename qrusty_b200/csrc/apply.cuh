@@ -33,8 +33,9 @@ __device__ __forceinline__ void cfma(double &yr, double &yi, double ar, double a
 
 // v0 (gather): thread <-> APPLY_ROWS rows (r, r+256, ...), so a warp's loads of v[r ^ x] stay one
 // permuted, fully coalesced 512-byte segment.  Group descriptors come through shared memory.
-// `diag` (optional): cached values of the mask-0 group for rows [row_lo,row_hi); when given, group 0
-// is not re-evaluated (an eigensolver applies the same operator hundreds of times).
+// `diag` / `diag_re` (optional): cached values of the mask-0 group for rows [row_lo,row_hi) -- complex, or the real parts
+// only when every c' of that group is real (half the bytes); when given, group 0 is not re-evaluated (an eigensolver
+// applies the same operator hundreds of times).
 // Row-sharded form: `peers` (optional) holds one pointer per rank, each pre-offset so that it can
 // be indexed with the GLOBAL row id; the shard that owns v[r ^ x] is rank ^ (x >> shard_bits) for
 // every row of this rank, so the base pointer is a per-group constant (staged beside the
@@ -45,7 +46,8 @@ __global__ void __launch_bounds__(APPLY_THREADS)
 apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
                     const double2 *__restrict__ v, double2 *__restrict__ y,
                     const double2 *__restrict__ diag,
-                    const double2 *const *__restrict__ peers, uint32_t shard_bits)
+                    const double2 *const *__restrict__ peers, uint32_t shard_bits,
+                    const double *__restrict__ diag_re = nullptr)
 {
     constexpr int E = APPLY_ROWS;
     __shared__ GroupDesc sd[APPLY_BATCH];
@@ -64,7 +66,14 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
         yr[e] = 0.0; yi[e] = 0.0;
     }
     uint32_t g_first = 0;
-    if (diag != nullptr) {
+    if (diag_re != nullptr) {                                      // real diagonal (every c' of the mask-0 group is real): 8 B per row
+        g_first = 1;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const double d = __ldcs(&diag_re[(uint64_t)r[e] - row_lo]);     // evict-first: keep L2 for v
+            cfma(yr[e], yi[e], d, 0.0, ld_nc_double2(&v_own[r[e]]), true);
+        }
+    } else if (diag != nullptr) {
         g_first = 1;
 #pragma unroll
         for (int e = 0; e < E; e++) {
@@ -212,13 +221,14 @@ apply_pass_kernel(PlanDev p, ApplyPass ps, uint64_t row_lo, const double2 *__res
 
 // diag(H): only the group with X-mask 0 (gx[0], masks are ascending) touches the diagonal.
 __global__ void __launch_bounds__(256)
-diagonal_kernel(PlanDev p, uint64_t row_lo, uint64_t row_hi, double2 *__restrict__ diag)
+diagonal_kernel(PlanDev p, uint64_t row_lo, uint64_t row_hi, double2 *__restrict__ diag, double *__restrict__ diag_re = nullptr)
 {
     const uint64_t r64 = row_lo + (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (r64 >= row_hi) return;
     double2 d = make_double2(0.0, 0.0);
     if (__ldg(&p.gx[0]) == 0u) d = group_value(p.tz, p.tc, 0u, __ldg(&p.goff[1]), (uint32_t)r64);
-    diag[r64 - row_lo] = d;
+    if (diag_re != nullptr) diag_re[r64 - row_lo] = d.x;          // real group: the imaginary part is a sum of +-0
+    else diag[r64 - row_lo] = d;
 }
 
 // CSR SpMV as rowwise::spmat_dot_densevec does it (accel.rs:355-364): one row per

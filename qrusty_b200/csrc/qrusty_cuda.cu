@@ -77,7 +77,9 @@ struct qr_plan {
     std::map<int, ApplyPlan> apply_plans;       // keyed by log2(rows of the block)
     std::vector<uint32_t> host_gx;
     // cached values of the mask-0 group (diag(H)) for one row range, reused by every apply
-    double2 *diag_cache = nullptr;
+    double2 *diag_cache = nullptr;              // complex values, or (diag_cache_real) doubles in the same allocation
+    bool diag_cache_real = false;
+    int diag_is_real = -1;                      // every c' of the mask-0 group is real (gflag bit 1)
     uint64_t diag_lo = 0, diag_hi = 0;
     int diag_terms = -1;                        // number of terms in group 0 if its mask is 0, else 0
     int device = 0;
@@ -1156,28 +1158,37 @@ static int apply_tile_bits()
 
 // diag(H) of rows [row_lo,row_hi), computed once and reused by every later apply on that range
 // (the mask-0 group is by far the most expensive one: all Z-only strings land in it).
-static int ensure_diag_cache(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, cudaStream_t st, const double2 **out)
+static int ensure_diag_cache(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, cudaStream_t st, const double2 **out,
+                             const double **out_re = nullptr)
 {
     *out = nullptr;
+    if (out_re) *out_re = nullptr;
     const char *off = getenv("QR_APPLY_NO_DIAG_CACHE");
     if (off && off[0] == '1') return QR_OK;
     if (pl->diag_terms < 0) {
-        uint32_t x0 = 1, goff1 = 0;
+        uint32_t x0 = 1, goff1 = 0, flag0 = 0;
         QR_CUDA(cudaMemcpy(&x0, pl->dev.gx, 4, cudaMemcpyDeviceToHost));
         QR_CUDA(cudaMemcpy(&goff1, pl->dev.goff + 1, 4, cudaMemcpyDeviceToHost));
+        QR_CUDA(cudaMemcpy(&flag0, pl->dev.gflag, 4, cudaMemcpyDeviceToHost));
         pl->diag_terms = x0 == 0 ? (int)goff1 : 0;
+        pl->diag_is_real = (flag0 & 2u) ? 1 : 0;
     }
     if (pl->diag_terms < 3) return QR_OK;        // cheaper to recompute than to read 16 B/row
-    if (!pl->diag_cache || pl->diag_lo != row_lo || pl->diag_hi != row_hi) {
+    // callers that can take it get the real parts only (8 B per row instead of 16) when the group is real
+    const char *re_off = getenv("QR_APPLY_DIAG_REAL");
+    const bool want_real = out_re != nullptr && pl->diag_is_real == 1 && !(re_off && re_off[0] == '0');
+    if (!pl->diag_cache || pl->diag_lo != row_lo || pl->diag_hi != row_hi || pl->diag_cache_real != want_real) {
         if (pl->diag_cache) { QR_CUDA(cudaFree(pl->diag_cache)); pl->diag_cache = nullptr; }
-        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&pl->diag_cache), (row_hi - row_lo) * 16));
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&pl->diag_cache), (row_hi - row_lo) * (want_real ? 8 : 16)));
         const uint64_t ctas = (row_hi - row_lo + 255) / 256;
-        qr::diagonal_kernel<<<(unsigned)ctas, 256, 0, st>>>(pl->dev, row_lo, row_hi, pl->diag_cache);
+        qr::diagonal_kernel<<<(unsigned)ctas, 256, 0, st>>>(pl->dev, row_lo, row_hi, want_real ? nullptr : pl->diag_cache,
+                                                            want_real ? reinterpret_cast<double *>(pl->diag_cache) : nullptr);
         QR_LAUNCH_CHECK("diagonal_kernel");
         QR_CUDA(cudaStreamSynchronize(st));      // one-time; later applies may use any stream
-        pl->diag_lo = row_lo; pl->diag_hi = row_hi;
+        pl->diag_lo = row_lo; pl->diag_hi = row_hi; pl->diag_cache_real = want_real;
     }
-    *out = pl->diag_cache;
+    if (want_real) *out_re = reinterpret_cast<const double *>(pl->diag_cache);
+    else *out = pl->diag_cache;
     return QR_OK;
 }
 
@@ -1293,13 +1304,15 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
 {
     const uint64_t rows = row_hi - row_lo;
     const double2 *diag = nullptr;
-    int rc = ensure_diag_cache(pl, row_lo, row_hi, st, &diag);
-    if (rc != QR_OK) return rc;
+    const double *diag_re = nullptr;
     // tiled path: the rows form an aligned power-of-two block of at least one tile
     const bool pow2 = (rows & (rows - 1)) == 0 && (row_lo & (rows - 1)) == 0;
     const char *mode = getenv("QR_APPLY_V0");
     const int K = apply_tile_bits();
-    if (pow2 && rows >= (1ull << K) && mode && mode[0] == '0') {
+    const bool tiled = pow2 && rows >= (1ull << K) && mode && mode[0] == '0';
+    int rc = ensure_diag_cache(pl, row_lo, row_hi, st, &diag, tiled ? nullptr : &diag_re);
+    if (rc != QR_OK) return rc;
+    if (tiled) {
         const int m = 63 - __builtin_clzll(rows);
         ApplyPlan *ap = nullptr;
         rc = make_apply_plan(pl, m, K, &ap);
@@ -1311,7 +1324,7 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
     const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
     const uint64_t ctas = (rows + per_cta - 1) / per_cta;
     if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "apply: row window too large for one launch");
-    qr::apply_direct_kernel<false><<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, nullptr, 0u);
+    qr::apply_direct_kernel<false><<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, nullptr, 0u, diag_re);
     QR_LAUNCH_CHECK("apply_direct_kernel");
     return QR_OK;
 }
