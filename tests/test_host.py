@@ -174,3 +174,6 @@ def test_bench_reference_arm_and_workloads():
         n, params = O.make_params(labels, coeffs)
         assert n == 20 + int(np.log2(world)) and len(labels) == 60 and len(np.unique(params["x"])) == 21
         assert int(params["x"].max()) < 1 << 20 and int(params["z"].max()) < 1 << 20       # spectators untouched
+    # the fairness line: tuned CPU variant, labelled as not the reference's algorithm
+    tuned = bench.cpu_tuned_rate(*H.xxz_chain(12, 1.0, 0.7), runs=2)
+    assert tuned["value"] > 0 and tuned["unit"] == "nnz/s" and "not the reference" in tuned["kind"] and tuned["cores"] >= 1
