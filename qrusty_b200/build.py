@@ -15,7 +15,7 @@ SRC = PKG / "csrc" / "qrusty_cuda.cu"
 OUT = PKG / "lib" / "libqrusty_cuda.so"
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "186",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-shared",
 ]

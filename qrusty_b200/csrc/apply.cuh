@@ -17,6 +17,63 @@ __device__ __forceinline__ double2 ld_nc_double2(const double2 *ptr)
     return r;
 }
 
+// ---- cross-GPU synchronisation through flags in IPC-mapped memory (fused distributed apply) -------------------
+// Every rank owns {ready[P], done[P]} epoch counters; rank q's array is mapped into every peer.  "ready[me] = epoch" on
+// a peer says "my shard of v is complete" (stream order: whatever produced it has finished when the apply kernel starts);
+// "done[me] = epoch" says "I no longer read your shard".  No NCCL call and no host round trip on the path.
+constexpr int APPLY_MAX_PEERS = 16;
+
+__device__ __forceinline__ void st_release_sys(uint64_t *ptr, uint64_t v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *ptr)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag >= epoch; a peer that never arrives must not hang the GPU: trap after 20 s
+__device__ __forceinline__ void wait_flag(const uint64_t *flag, uint64_t epoch)
+{
+    const uint64_t t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) < epoch) {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > 20000000000ull) __trap();
+    }
+}
+
+struct ApplyPeerArgs {
+    const double2 *peer[APPLY_MAX_PEERS];     // v shard of rank q, pre-offset so that it is indexed by the GLOBAL row id
+    uint32_t n_peers, shard_bits;
+};
+
+// One CTA before the fused apply: tell every peer that this rank's shard is complete (stream order: whatever produced it
+// has finished), then wait until the ranks this one reads from have said the same.  The apply kernel follows in stream
+// order, so none of its CTAs needs to look at a flag (measured: a system-scope acquire per CTA cost 5 % of the kernel).
+__global__ void p2p_ready_kernel(uint64_t *flags_local, uint64_t *const *peer_flags_dev, uint32_t n_peers, uint32_t my_rank,
+                                 uint32_t need_mask, uint64_t epoch)
+{
+    const uint32_t q = threadIdx.x;
+    if (q < n_peers && q != my_rank) st_release_sys(peer_flags_dev[q] + my_rank, epoch);
+    if (q < n_peers && ((need_mask >> q) & 1u)) wait_flag(flags_local + q, epoch);
+}
+// ... and one after it: tell every peer that this rank no longer reads their shards, then wait until the ranks that read
+// this rank's shard (the same set) have said so -- whatever the stream runs next may overwrite the shard.
+__global__ void p2p_done_kernel(uint64_t *flags_local, uint64_t *const *peer_flags_dev, uint32_t n_peers, uint32_t my_rank,
+                                uint32_t need_mask, uint64_t epoch)
+{
+    const uint32_t q = threadIdx.x;
+    if (q < n_peers && q != my_rank) st_release_sys(peer_flags_dev[q] + n_peers + my_rank, epoch);
+    if (q < n_peers && ((need_mask >> q) & 1u)) wait_flag(flags_local + n_peers + q, epoch);
+}
+
 // v0: lane <-> row, walk the groups.  For 32 aligned consecutive rows the gather
 // v[r ^ x] is one aligned 512-byte segment with lanes permuted, so every load is
 // fully coalesced; re-use across groups is left to L1/L2.
@@ -24,11 +81,14 @@ constexpr int APPLY_THREADS = 256;
 constexpr int APPLY_ROWS = 4;          // rows per thread: group descriptors are read once per 4 rows
 constexpr int APPLY_BATCH = 128;       // descriptors staged in shared memory at a time (4 KB)
 
-// acc += a * w, with the 2-FMA form when a is known to be real (warp-uniform flag)
+// acc += a * w, with the 2-FMA form when a is known to be real (warp-uniform flag).  The FMA sequence is spelled out so
+// that every kernel that walks the groups in the same order (gather, tiled, fused distributed) rounds identically: left
+// to the compiler, the contraction of `ar*w.x - ai*w.y` differs from one instantiation to the next.
 __device__ __forceinline__ void cfma(double &yr, double &yi, double ar, double ai, double2 w, bool a_real)
 {
-    if (a_real) { yr += ar * w.x; yi += ar * w.y; }
-    else { yr += ar * w.x - ai * w.y; yi += ar * w.y + ai * w.x; }
+    yr = __fma_rn(ar, w.x, yr);
+    yi = __fma_rn(ar, w.y, yi);
+    if (!a_real) { yr = __fma_rn(-ai, w.y, yr); yi = __fma_rn(ai, w.x, yi); }
 }
 
 // v0 (gather): thread <-> APPLY_ROWS rows (r, r+256, ...), so a warp's loads of v[r ^ x] stay one
@@ -36,25 +96,29 @@ __device__ __forceinline__ void cfma(double &yr, double &yi, double ar, double a
 // `diag` / `diag_re` (optional): cached values of the mask-0 group for rows [row_lo,row_hi) -- complex, or the real parts
 // only when every c' of that group is real (half the bytes); when given, group 0 is not re-evaluated (an eigensolver
 // applies the same operator hundreds of times).
-// Row-sharded form: `peers` (optional) holds one pointer per rank, each pre-offset so that it can
-// be indexed with the GLOBAL row id; the shard that owns v[r ^ x] is rank ^ (x >> shard_bits) for
-// every row of this rank, so the base pointer is a per-group constant (staged beside the
-// descriptor) and remote shards are read in place over NVLink -- the collective is fused into
-// the apply.  Without `peers`, v is the full vector in local memory.
-template <bool PEERS>
-__global__ void __launch_bounds__(APPLY_THREADS)
+// Row-sharded form (pa.n_peers > 1): the shard that owns v[r ^ x] is rank ^ (x >> shard_bits) for every row of this rank,
+// so the base pointer is a per-group constant (staged beside the descriptor) and remote shards are read in place over
+// NVLink -- the collective is fused into the apply.  p2p_ready_kernel / p2p_done_kernel bracket it.
+// One kernel for both forms: the unsharded and the distributed apply run the same instruction sequence and agree bit for
+// bit.  Measured and dropped (profiles/r04_summary.md): requesting the remote partners first with cp.async into shared
+// memory (2.3x slower: LDGSTS to peer memory), pulling them by TMA into a tile (apply_tile.cuh, slower at 2 GPUs).
+__global__ void __launch_bounds__(APPLY_THREADS, 4)
 apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
                     const double2 *__restrict__ v, double2 *__restrict__ y,
-                    const double2 *__restrict__ diag,
-                    const double2 *const *__restrict__ peers, uint32_t shard_bits,
-                    const double *__restrict__ diag_re = nullptr)
+                    const double2 *__restrict__ diag, const double *__restrict__ diag_re,
+                    const __grid_constant__ ApplyPeerArgs pa,
+                    const uint32_t *__restrict__ glist = nullptr, uint32_t n_list = 0)
 {
+    // glist (optional): apply only these groups (ascending ids; the mask-0 group, when cached in diag, first) --
+    // the NEAR pass of the two-pass apply (apply_tile.cuh)
+    if (glist != nullptr) G = n_list;
     constexpr int E = APPLY_ROWS;
     __shared__ GroupDesc sd[APPLY_BATCH];
-    __shared__ const double2 *sv[PEERS ? APPLY_BATCH : 1];
+    __shared__ const double2 *sv[APPLY_BATCH];
+    const bool PEERS = pa.n_peers > 1u;
     const uint64_t cta_base = row_lo + (uint64_t)blockIdx.x * (APPLY_THREADS * E);
-    const uint32_t my_rank = PEERS ? (uint32_t)(row_lo >> shard_bits) : 0u;
-    const double2 *v_own = PEERS ? peers[my_rank] : v;
+    const uint32_t my_rank = PEERS ? (uint32_t)(row_lo >> pa.shard_bits) : 0u;
+    const double2 *v_own = PEERS ? pa.peer[my_rank] : v;
     uint32_t r[E];
     bool live[E];
     double yr[E], yi[E];
@@ -65,6 +129,7 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
         r[e] = (uint32_t)(live[e] ? r64 : row_hi - 1);          // clamp: dead rows recompute a live one
         yr[e] = 0.0; yi[e] = 0.0;
     }
+    const uint32_t G_main = G;
     uint32_t g_first = 0;
     if (diag_re != nullptr) {                                      // real diagonal (every c' of the mask-0 group is real): 8 B per row
         g_first = 1;
@@ -81,18 +146,18 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
             cfma(yr[e], yi[e], d.x, d.y, ld_nc_double2(&v_own[r[e]]), false);
         }
     }
-    for (uint32_t g0 = g_first; g0 < G; g0 += APPLY_BATCH) {
-        const uint32_t nb = min((uint32_t)APPLY_BATCH, G - g0);
+    for (uint32_t g0 = g_first; g0 < G_main; g0 += APPLY_BATCH) {
+        const uint32_t nb = min((uint32_t)APPLY_BATCH, G_main - g0);
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < nb; i += APPLY_THREADS) {
-            const GroupDesc d = p.gdesc[g0 + i];
+            const GroupDesc d = p.gdesc[glist != nullptr ? __ldg(&glist[g0 + i]) : g0 + i];
             sd[i] = d;
-            if (PEERS) sv[i] = peers[my_rank ^ (d.x >> shard_bits)];
+            sv[i] = PEERS ? pa.peer[my_rank ^ (d.x >> pa.shard_bits)] : v;
         }
         __syncthreads();
         for (uint32_t k = 0; k < nb; k++) {
             const GroupDesc d = sd[k];
-            const double2 *vb = PEERS ? sv[k] : v;
+            const double2 *vb = sv[k];
             const bool real = (d.flag & 2u) != 0u;
             if (d.flag & 1u) {
 #pragma unroll

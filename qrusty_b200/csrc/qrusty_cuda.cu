@@ -22,6 +22,7 @@
 
 #include "../../include/qrusty_cuda.h"
 #include "apply.cuh"
+#include "apply_tile.cuh"
 #include "canonicalise.cuh"
 #include "compact.cuh"
 #include "fill.cuh"
@@ -72,9 +73,27 @@ struct ApplyPlan {
     void *slab = nullptr;
 };
 
+// Tiled H.v plan for one aligned block of 2^m rows cut at bit d (apply_tile.cuh): which groups are FAR
+// (served from shared memory), the chunks a tile loads, the NEAR groups left to the gather
+struct TilePlan {
+    bool ok = false;
+    uint32_t m = 0, d = 0, log2_run = 0, n_row_slots = 0, stages = 0, n_far = 0, n_near = 0, e = 4;
+    uint32_t need_mask = 0;                     // other blocks (ranks) whose memory this block reads
+    bool own_loaded = true;                     // the row slots are chunks 0.. of the tile
+    struct Load { uint32_t block, lambda, xi; };
+    std::vector<Load> loads;
+    std::vector<uint32_t> far_host;             // the groups this plan serves from shared memory
+    void *slab = nullptr;
+    const uint32_t *d_far = nullptr, *d_near = nullptr;
+    const uint8_t *d_part = nullptr;
+    size_t smem = 0;
+};
+
 struct qr_plan {
     qr::PlanDev dev{};
     std::map<int, ApplyPlan> apply_plans;       // keyed by log2(rows of the block)
+    std::map<uint64_t, TilePlan> tile_plans;    // keyed by (m, block, d, fused)
+    int n_sm = 0;                               // multiprocessors of the plan's device
     std::vector<uint32_t> host_gx;
     // cached values of the mask-0 group (diag(H)) for one row range, reused by every apply
     double2 *diag_cache = nullptr;              // complex values, or (diag_cache_real) doubles in the same allocation
@@ -115,10 +134,14 @@ struct qr_plan {
 struct qr_comm {
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0, device = 0;
-    // qr_apply_p2p: device table of pre-offset peer shard pointers, barrier scratch
-    const double2 **d_peers = nullptr;
-    std::vector<const void *> host_peers;
+    // qr_apply_p2p without flags: scratch of the two NCCL all-reduce barriers
     double *d_scratch = nullptr;
+    // qr_apply_p2p, tiled path: {ready[P], done[P]} epoch flags of every rank, IPC-mapped (apply_tile.cuh)
+    uint64_t *d_flags = nullptr;                // this rank's flags + a CTA counter behind them
+    uint64_t *peer_flags[qr::TILE_MAX_PEERS] = {nullptr};
+    uint64_t **d_peer_flags = nullptr;          // the same table in device memory (p2p_ready_kernel / p2p_done_kernel)
+    bool flags_ok = false;
+    uint64_t epoch = 0;
 };
 
 namespace {
@@ -493,6 +516,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     qr_plan *pl = new (std::nothrow) qr_plan();
     if (!pl) return fail(QR_ERR_OOM, "qr_plan_create: host allocation failed");
     pl->device = device; pl->n_qubits = n_qubits; pl->dim = dim; pl->n_terms = n_terms;
+    if (cudaDeviceGetAttribute(&pl->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || pl->n_sm < 1) { cudaGetLastError(); pl->n_sm = 148; }
     pl->merge_dups = (flags & QR_PLAN_MERGE_DUPLICATES) ? 1u : 0u;
 
     const size_t T = n_terms;
@@ -558,6 +582,7 @@ extern "C" int qr_plan_destroy(qr_plan *pl)
     if (!pl) return QR_OK;
     cudaSetDevice(pl->device);
     for (auto &kv : pl->apply_plans) if (kv.second.slab) cudaFree(kv.second.slab);
+    for (auto &kv : pl->tile_plans) if (kv.second.slab) cudaFree(kv.second.slab);
     if (pl->diag_cache) cudaFree(pl->diag_cache);
     if (pl->dot_partials) cudaFree(pl->dot_partials);
     if (pl->slab) cudaFree(pl->slab);
@@ -1300,6 +1325,207 @@ static int launch_apply_passes(qr_plan *pl, ApplyPlan *ap, uint64_t row_lo, uint
     return QR_OK;
 }
 
+
+// ---- tiled apply (apply_tile.cuh): plan ------------------------------------------------------------
+static int host_masks(qr_plan *pl)
+{
+    if (pl->host_gx.empty()) {
+        pl->host_gx.resize(pl->n_groups);
+        QR_CUDA(cudaMemcpy(pl->host_gx.data(), pl->dev.gx, pl->n_groups * 4, cudaMemcpyDeviceToHost));
+    }
+    return QR_OK;
+}
+
+constexpr size_t TILE_SMEM_CAP = MAX_SMEM - 2048;
+// run kernel shape: threads per CTA, rows per thread and chunk, CTAs per SM (registers: 65536 / (threads * CTAs))
+struct RunShape { int threads, e, minb; };
+static RunShape run_shape(uint32_t R)
+{
+    RunShape s = R >= 2048 ? RunShape{512, 4, 1} : RunShape{256, 4, 3};
+    if (const char *env = getenv("QR_APPLY_RUN_SHAPE")) {                 // "threads,e,ctas" (sweeps)
+        int t = 0, e = 0, b = 0;
+        if (sscanf(env, "%d,%d,%d", &t, &e, &b) == 3 && (uint32_t)(t * e) <= R) s = RunShape{t, e, b};
+    }
+    return s;
+}
+
+
+// What a tile kernel launch does with the groups of a block of 2^m rows:
+//   TILE_FAR    rows cut at bit d: a tile = one run in each of the 2^(m-d) slices; groups whose mask has a bit >= d (and
+//               none between the run and d) come from shared memory, y += ...; nothing is gathered  (second pass)
+//   TILE_LOCAL  a tile = one contiguous run of 2^lr rows; groups whose mask lies inside the run come from shared memory,
+//               every other group that is not `excluded` is gathered through L1/L2 by the same kernel  (first / only pass)
+//   TILE_P2P    TILE_LOCAL on a rank's shard, plus the runs of the peers' shards pulled over NVLink by the TMA
+enum TileRole { TILE_FAR = 0, TILE_LOCAL = 1, TILE_P2P = 2 };
+
+static int make_tile_plan(qr_plan *pl, uint32_t m, uint32_t blk, uint32_t d, TileRole role, bool skip_diag,
+                          const TilePlan *excluded, TilePlan **out)
+{
+    const uint64_t key = (uint64_t)m | ((uint64_t)d << 8) | ((uint64_t)role << 16) | ((uint64_t)(skip_diag ? 1 : 0) << 20) |
+                         ((uint64_t)(excluded ? excluded->d : 0) << 24) | ((uint64_t)blk << 32);
+    auto it = pl->tile_plans.find(key);
+    if (it != pl->tile_plans.end()) { *out = &it->second; return QR_OK; }
+    int rc = host_masks(pl);
+    if (rc != QR_OK) return rc;
+    const std::vector<uint32_t> &gx = pl->host_gx;
+    const uint32_t G = (uint32_t)pl->n_groups;
+    TilePlan tp;
+    tp.m = m; tp.d = d;
+    const uint32_t nrs = 1u << (m - d);
+    auto hi_of = [&](uint32_t x) { return (uint32_t)((uint64_t)x >> d); };          // d may be 32
+    auto blk_of = [&](uint32_t x) { return (uint32_t)((uint64_t)x >> m); };
+    std::vector<char> skip(G, 0);
+    if (excluded) for (uint32_t g : excluded->far_host) skip[g] = 1;
+    if (skip_diag && gx[0] == 0u) skip[0] = 1;
+    std::vector<uint32_t> far, near;
+    std::vector<uint8_t> part;
+    int lr_hi = (int)std::min<uint32_t>(11, d);
+    if (const char *env = getenv("QR_APPLY_LR")) { int v = atoi(env); if (v >= 5 && v <= 13 && role != TILE_FAR) lr_hi = std::min<int>(v, (int)d); }
+    if (nrs <= (uint32_t)qr::TILE_MAX_ROWSLOTS && (role == TILE_FAR || nrs == 1)) {
+        for (int lr = lr_hi; lr >= 5 && !tp.ok; lr--) {
+            const uint32_t R = 1u << lr;
+            if ((uint64_t)nrs * R < (uint64_t)(role == TILE_FAR ? qr::TILE_THREADS : 1024)) break;   // a tile is at least one chunk of rows
+            std::vector<TilePlan::Load> loads;
+            // the row slots themselves -- except in the fused distributed apply, where the local groups are gathered through
+            // L1/L2 (measured: the gather kernel beats shared-memory tiles for local partners) and only peers' runs are chunks
+            const bool own = role != TILE_P2P || getenv("QR_P2P_OWN_RUN") != nullptr;
+            if (own) for (uint32_t l = 0; l < nrs; l++) loads.push_back({blk, l, 0u});
+            far.clear(); part.clear(); near.clear();
+            std::vector<char> is_far(G, 0);
+            for (uint32_t g = 0; g < G; g++) {
+                if (skip[g] || far.size() >= (size_t)qr::TILE_MAX_FAR) continue;
+                const uint32_t x = gx[g], xb = blk_of(x), xl = hi_of(x) & (nrs - 1u);
+                const uint32_t xi = (uint32_t)(((uint64_t)x & ((1ull << d) - 1ull)) >> lr);
+                if (role == TILE_FAR && hi_of(x) == 0) continue;                    // the first pass's group
+                if (role == TILE_FAR && xi != 0) continue;                          // a bit between the run and the cut: gathered by the first pass
+                if (role == TILE_LOCAL && (xb != 0 || xi != 0)) continue;           // outside the run: gathered
+                if (role == TILE_P2P && xb == 0 && (xi != 0 || !own)) continue;     // local: gathered (always, unless the own run is a chunk)
+                const size_t keep = loads.size();
+                std::vector<uint8_t> pr(nrs);
+                bool ok = true;
+                for (uint32_t l = 0; l < nrs && ok; l++) {
+                    const TilePlan::Load want{blk ^ xb, l ^ xl, xi};
+                    size_t j = 0;
+                    for (; j < loads.size(); j++)
+                        if (loads[j].block == want.block && loads[j].lambda == want.lambda && loads[j].xi == want.xi) break;
+                    if (j == loads.size()) {
+                        if (loads.size() >= (size_t)qr::TILE_MAX_LOAD) { ok = false; break; }
+                        loads.push_back(want);
+                    }
+                    pr[l] = (uint8_t)j;
+                }
+                // a remote run costs a chunk of its own: stop taking them when two stages no longer fit (the rest is gathered)
+                if (ok && loads.size() > keep && loads.size() * (size_t)R * 16 + 16384 > (role == TILE_FAR ? TILE_SMEM_CAP / 2 : (TILE_SMEM_CAP - 2048) / (size_t)run_shape(R).minb - 1024)) ok = false;
+                if (!ok) { loads.resize(keep); continue; }
+                far.push_back(g); is_far[g] = 1;
+                part.insert(part.end(), pr.begin(), pr.end());
+            }
+            if (far.empty()) continue;
+            if (role != TILE_FAR) {
+                for (uint32_t g = 0; g < G; g++) if (!skip[g] && !is_far[g]) near.push_back(g);
+                if (near.size() > (size_t)qr::TILE_MAX_NEAR) break;
+            }
+            const size_t fixed = 64 + far.size() * sizeof(qr::GroupDesc) + near.size() * (sizeof(qr::GroupDesc) + 8) + far.size() * std::max<size_t>(nrs, 4) + 64;
+            const size_t stage_bytes = loads.size() * (size_t)R * 16;
+            size_t stages;
+            if (role == TILE_FAR) {
+                if (fixed + 2 * stage_bytes > TILE_SMEM_CAP) continue;              // try shorter runs
+                stages = std::min<size_t>(3, (TILE_SMEM_CAP - fixed) / stage_bytes);
+                if (const char *env = getenv("QR_APPLY_TILE_STAGES")) { int v = atoi(env); if (v >= 1 && (size_t)v <= stages) stages = (size_t)v; }
+            } else {
+                // run kernel: one tile per CTA, two CTAs (512 threads) or four (256) per SM must fit
+                const size_t per_cta = (TILE_SMEM_CAP - 2048) / (size_t)run_shape(R).minb - 1024;
+                if (fixed + stage_bytes > per_cta) continue;
+                stages = 1;
+                if (const char *env = getenv("QR_APPLY_RUN_STAGES")) { int v = atoi(env); if (v >= 1 && v <= 3 && fixed + (size_t)v * stage_bytes <= per_cta) stages = (size_t)v; }
+            }
+            const uint64_t tile_rows = (uint64_t)nrs * R;
+            tp.ok = true; tp.log2_run = (uint32_t)lr; tp.n_row_slots = nrs; tp.stages = (uint32_t)stages;
+            tp.n_far = (uint32_t)far.size(); tp.n_near = (uint32_t)near.size();
+            tp.e = tile_rows % (qr::TILE_THREADS * 4) == 0 ? 4 : tile_rows % (qr::TILE_THREADS * 2) == 0 ? 2 : 1;
+            tp.loads = loads;
+            tp.own_loaded = own;
+            tp.far_host = far;
+            tp.smem = fixed + stages * stage_bytes;
+        }
+    }
+    if (tp.ok) {
+        for (uint32_t g = 0; g < G; g++) if (blk_of(gx[g]) != 0) tp.need_mask |= 1u << ((blk ^ blk_of(gx[g])) & 31u);
+        const size_t b_far = align_up(far.size() * 4, 16), b_near = align_up(near.size() * 4 + 4, 16), b_part = align_up(part.size(), 16);
+        std::vector<unsigned char> host(b_far + b_near + b_part, 0);
+        memcpy(host.data(), far.data(), far.size() * 4);
+        memcpy(host.data() + b_far, near.data(), near.size() * 4);
+        memcpy(host.data() + b_far + b_near, part.data(), part.size());
+        QR_CUDA(cudaMalloc(&tp.slab, host.size()));
+        cudaError_t e = cudaMemcpy(tp.slab, host.data(), host.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(tp.slab); return fail(QR_ERR_CUDA, std::string("make_tile_plan: ") + cudaGetErrorString(e)); }
+        unsigned char *b = static_cast<unsigned char *>(tp.slab);
+        tp.d_far = reinterpret_cast<const uint32_t *>(b);
+        tp.d_near = reinterpret_cast<const uint32_t *>(b + b_far);
+        tp.d_part = b + b_far + b_near;
+    }
+    *out = &(pl->tile_plans[key] = tp);
+    return QR_OK;
+}
+
+// fills the per-call part of the kernel arguments; block_ptr(q) = element 0 of block q of v
+template <typename BlockPtr>
+static void tile_args(const qr_plan *pl, const TilePlan &tp, uint32_t blk, BlockPtr block_ptr, qr::ApplyTileArgs &a)
+{
+    a = qr::ApplyTileArgs{};
+    for (size_t j = 0; j < tp.loads.size(); j++) {
+        a.base[j] = block_ptr(tp.loads[j].block) + ((uint64_t)tp.loads[j].lambda << tp.d);
+        a.xi[j] = tp.loads[j].xi;
+    }
+    for (uint32_t l = 0; l < tp.n_row_slots; l++) a.row0[l] = (uint32_t)(((uint64_t)blk << tp.m) + ((uint64_t)l << tp.d));
+    a.n_load = (uint32_t)tp.loads.size(); a.n_row_slots = tp.n_row_slots; a.log2_run = tp.log2_run;
+    a.n_tiles = (uint32_t)((1ull << tp.d) >> tp.log2_run); a.stages = tp.stages;
+    a.n_far = tp.n_far; a.n_near = tp.n_near; a.block_bits = tp.m; a.my_block = blk;
+    a.far_groups = tp.d_far; a.far_part = tp.d_part; a.near_groups = tp.d_near;
+    a.own_loaded = tp.own_loaded ? 1u : 0u;
+    (void)pl;
+}
+
+template <bool NEAR>
+static int launch_tile(qr_plan *pl, const TilePlan &tp, const qr::ApplyTileArgs &a, uint64_t row_lo, double2 *y,
+                       const double2 *diag, const double *diag_re, cudaStream_t st)
+{
+    using Fn = void (*)(qr::PlanDev, const qr::ApplyTileArgs, uint64_t, double2 *, const double2 *, const double *);
+    Fn kern = tp.e == 4 ? (Fn)qr::apply_tile_kernel<NEAR, 4> : tp.e == 2 ? (Fn)qr::apply_tile_kernel<NEAR, 2> : (Fn)qr::apply_tile_kernel<NEAR, 1>;
+    QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)pl->n_sm);
+    kern<<<grid, qr::TILE_THREADS, tp.smem, st>>>(pl->dev, a, row_lo, y, diag, diag_re);
+    QR_LAUNCH_CHECK("apply_tile_kernel");
+    return QR_OK;
+}
+
+static int launch_run(qr_plan *pl, const TilePlan &tp, const qr::ApplyTileArgs &a, uint64_t row_lo, double2 *y,
+                      const double2 *diag, const double *diag_re, cudaStream_t st)
+{
+    using Fn = void (*)(qr::PlanDev, const qr::ApplyTileArgs, uint64_t, double2 *, const double2 *, const double *);
+    const RunShape sh = run_shape(1u << tp.log2_run);
+    Fn kern = nullptr;
+#define QR_RUN(T_, E_, B_) if (sh.threads == T_ && sh.e == E_ && sh.minb == B_) kern = (Fn)qr::apply_run_kernel<T_, E_, B_>;
+    QR_RUN(256, 4, 3) QR_RUN(256, 4, 2) QR_RUN(256, 2, 4) QR_RUN(256, 4, 4) QR_RUN(512, 4, 1) QR_RUN(512, 2, 2) QR_RUN(512, 4, 2) QR_RUN(1024, 2, 1) QR_RUN(1024, 1, 1)
+#undef QR_RUN
+    if (!kern) return fail(QR_ERR_INVALID, "apply_run: no kernel instance for QR_APPLY_RUN_SHAPE");
+    QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
+    // one tile per CTA unless the plan holds a ring of stages (then one persistent CTA per resident slot)
+    const uint64_t resident = (uint64_t)pl->n_sm * sh.minb;
+    const unsigned grid = (unsigned)(tp.stages > 1 ? std::min<uint64_t>(a.n_tiles, resident) : a.n_tiles);
+    kern<<<grid, sh.threads, tp.smem, st>>>(pl->dev, a, row_lo, y, diag, diag_re);
+    QR_LAUNCH_CHECK("apply_run_kernel");
+    return QR_OK;
+}
+
+// bit at which the two-pass apply cuts the rows: masks below it are gathered through L2 (the window they span,
+// 2^d * 16 B, must stay resident beside the streaming y and diag), masks at or above it go through shared memory
+static uint32_t apply_cut_bit()
+{
+    if (const char *env = getenv("QR_APPLY_D")) { int v = atoi(env); if (v == 0 || (v >= 10 && v <= 32)) return (uint32_t)v; }
+    return 21;
+}
+
 static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double2 *v, double2 *y, cudaStream_t st)
 {
     const uint64_t rows = row_hi - row_lo;
@@ -1324,7 +1550,39 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
     const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
     const uint64_t ctas = (rows + per_cta - 1) / per_cta;
     if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "apply: row window too large for one launch");
-    qr::apply_direct_kernel<false><<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, nullptr, 0u, diag_re);
+    // Tiled apply (apply_tile.cuh).  The gather kernel is bound by L2 throughput (ncu, C4: 11.9 GB through L2 for 1.3 GB
+    // compulsory), so from 2^20 rows up a CTA takes a contiguous run of v into shared memory with the TMA and serves every
+    // group whose mask lies inside the run from there; the others are gathered by the same kernel.  When the block is larger
+    // than the window L2 can hold (m > cut bit) a second pass adds the groups with a bit at or above the cut from
+    // shared-memory tiles that span the top row bits (y += ...) instead of missing L2 once per group and row.
+    const char *tile_env = getenv("QR_APPLY_TILE");
+    const uint32_t m_blk = pow2 ? (uint32_t)(63 - __builtin_clzll(rows)) : 0u;
+    uint32_t min_m = 20;
+    if (const char *env = getenv("QR_APPLY_TILE_MIN")) { int v = atoi(env); if (v >= 9 && v <= 32) min_m = (uint32_t)v; }   // tests
+    if (pow2 && m_blk >= min_m && !(mode && mode[0] == '1') && tile_env && tile_env[0] == '1') {
+        const uint32_t blk = (uint32_t)(row_lo >> m_blk), d0 = apply_cut_bit();
+        const bool use_diag = diag != nullptr || diag_re != nullptr;
+        TilePlan *tb = nullptr, *ta = nullptr;
+        if (d0 != 0 && m_blk > d0) {
+            rc = make_tile_plan(pl, m_blk, blk, std::max(d0, m_blk - 7u), TILE_FAR, false, nullptr, &tb);
+            if (rc != QR_OK) return rc;
+            if (!tb->ok) tb = nullptr;
+        }
+        rc = make_tile_plan(pl, m_blk, blk, m_blk, TILE_LOCAL, use_diag, tb, &ta);
+        if (rc != QR_OK) return rc;
+        if (ta->ok) {
+            auto block_ptr = [&](uint32_t q) { return v + ((uint64_t)q << m_blk); };
+            qr::ApplyTileArgs a;
+            tile_args(pl, *ta, blk, block_ptr, a);
+            a.peer[0] = v; a.n_peers = 1;
+            rc = launch_run(pl, *ta, a, row_lo, y, diag, diag_re, st);
+            if (rc != QR_OK || tb == nullptr) return rc;
+            tile_args(pl, *tb, blk, block_ptr, a);
+            a.accumulate = 1u;
+            return launch_tile<false>(pl, *tb, a, row_lo, y, nullptr, nullptr, st);
+        }
+    }
+    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re, qr::ApplyPeerArgs{});
     QR_LAUNCH_CHECK("apply_direct_kernel");
     return QR_OK;
 }
@@ -1687,6 +1945,42 @@ extern "C" int qr_comm_create(const void *id, int n_ranks, int rank, int device,
     if (!cm) return fail(QR_ERR_OOM, "qr_comm_create: host allocation failed");
     cm->comm = c; cm->n_ranks = n_ranks; cm->rank = rank; cm->device = device;
     *out = cm;
+    // Epoch flags for the fused apply, exchanged over the communicator itself: every rank allocates
+    // {ready[P], done[P], counter}, all-gathers the CUDA IPC handles and maps its peers' arrays.  If any step
+    // fails (IPC unavailable, peers in one process) the fused apply keeps its NCCL-barrier form.
+    if (n_ranks > 1 && n_ranks <= qr::TILE_MAX_PEERS) {
+        const size_t flag_bytes = 4096;
+        cudaIpcMemHandle_t *d_handles = nullptr;
+        std::vector<cudaIpcMemHandle_t> handles((size_t)n_ranks);
+        bool ok = cudaMalloc(reinterpret_cast<void **>(&cm->d_flags), flag_bytes) == cudaSuccess &&
+                  cudaMemset(cm->d_flags, 0, flag_bytes) == cudaSuccess &&
+                  cudaIpcGetMemHandle(&handles[rank], cm->d_flags) == cudaSuccess &&
+                  cudaMalloc(reinterpret_cast<void **>(&d_handles), sizeof(cudaIpcMemHandle_t) * n_ranks) == cudaSuccess &&
+                  cudaMemcpy(d_handles + rank, &handles[rank], sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice) == cudaSuccess;
+        // every rank takes part in the collective whatever its local outcome (a rank that failed sends zeros)
+        if (!ok && d_handles == nullptr) cudaMalloc(reinterpret_cast<void **>(&d_handles), sizeof(cudaIpcMemHandle_t) * n_ranks);
+        if (d_handles != nullptr) {
+            if (!ok) cudaMemset(d_handles + rank, 0, sizeof(cudaIpcMemHandle_t));
+            const bool sent = nccl().AllGather(d_handles + rank, d_handles, sizeof(cudaIpcMemHandle_t), ncclChar, c, nullptr) == ncclSuccess &&
+                              cudaStreamSynchronize(nullptr) == cudaSuccess &&
+                              cudaMemcpy(handles.data(), d_handles, sizeof(cudaIpcMemHandle_t) * n_ranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+            ok = ok && sent;
+            cudaFree(d_handles);
+        }
+        const cudaIpcMemHandle_t zero{};
+        for (int q = 0; ok && q < n_ranks; q++) {
+            if (q == rank) { cm->peer_flags[q] = cm->d_flags; continue; }
+            void *ptr = nullptr;
+            ok = memcmp(&handles[q], &zero, sizeof(zero)) != 0 &&
+                 cudaIpcOpenMemHandle(&ptr, handles[q], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            cm->peer_flags[q] = static_cast<uint64_t *>(ptr);
+        }
+        if (ok) ok = cudaMalloc(reinterpret_cast<void **>(&cm->d_peer_flags), sizeof(uint64_t *) * n_ranks) == cudaSuccess &&
+                     cudaMemcpy(cm->d_peer_flags, cm->peer_flags, sizeof(uint64_t *) * n_ranks, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (const char *env = getenv("QR_P2P_FLAGS")) if (env[0] == '0') ok = false;
+        cm->flags_ok = ok;
+        cudaGetLastError();
+    }
     return QR_OK;
 }
 
@@ -1694,8 +1988,11 @@ extern "C" int qr_comm_destroy(qr_comm *cm)
 {
     if (!cm) return QR_OK;
     cudaSetDevice(cm->device);
-    if (cm->d_peers) cudaFree(cm->d_peers);
     if (cm->d_scratch) cudaFree(cm->d_scratch);
+    for (int q = 0; q < cm->n_ranks && q < qr::TILE_MAX_PEERS; q++)
+        if (q != cm->rank && cm->peer_flags[q]) cudaIpcCloseMemHandle(cm->peer_flags[q]);
+    if (cm->d_flags) cudaFree(cm->d_flags);
+    if (cm->d_peer_flags) cudaFree(cm->d_peer_flags);
     if (cm->comm && nccl().ok) nccl().CommDestroy(cm->comm);
     delete cm;
     return QR_OK;
@@ -1727,34 +2024,75 @@ extern "C" int qr_apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_sha
         if (!v_shards[o] || ((uintptr_t)v_shards[o] & 15)) return fail(QR_ERR_INVALID, "qr_apply_p2p: bad shard pointer");
     QR_CUDA(cudaSetDevice(pl->device));
     cudaStream_t st = as_stream(stream);
-    if (!cm->d_peers) {
-        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&cm->d_peers), P * sizeof(void *)));
-        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&cm->d_scratch), 16));
-        QR_CUDA(cudaMemset(cm->d_scratch, 0, 16));
-    }
-    bool same = cm->host_peers.size() == P;
-    for (uint64_t o = 0; same && o < P; o++) same = cm->host_peers[o] == v_shards[o];
-    if (!same) {
-        cm->host_peers.assign(v_shards, v_shards + P);
-        std::vector<const double2 *> adj(P);                      // indexable with the GLOBAL row id
-        for (uint64_t o = 0; o < P; o++) adj[o] = reinterpret_cast<const double2 *>(v_shards[o]) - (o << m);
-        QR_CUDA(cudaStreamSynchronize(st));
-        QR_CUDA(cudaMemcpy(cm->d_peers, adj.data(), P * sizeof(void *), cudaMemcpyHostToDevice));
-    }
     const uint64_t row_lo = shard * cm->rank, row_hi = row_lo + shard;
     const double2 *diag = nullptr;
-    int rc = ensure_diag_cache(pl, row_lo, row_hi, st, &diag);
+    const double *diag_re = nullptr;
+    int rc = ensure_diag_cache(pl, row_lo, row_hi, st, &diag, &diag_re);
     if (rc != QR_OK) return rc;
-    // every rank's shard is complete before anyone reads it ...
-    QR_NCCL(nccl().AllReduce(cm->d_scratch, cm->d_scratch, 1, ncclDouble, ncclSum, cm->comm, st));
+
+    // Tiled path: remote runs pulled by TMA into shared memory while the local groups are gathered; ranks
+    // synchronise through epoch flags in IPC-mapped memory, no NCCL call (apply_tile.cuh).
+    const char *tile_env = getenv("QR_P2P_TILE");
+    if (cm->flags_ok && P <= (uint64_t)qr::TILE_MAX_PEERS && tile_env && tile_env[0] == '1') {
+        TilePlan *tp = nullptr;
+        rc = make_tile_plan(pl, m, (uint32_t)cm->rank, m, TILE_P2P, diag != nullptr || diag_re != nullptr, nullptr, &tp);
+        if (rc != QR_OK) return rc;
+        if (tp->ok) {
+            qr::ApplyTileArgs a;
+            tile_args(pl, *tp, (uint32_t)cm->rank, [&](uint32_t q) { return reinterpret_cast<const double2 *>(v_shards[q]); }, a);
+            for (uint64_t o = 0; o < P; o++) {
+                a.peer[o] = reinterpret_cast<const double2 *>(v_shards[o]) - (o << m);      // indexable with the GLOBAL row id
+                a.peer_flags[o] = cm->peer_flags[o];
+            }
+            a.flags_local = cm->d_flags;
+            a.cta_counter = reinterpret_cast<uint32_t *>(cm->d_flags + 2 * P);
+            a.epoch = ++cm->epoch;
+            a.n_peers = (uint32_t)P; a.need_mask = tp->need_mask;
+            rc = launch_run(pl, *tp, a, row_lo, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, st);
+            if (rc != QR_OK) return rc;
+            // nobody overwrites a shard while a peer may still be reading it: the ranks that read mine are the ones I read
+            qr::p2p_wait_done_kernel<<<1, 32, 0, st>>>(cm->d_flags, (uint32_t)P, (uint32_t)cm->rank, tp->need_mask, a.epoch);
+            QR_LAUNCH_CHECK("p2p_wait_done_kernel");
+            return QR_OK;
+        }
+    }
+
+    // Gather path (default): the gather kernel with the peers' shards read in place over NVLink.  Ranks synchronise through
+    // epoch flags in IPC-mapped memory, set and awaited by two one-CTA kernels around the apply; without flags (IPC
+    // unavailable) two NCCL all-reduces of one double do.
+    rc = host_masks(pl);
+    if (rc != QR_OK) return rc;
+    uint32_t need_mask = 0;
+    for (uint32_t x : pl->host_gx) if (((uint64_t)x >> m) != 0) need_mask |= 1u << (((uint32_t)cm->rank ^ (uint32_t)((uint64_t)x >> m)) & 31u);
+    qr::ApplyPeerArgs pa{};
+    for (uint64_t o = 0; o < P; o++) pa.peer[o] = reinterpret_cast<const double2 *>(v_shards[o]) - (o << m);   // indexable with the GLOBAL row id
+    pa.n_peers = (uint32_t)P; pa.shard_bits = m;
+    const bool flags = cm->flags_ok && P <= (uint64_t)qr::APPLY_MAX_PEERS;
+    uint64_t epoch = 0;
+    if (flags) {
+        epoch = ++cm->epoch;
+        qr::p2p_ready_kernel<<<1, 32, 0, st>>>(cm->d_flags, cm->d_peer_flags, (uint32_t)P, (uint32_t)cm->rank, need_mask, epoch);
+        QR_LAUNCH_CHECK("p2p_ready_kernel");
+    } else {
+        if (!cm->d_scratch) {
+            QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&cm->d_scratch), 16));
+            QR_CUDA(cudaMemset(cm->d_scratch, 0, 16));
+        }
+        // every rank's shard is complete before anyone reads it ...
+        QR_NCCL(nccl().AllReduce(cm->d_scratch, cm->d_scratch, 1, ncclDouble, ncclSum, cm->comm, st));
+    }
     const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
     const uint64_t ctas = (shard + per_cta - 1) / per_cta;
-    qr::apply_direct_kernel<true><<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(
-        pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag,
-        cm->d_peers, m);
+    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(
+        pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa);
     QR_LAUNCH_CHECK("apply_direct_kernel(p2p)");
     // ... and nobody overwrites a shard while a peer may still be reading it
-    QR_NCCL(nccl().AllReduce(cm->d_scratch, cm->d_scratch, 1, ncclDouble, ncclSum, cm->comm, st));
+    if (flags) {
+        qr::p2p_done_kernel<<<1, 32, 0, st>>>(cm->d_flags, cm->d_peer_flags, (uint32_t)P, (uint32_t)cm->rank, need_mask, epoch);
+        QR_LAUNCH_CHECK("p2p_done_kernel");
+    } else {
+        QR_NCCL(nccl().AllReduce(cm->d_scratch, cm->d_scratch, 1, ncclDouble, ncclSum, cm->comm, st));
+    }
     return QR_OK;
 }
 

@@ -653,6 +653,43 @@ def test_apply_tiled_passes(fixtures, monkeypatch, name):
         assert np.abs(ys - y0).max() <= tol, parts
 
 
+@pytest.mark.parametrize("name", ["xxz16", "tfim_4x4", "H8", "random_n14", "heis_n18"])
+@pytest.mark.parametrize("cut", ["0", "10", "12"])
+def test_apply_two_pass(fixtures, monkeypatch, name, cut):
+    """Tiled H.v (apply_tile.cuh): a TMA-fed run of v per CTA serves the masks inside it, the rest is gathered (cut 0:
+    that pass alone); with a cut bit a second pass adds the masks from that bit up out of shared-memory tiles spanning
+    the top row bits.  Against the gather kernel and the oracle, on the whole vector and on aligned row blocks of a full
+    vector (groups reaching outside the block pull their runs from the neighbouring blocks)."""
+    labels, coeffs = {"xxz16": lambda: H.xxz_chain(16, 1.0, 0.7), "tfim_4x4": lambda: H.tfim_lattice(4, 4, 1.0, 3.0),
+                      "H8": lambda: fixtures["H8"], "random_n14": lambda: H.random_pauli_sum(14, 300, 200, 30, 11),
+                      "heis_n18": lambda: H.heisenberg_chain(18)}[name]()
+    n, params = O.make_params(labels, coeffs)
+    dim = 1 << n
+    v = H.lanczos_start_vector(0, dim, seed=33)
+    dv = DeviceBuffer(dim * 16); dv.upload(v)
+    monkeypatch.setenv("QR_APPLY_TILE", "0")
+    y0 = _apply_block(make_op(labels, coeffs).plan(), 0, dim, dv)
+    monkeypatch.setenv("QR_APPLY_TILE", "1")
+    monkeypatch.setenv("QR_APPLY_TILE_MIN", "9")
+    monkeypatch.setenv("QR_APPLY_D", cut)
+    plan = make_op(labels, coeffs).plan()
+    _apply_block(plan, 0, dim, dv)                                   # builds the diag cache
+    before = _ffi.kernel_launches()
+    y1 = _apply_block(plan, 0, dim, dv)
+    if name != "H8":                                                 # H8 (981 groups) is beyond the tile kernel's descriptor budget: gather
+        assert _ffi.kernel_launches() - before == (1 if cut == "0" else 2)
+    absH = np.abs(params["re"] + 1j * params["im"]).sum()
+    tol = 1e-12 * absH * np.abs(v).max()
+    assert np.abs(y1 - y0).max() <= tol
+    rows = np.random.default_rng(13).integers(0, dim, 512).astype(np.uint64)
+    ref = O.apply_rows(params, rows, v)
+    assert np.abs(y1[rows.astype(np.int64)] - ref).max() <= tol
+    for parts in (2, 4):
+        blk = dim // parts
+        ys = np.concatenate([_apply_block(plan, p * blk, (p + 1) * blk, dv) for p in range(parts)])
+        assert np.abs(ys - y0).max() <= tol, parts
+
+
 # ---- accel.rs:374-393 (test_it.py:232-269, lib.rs:921-990) ------------------------------------
 def test_vector_ops_bit_exact():
     rng = np.random.default_rng(8)

@@ -108,7 +108,9 @@ if comm is not None:
     t_p2p = maxr(elapsed(e0, e1) / reps)
     ya, yb = np.empty(min(rows, 1 << 16), np.complex128), np.empty(min(rows, 1 << 16), np.complex128)
     d_y.download(ya); d_y2.download(yb)
-    out.update(hv_p2p_ms=t_p2p, hv_p2p_GBps_compulsory=32.0 * dim / t_p2p / 1e6,
+    diff = np.abs(ya - yb)
+    out.update(hv_p2p_ms=t_p2p, hv_p2p_GBps_compulsory=32.0 * dim / t_p2p / 1e6, hv_p2p_max_abs_diff=maxr(float(diff.max())),
+               hv_p2p_n_diff=int(maxr(float(np.count_nonzero(diff)))), hv_p2p_first_diff=int(np.flatnonzero(diff)[0]) if diff.any() else -1,
                hv_p2p_equals_allgather=bool(maxr(0.0 if np.array_equal(ya.view(np.uint64), yb.view(np.uint64)) else 1.0) == 0.0))
     barrier()
     qd.close_shards(opened)
