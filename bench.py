@@ -575,13 +575,12 @@ def run_b200(args, rank, local_rank, world):
             del out
         call("qr_stream_synchronize", None)
         t_e2e = max_over_ranks((time.perf_counter() - t0) / reps)
-        wire = int(C.c_uint64.in_dll(_ffi.lib, "qr_last_build_host_wire_bytes").value) if hasattr(_ffi.lib, "qr_last_build_host_wire_bytes") else None
         e2e = {"value": nnz_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(len(terms) * 32),
-               "d2h_bytes_per_step": int(_ffi.last_wire_bytes() if hasattr(_ffi, "last_wire_bytes") else bytes_local),
+               "d2h_bytes_per_step": int(_ffi.last_d2h_bytes()),
                "host_bytes_produced_per_step": int(bytes_local), "ms_per_step": t_e2e * 1e3,
                "sampled_rows_equal_oracle": ref_ok,
+               "wire": "data as stored + one group id per entry (u8/u16); indptr and the u64 columns are rebuilt by host threads during the DMA",
                "path": "SparsePauliOp.from_terms(terms).to_matrix_mode('Cuda').export(): plan (H2D + K1), K3, D2H of the CSR into pinned host arrays (per rank: its row block)"}
-        del wire
     barrier()
 
     # ---- extras: the multi-GPU BASELINE config 5 where it fits (N >= 2: 94.5 GB of CSR per GPU at N = 2) ----

@@ -124,8 +124,16 @@ QR_API int qr_build_rows_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
  * pageable memory (a Rust Vec, a numpy array) is filled through pinned staging windows by a
  * few host threads, which keeps the PCIe copy at full rate (QR_HOST_NO_STAGING: plain cudaMemcpy). */
 #define QR_HOST_NO_STAGING 4u
+/* On the wire (PCIe is the bound of this call: 56 GB/s against a 6.4 TB/s build) the shard is 17-18 bytes per entry, not 24:
+ * data as stored; the column of an entry as the id of its group (1 byte while G <= 256, 2 while G <= 65536, else the 32-bit
+ * column), rebuilt into the u64 column row ^ mask by host threads while the next window is in flight; indptr written by the
+ * host (affine, r*G).  The arrays the caller receives are the same, bit for bit.  QR_HOST_WIDE: copy all three arrays as
+ * stored (24 + 8/G bytes per entry; comparison and tests). */
+#define QR_HOST_WIDE 8u
 QR_API int qr_build_host(qr_plan *plan, uint64_t row_lo, uint64_t row_hi,
                   uint64_t *indptr, uint64_t *indices, double *data, uint32_t flags);
+/* Bytes the last qr_build_host of the calling thread copied device -> host. */
+QR_API uint64_t qr_last_d2h_bytes(void);
 
 /* rawio::write (qrusty/src/rawio.rs:128-148) of rows [row_lo,row_hi) as a (row_hi-row_lo) x 2^n CSR,
  * streamed from the GPU in row windows (fill -> pinned staging -> pwrite at the section offsets): the

@@ -11,7 +11,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("QRUSTY_CUDA_LIB", _PKG / "lib" / "libqrusty_cuda.so"))
 
 QR_OK, QR_ERR_INVALID, QR_ERR_CUDA, QR_ERR_NCCL, QR_ERR_OOM, QR_ERR_UNSUPPORTED = range(6)
-QR_INDPTR_LOCAL, QR_INDPTR_GLOBAL, QR_FILL_DIRECT, QR_HOST_NO_STAGING = 0, 1, 2, 4
+QR_INDPTR_LOCAL, QR_INDPTR_GLOBAL, QR_FILL_DIRECT, QR_HOST_NO_STAGING, QR_HOST_WIDE = 0, 1, 2, 4, 8
 QR_PLAN_MERGE_DUPLICATES = 1
 QR_UNIQUE_ID_BYTES = 128
 QR_IPC_HANDLE_BYTES = 64
@@ -111,9 +111,11 @@ lib.qr_last_error.restype = C.c_char_p
 lib.qr_last_error.argtypes = []
 lib.qr_version.restype = C.c_int
 lib.qr_kernel_launches.restype = C.c_uint64
+lib.qr_last_d2h_bytes.restype = C.c_uint64
+lib.qr_last_d2h_bytes.argtypes = []
 lib.qr_plan_fill_kernel.restype = C.c_char_p
 lib.qr_plan_fill_kernel.argtypes = [_vp]
-EXPORTS = sorted(list(SIGNATURES) + ["qr_last_error", "qr_version", "qr_kernel_launches", "qr_plan_fill_kernel"])
+EXPORTS = sorted(list(SIGNATURES) + ["qr_last_error", "qr_version", "qr_kernel_launches", "qr_plan_fill_kernel", "qr_last_d2h_bytes"])
 
 
 def check(rc):
@@ -123,6 +125,10 @@ def check(rc):
 
 def call(name, *args):
     check(getattr(lib, name)(*args))
+
+
+def last_d2h_bytes():
+    return int(lib.qr_last_d2h_bytes())
 
 
 def kernel_launches():

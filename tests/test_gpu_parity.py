@@ -449,6 +449,34 @@ def test_build_host_pageable_destination(monkeypatch, threads):
             assert_same((ip, ix, dt), (want_ip, ref[1], ref[2]), f"pageable [{lo},{hi}) flags={flags | extra}")
 
 
+@pytest.mark.parametrize("name,wire_col,want_col", [("xxz16", None, 1), ("xxz16", "2", 2), ("xxz16", "4", 4), ("random_n14", None, 2),
+                                                   ("random_n14", "4", 4), ("H4", None, 1)])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_build_host_wire_forms(fixtures, monkeypatch, name, wire_col, want_col, pinned):
+    """The compact wire form of qr_build_host (wire.cuh): group ids of 1 / 2 bytes or 32-bit columns cross PCIe, the host
+    pool rebuilds the u64 columns and writes indptr itself.  The caller's arrays must equal the oracle's bit for bit, as they
+    do with QR_HOST_WIDE (every array copied as stored), and the D2H byte count must be what the form promises."""
+    labels, coeffs = {"xxz16": lambda: H.xxz_chain(16, 1.0, 0.7), "random_n14": lambda: H.random_pauli_sum(14, 400, 300, 30, 5),
+                      "H4": lambda: fixtures["H4"]}[name]()
+    n, params = O.make_params(labels, coeffs)
+    plan = make_op(labels, coeffs).plan()
+    G, dim = plan.n_groups, 1 << n
+    if wire_col:
+        monkeypatch.setenv("QR_HOST_WIRE_COL", wire_col)
+    from qrusty_b200._runtime import pinned_empty
+    for lo, hi, flags in [(0, dim, 0), (5, dim - 3, _ffi.QR_INDPTR_GLOBAL)]:
+        rows = hi - lo
+        ref = O.build_csr(params, n, lo, hi)
+        want_ip = ref[0] + (np.uint64(lo * G) if flags & _ffi.QR_INDPTR_GLOBAL else np.uint64(0))
+        for extra, col in ((0, want_col), (_ffi.QR_HOST_WIDE, 8)):
+            alloc = pinned_empty if pinned else np.empty
+            ip, ix, dt = alloc(rows + 1, np.uint64), alloc(rows * G, np.uint64), alloc(rows * G, np.complex128)
+            ip[:] = 0xFFFF; ix[:] = 0xFFFF; dt[:] = np.nan
+            _ffi.call("qr_build_host", plan.handle, lo, hi, ip.ctypes.data, ix.ctypes.data, dt.ctypes.data, flags | extra)
+            assert_same((ip, ix, dt), (want_ip, ref[1], ref[2]), f"wire form {col} B/col [{lo},{hi}) pinned={pinned}")
+            assert _ffi.last_d2h_bytes() == rows * G * (16 + col)
+
+
 def test_abi_argument_errors(fixtures):
     plan = make_op(*fixtures["H2"]).plan()
     buf = DeviceBuffer(1 << 16)
