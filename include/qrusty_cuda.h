@@ -151,6 +151,10 @@ QR_API int qr_apply_host(qr_plan *plan, const double *v, double *y);   /* full v
 /* diag(H) for rows [row_lo,row_hi) (SpMat.diagonal, pyqrusty/src/lib.rs:118-125). */
 QR_API int qr_diagonal_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi, double *d_diag, void *stream);
 
+/* diag of a CSR shard already resident in HBM: d_diag[i] = the stored entry (i, col0 + i), 0 if none
+ * (SpMat.diagonal, pyqrusty/src/lib.rs:118-125, on a matrix that was scaled or compacted after the build). */
+QR_API int qr_csr_diagonal_device(uint64_t n_rows, uint64_t col0, const uint64_t *d_indptr, const uint64_t *d_indices,
+                           const double *d_data, double *d_diag, void *stream);
 /* CSR SpMV on a device-resident CSR shard, the reference's own H.v
  * (accel.rs:338-370): y[r] = sum_k data[k]*v[indices[k]] in stored order,
  * starting from zero; indptr may be local or global (rebased by d_indptr[0]). */

@@ -392,16 +392,25 @@ class SpMat:
         return SpMat._from_shards(self._shape, shards)
 
     def diagonal(self):
+        """pyqrusty/src/lib.rs:118-125: the diagonal of the STORED matrix.  A shard that has not been built yet (lazy, square
+        placement) takes it straight from the plan -- the mask-0 group, no matrix needed; a shard that is resident (and may
+        have been scaled or compacted since) is searched on the device."""
         shards = self._live("SpMat.diagonal(): already-exported sparse matrix")
-        out = np.empty(min(self._shape), np.complex128)
+        out = np.zeros(min(self._shape), np.complex128)
         for s in shards:
-            if s.plan is None:      # caller-supplied CSR (new_unchecked): generic sparse algebra, off the path
-                shape, data, indices, indptr = self.__copy__().export()
-                from scipy.sparse import csr_matrix as _csr
-                return _csr((data, indices, indptr), shape=shape).diagonal()
-            d = DeviceBuffer((s.hi - s.lo) * 16, s.device)
-            call("qr_diagonal_device", s.plan.handle, s.lo, s.hi, d.ptr, None)
-            d.download(out[s.off:s.off + s.hi - s.lo])
+            rows = s.hi - s.lo
+            n = min(rows, max(0, len(out) - s.off))
+            if n == 0:
+                continue
+            call("qr_set_device", s.device)
+            d = DeviceBuffer(rows * 16, s.device)
+            if s.plan is not None and s.data is None and s.off == s.lo:
+                call("qr_diagonal_device", s.plan.handle, s.lo, s.hi, d.ptr, None)
+            else:
+                s.materialise()
+                call("qr_csr_diagonal_device", rows, s.off, s.indptr.ptr, s.indices.ptr, s.data.ptr, d.ptr, None)
+            tmp = d.download(np.empty(rows, np.complex128))
+            out[s.off:s.off + n] = tmp[:n]
         return out
 
     def scale(self, factor):
@@ -612,6 +621,8 @@ def spmat_dot_densevec(spmat, x):
     CSR SpMV over the device-resident matrix, sequential per row in stored order."""
     shards = spmat.to_device()._live("cannot multiply with an exported sparse matrix")
     x = np.ascontiguousarray(x, dtype=np.complex128)
+    if x.shape != (spmat._shape[1],):
+        raise Exception("spmat_dot_densevec: vector of length %d against a matrix with %d columns" % (x.size, spmat._shape[1]))
     y = np.empty(spmat._shape[0], np.complex128)
     for s in shards:
         rows = s.hi - s.lo
@@ -650,12 +661,16 @@ def _vec(x):
 def axpby(a, x, b, y):
     """z = a*x + b*y (accel.rs:374-379)."""
     x, y = _vec(x), _vec(y)
+    if x.shape != y.shape:
+        raise Exception("axpby: x and y differ in length")
     return _vec_op("qr_axpby_device", len(x), [_c2(a), _c2(b)], [x, y])
 
 
 def axpy(a, x, y):
     """z = a*x + y (accel.rs:381-386)."""
     x, y = _vec(x), _vec(y)
+    if x.shape != y.shape:
+        raise Exception("axpy: x and y differ in length")
     return _vec_op("qr_axpy_device", len(x), [_c2(a)], [x, y])
 
 

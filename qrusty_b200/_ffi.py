@@ -61,6 +61,7 @@ SIGNATURES = {
     "qr_apply_host": [_vp, _vp, _vp],
     "qr_diagonal_device": [_vp, _u64, _u64, _vp, _vp],
     "qr_spmv_device": [_u64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "qr_csr_diagonal_device": [_u64, _u64, _vp, _vp, _vp, _vp, _vp],
     "qr_count_kept_device": [_u64, _u64, _vp, C.c_double, _vp, C.POINTER(_u64), _vp],
     "qr_compact_rows_device": [_u64, _u64, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp],
     "qr_build_compact_count": [_vp, _u64, _u64, C.c_double, _vp, C.POINTER(_u64), _vp],

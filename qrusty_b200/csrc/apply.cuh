@@ -296,6 +296,26 @@ diagonal_kernel(PlanDev p, uint64_t row_lo, uint64_t row_hi, double2 *__restrict
     else diag[r64 - row_lo] = d;
 }
 
+// diag of a stored CSR shard (pyqrusty/src/lib.rs:118-125 reads it from the stored matrix: after scale() or
+// eliminate_zeros() the plan no longer describes the values).  Row i of the shard is row col0 + i of the matrix:
+// diag[i] = the stored entry of row i whose column is col0 + i, else 0.  Columns ascend inside a row: binary search.
+__global__ void __launch_bounds__(256)
+csr_diagonal_kernel(uint64_t n_rows, uint64_t col0, const uint64_t *__restrict__ indptr, const uint64_t *__restrict__ indices,
+                    const double2 *__restrict__ data, double2 *__restrict__ diag)
+{
+    const uint64_t row = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t base = indptr[0], want = col0 + row;
+    uint64_t lo = indptr[row] - base, hi = indptr[row + 1] - base;
+    double2 d = make_double2(0.0, 0.0);
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1, c = indices[mid];
+        if (c == want) { d = data[mid]; break; }
+        if (c < want) lo = mid + 1; else hi = mid;
+    }
+    diag[row] = d;
+}
+
 // CSR SpMV as rowwise::spmat_dot_densevec does it (accel.rs:355-364): one row per
 // thread, products accumulated sequentially in stored order starting from zero,
 // with the multiply written out as num_complex does (no FMA contraction) so the

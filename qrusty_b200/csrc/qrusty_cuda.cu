@@ -70,6 +70,25 @@ struct WinScratch {
 std::mutex g_win_mutex;                                            // guards the map, not the transfers
 std::map<int, WinScratch> g_win;
 
+// small device scratch of the scan and the reductions, one set per device (a host thread may drive several GPUs in turn:
+// thread-local pointers would leak the previous device's block on every switch)
+struct DevScratch { uint64_t *tiles = nullptr; uint64_t tiles_cap = 0; double2 *partials = nullptr; double2 *tmp = nullptr; int n_sm = 0; };
+std::mutex g_dev_mutex;
+std::map<int, DevScratch> g_dev;
+DevScratch *dev_scratch(int dev)
+{
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DevScratch &d = g_dev[dev];
+    if (d.n_sm == 0 && (cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.n_sm < 1)) { cudaGetLastError(); d.n_sm = 148; }
+    return &d;
+}
+int current_sm_count()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+    return dev_scratch(dev)->n_sm;
+}
+
 }  // namespace
 
 // H.v pass plan for a local row block of 2^m rows (see apply.cuh)
@@ -678,7 +697,8 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             const uint64_t span = row_hi - row_lo;
             while (k > 5 && k > qb) {
                 const uint64_t runs = span >> k;
-                if (runs >= 148 && (runs + 147) / 148 * 148 * 100 <= runs * 104) break;    // <= 4 % idle tail on 148 CTAs
+                const uint64_t sm = (uint64_t)pl->n_sm;
+                if (runs >= sm && (runs + sm - 1) / sm * sm * 100 <= runs * 104) break;    // <= 4 % idle tail on one persistent CTA per SM
                 k--;
             }
         }
@@ -774,7 +794,7 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             // persistent CTAs: J groups of n_light sibling CTAs, as many as are resident at once
             const uint64_t n_runs = (s1 - s0) / R;
             if (n_runs > 0xffffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_lanes: row window too large for one launch");
-            const uint32_t resident = 148u * (32u / LW);
+            const uint32_t resident = (uint32_t)pl->n_sm * (32u / LW);
             const uint64_t J = std::min<uint64_t>(n_runs, std::max<uint32_t>(1u, (resident + n_light - 1) / n_light));
             uint64_t J2 = pl->lanes_persist ? J : n_runs;
             if (J2 * n_light > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_lanes: row window too large for one launch");
@@ -825,7 +845,7 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             // enough CTAs to fill the chip several times over, else as many strips per CTA as
             // amortise the table load (10 KB at S=32 against ~17 KB of output per strip)
             uint32_t per_cta = 8;
-            while (per_cta > (uint32_t)E && (strips + per_cta - 1) / per_cta * pl->n_blocks < 148ull * 16) per_cta /= 2;
+            while (per_cta > (uint32_t)E && (strips + per_cta - 1) / per_cta * pl->n_blocks < (uint64_t)pl->n_sm * 16) per_cta /= 2;
             const uint64_t ctas = (strips + per_cta - 1) / per_cta * pl->n_blocks;
             if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_blocked: row window too large for one launch");
             auto kern = E == 2 ? qr::fill_blocked_kernel<2> : qr::fill_blocked_kernel<1>;
@@ -1229,6 +1249,13 @@ extern "C" int qr_release_scratch(void)
         }
     }
     g_win.clear();
+    std::lock_guard<std::mutex> lock2(g_dev_mutex);
+    for (auto &kv : g_dev) {
+        if (cudaSetDevice(kv.first) != cudaSuccess) continue;
+        if (kv.second.tiles) cudaFree(kv.second.tiles);
+        if (kv.second.partials) cudaFree(kv.second.partials);
+    }
+    g_dev.clear();
     return QR_OK;
 }
 
@@ -1690,6 +1717,19 @@ extern "C" int qr_diagonal_device(qr_plan *pl, uint64_t row_lo, uint64_t row_hi,
     return QR_OK;
 }
 
+extern "C" int qr_csr_diagonal_device(uint64_t n_rows, uint64_t col0, const uint64_t *d_indptr, const uint64_t *d_indices,
+                                      const double *d_data, double *d_diag, void *stream)
+{
+    if (!d_indptr || !d_indices || !d_data || !d_diag) return fail(QR_ERR_INVALID, "qr_csr_diagonal_device: NULL argument");
+    if (n_rows == 0) return QR_OK;
+    const uint64_t ctas = (n_rows + 255) / 256;
+    if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "qr_csr_diagonal_device: shard too large for one launch");
+    qr::csr_diagonal_kernel<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(
+        n_rows, col0, d_indptr, d_indices, reinterpret_cast<const double2 *>(d_data), reinterpret_cast<double2 *>(d_diag));
+    QR_LAUNCH_CHECK("csr_diagonal_kernel");
+    return QR_OK;
+}
+
 extern "C" int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const uint64_t *d_indices,
                               const double *d_data, const double *d_v, double *d_y, void *stream)
 {
@@ -1710,19 +1750,17 @@ extern "C" int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const u
 static int scan_counts(uint64_t n_rows, uint64_t *d_indptr, uint64_t *nnz_out, cudaStream_t st, const char *who)
 {
     const uint64_t n_tiles = (n_rows + qr::SCAN_TILE - 1) / qr::SCAN_TILE;
-    // tile sums: a small scratch kept per host thread and device (cudaFree would serialise the device)
-    static thread_local uint64_t *d_tiles = nullptr;
-    static thread_local uint64_t tiles_cap = 0;
-    static thread_local int tiles_dev = -1;
+    // tile sums: a small scratch kept per device (cudaFree would serialise the device)
     int dev = 0;
     QR_CUDA(cudaGetDevice(&dev));
-    if (!d_tiles || tiles_dev != dev || tiles_cap < n_tiles + 1) {
-        if (d_tiles && tiles_dev == dev) cudaFree(d_tiles);
-        d_tiles = nullptr;
-        tiles_cap = std::max<uint64_t>(n_tiles + 1, 4096);
-        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_tiles), tiles_cap * 8));
-        tiles_dev = dev;
+    DevScratch *ds = dev_scratch(dev);
+    if (!ds->tiles || ds->tiles_cap < n_tiles + 1) {
+        if (ds->tiles) { QR_CUDA(cudaStreamSynchronize(st)); cudaFree(ds->tiles); }
+        ds->tiles = nullptr;
+        ds->tiles_cap = std::max<uint64_t>(n_tiles + 1, 4096);
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&ds->tiles), ds->tiles_cap * 8));
     }
+    uint64_t *d_tiles = ds->tiles;
     qr::scan_tile_sums_kernel<<<(unsigned)n_tiles, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr, d_tiles);
     g_launches.fetch_add(1);
     qr::scan_tile_offsets_kernel<<<1, qr::K2_THREADS, 0, st>>>(n_tiles, d_tiles, d_tiles + n_tiles);
@@ -1760,7 +1798,7 @@ extern "C" int qr_compact_rows_device(uint64_t n_rows, uint64_t G, const uint64_
         return fail(QR_ERR_INVALID, "qr_compact_rows_device: NULL argument");
     if (n_rows == 0 || G == 0 || G > 0xffffffffull) return fail(QR_ERR_INVALID, "qr_compact_rows_device: bad shape");
     const uint64_t per_cta = qr::K2_THREADS / 32;
-    const uint64_t ctas = std::min<uint64_t>((n_rows + per_cta - 1) / per_cta, 148ull * 64);
+    const uint64_t ctas = std::min<uint64_t>((n_rows + per_cta - 1) / per_cta, (uint64_t)current_sm_count() * 64);
     qr::compact_rows_kernel<<<(unsigned)ctas, qr::K2_THREADS, 0, as_stream(stream)>>>(
         n_rows, (uint32_t)G, d_indices, reinterpret_cast<const double2 *>(d_data), tol, d_indptr, d_indices_out,
         reinterpret_cast<double2 *>(d_data_out));
@@ -1819,7 +1857,7 @@ extern "C" int qr_build_compact_fill(qr_plan *pl, uint64_t row_lo, uint64_t row_
         rc = build_rows(pl, w0, w1, nullptr, t_idx, t_dat, 0, st);
         if (rc != QR_OK) break;
         const uint64_t per_cta = qr::K2_THREADS / 32;
-        const uint64_t ctas = std::min<uint64_t>((n + per_cta - 1) / per_cta, 148ull * 64);
+        const uint64_t ctas = std::min<uint64_t>((n + per_cta - 1) / per_cta, (uint64_t)pl->n_sm * 64);
         qr::compact_rows_kernel<<<(unsigned)ctas, qr::K2_THREADS, 0, st>>>(
             n, (uint32_t)G, t_idx, t_dat, tol, d_indptr + (w0 - row_lo), d_indices, reinterpret_cast<double2 *>(d_data));
         g_launches.fetch_add(1);
@@ -1833,7 +1871,7 @@ extern "C" int qr_build_compact_fill(qr_plan *pl, uint64_t row_lo, uint64_t row_
 static unsigned vec_grid(uint64_t n)
 {
     uint64_t ctas = (n + 255) / 256;
-    const uint64_t cap = 148ull * 16;
+    const uint64_t cap = (uint64_t)current_sm_count() * 16;
     return (unsigned)(ctas < cap ? (ctas ? ctas : 1) : cap);
 }
 
@@ -1881,18 +1919,18 @@ extern "C" int qr_precond2_device(uint64_t n, const double *d_diag, const double
     return QR_OK;
 }
 
-constexpr unsigned kReduceGrid = 148 * 8;
-static int reduce_scratch(double2 **out)                 // one scratch per host thread (and its device)
+constexpr unsigned kReduceGrid = 148 * 8;             // partial sums per reduction (a fixed count keeps the fold order, hence the result, device-independent)
+static int reduce_scratch(double2 **partials, double2 **tmp)  // per device: kReduceGrid partial sums + one folded value
 {
-    static thread_local double2 *partials = nullptr;
-    static thread_local int partials_dev = -1;
     int dev = 0;
     QR_CUDA(cudaGetDevice(&dev));
-    if (!partials || partials_dev != dev) {
-        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&partials), kReduceGrid * sizeof(double2)));
-        partials_dev = dev;
+    DevScratch *ds = dev_scratch(dev);
+    if (!ds->partials) {
+        QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&ds->partials), (kReduceGrid + 1) * sizeof(double2)));
+        ds->tmp = ds->partials + kReduceGrid;
     }
-    *out = partials;
+    *partials = ds->partials;
+    if (tmp) *tmp = ds->tmp;
     return QR_OK;
 }
 
@@ -1901,8 +1939,8 @@ extern "C" int qr_lanczos_update_device(uint64_t n, const double alpha[2], const
                                         void *stream)
 {
     if (!alpha || !beta || !w || !v || !w_out || !d_norm2_out) return fail(QR_ERR_INVALID, "qr_lanczos_update_device: NULL argument");
-    double2 *partials = nullptr;
-    int rc = reduce_scratch(&partials);
+    double2 *partials = nullptr, *tmp = nullptr;
+    int rc = reduce_scratch(&partials, &tmp);
     if (rc != QR_OK) return rc;
     qr::lanczos_update_kernel<<<kReduceGrid, 256, 0, as_stream(stream)>>>(
         n, make_double2(alpha[0], alpha[1]), make_double2(beta[0], beta[1]), reinterpret_cast<const double2 *>(w),
@@ -1910,11 +1948,6 @@ extern "C" int qr_lanczos_update_device(uint64_t n, const double alpha[2], const
         reinterpret_cast<double2 *>(w_out), partials);
     QR_LAUNCH_CHECK("lanczos_update_kernel");
     // fold the partials; the result is (norm2, 0): only the first double is the caller's
-    static thread_local double2 *tmp = nullptr;
-    static thread_local int tmp_dev = -1;
-    int dev = 0;
-    QR_CUDA(cudaGetDevice(&dev));
-    if (!tmp || tmp_dev != dev) { QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&tmp), sizeof(double2))); tmp_dev = dev; }
     qr::dotc_final_kernel<<<1, qr::DOT_THREADS, 0, as_stream(stream)>>>(kReduceGrid, partials, tmp);
     QR_LAUNCH_CHECK("dotc_final_kernel");
     QR_CUDA(cudaMemcpyAsync(d_norm2_out, tmp, sizeof(double), cudaMemcpyDeviceToDevice, as_stream(stream)));
@@ -1926,7 +1959,7 @@ extern "C" int qr_dotc_device(uint64_t n, const double *x, const double *y, doub
     if (!x || !y || !d_out) return fail(QR_ERR_INVALID, "qr_dotc_device: NULL argument");
     const unsigned grid = kReduceGrid;
     double2 *partials = nullptr;
-    { int rc = reduce_scratch(&partials); if (rc != QR_OK) return rc; }
+    { int rc = reduce_scratch(&partials, nullptr); if (rc != QR_OK) return rc; }
     qr::dotc_partial_kernel<<<grid, qr::DOT_THREADS, 0, as_stream(stream)>>>(
         n, reinterpret_cast<const double2 *>(x), reinterpret_cast<const double2 *>(y), partials);
     QR_LAUNCH_CHECK("dotc_partial_kernel");

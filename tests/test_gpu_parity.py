@@ -958,6 +958,48 @@ def test_spmat_scale_and_strategy_aliases(fixtures):
         assert_same((indptr, indices, data), ref, "strategy alias")
 
 
+@pytest.mark.parametrize("name", ["H4", "xxz_n10", "C1"])
+def test_diagonal_follows_the_stored_matrix(fixtures, name):
+    """SpMat.diagonal / precond read the STORED matrix (pyqrusty/src/lib.rs:118-125, 442-455): after scale() the scaled
+    diagonal, after eliminate_zeros() zero where the entry was dropped, on a row-window shard M[i,i] = H[lo+i, i]."""
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    indptr, indices, data = O.build_csr(params, n)
+    dim = 1 << n
+    import scipy.sparse
+    dense_diag = scipy.sparse.csr_matrix((data, indices.astype(np.int64), indptr.astype(np.int64)), shape=(dim, dim)).diagonal()
+    op = make_op(labels, coeffs)
+    m = op.to_matrix()
+    assert np.array_equal(m.diagonal(), np.asarray(dense_diag))                             # lazy shard: from the plan (scipy drops the sign of a stored -0.0)
+    f = 0.5 - 2j
+    m.scale(f)
+    want = O.ax(f, np.asarray(dense_diag, dtype=np.complex128))
+    assert np.array_equal(m.diagonal(), want)                                               # resident, scaled
+    dx = np.random.default_rng(3).standard_normal(dim) + 0j
+    assert np.array_equal(Q.precond(m, dx, 0.25 + 0j, 1e-8), O.precond2(want, dx, 0.25 + 0j, 1e-8))
+    tol = float(np.median(np.abs(dense_diag))) if np.any(dense_diag) else 1e-7             # drops about half of the diagonal
+    z = op.to_matrix().eliminate_zeros(tol)
+    kept = np.where(np.hypot(dense_diag.real, dense_diag.imag) > tol, dense_diag, 0)
+    assert np.array_equal(z.diagonal(), kept)
+    lo, hi = dim // 4, dim // 2                                                             # rows [lo,hi): M[i,i] = H[lo+i, i]
+    sh = op.to_matrix_rows(lo, hi)
+    ref_rows = scipy.sparse.csr_matrix((data, indices.astype(np.int64), indptr.astype(np.int64)), shape=(dim, dim))[lo:hi]
+    assert np.array_equal(sh.diagonal(), ref_rows.diagonal())
+
+
+def test_vector_length_checks(fixtures):
+    labels, coeffs = fixtures["H2"]
+    m = make_op(labels, coeffs).to_matrix()
+    with pytest.raises(Exception, match="columns"):
+        Q.spmat_dot_densevec(m, np.zeros(15, complex))
+    with pytest.raises(Exception, match="differ in length"):
+        Q.axpby(1.0, np.zeros(4, complex), 2.0, np.zeros(5, complex))
+    with pytest.raises(Exception, match="differ in length"):
+        Q.axpy(1.0, np.zeros(4, complex), np.zeros(5, complex))
+    with pytest.raises(Exception, match="wrong length"):
+        make_op(labels, coeffs).apply(np.zeros(15, complex))
+
+
 def test_graph_capture_replay(fixtures):
     """qr_graph_*: the canonicalise -> fill sequence recorded once, replayed into zeroed buffers; event
     records inside the capture become graph nodes whose timestamps are readable after the replay."""

@@ -27,6 +27,43 @@ def test_library_exports_every_declared_symbol():
     assert C.sizeof(_ffi.PlanInfo) == 40
 
 
+def _c_prototypes(header):
+    """name -> list of parameter type strings, from the QR_API declarations of the header."""
+    protos = {}
+    for m in re.finditer(r"^QR_API\s+[\w\s\*]+?\b(qr_\w+)\s*\(([^;]*?)\)\s*;", re.sub(r"/\*.*?\*/", "", header, flags=re.S), re.M | re.S):
+        args = [a.strip() for a in m.group(2).split(",")]
+        protos[m.group(1)] = [] if args in ([""], ["void"]) else args
+    return protos
+
+
+def test_rust_shim_in_lock_step_with_the_header():
+    """rust/cuda.rs cannot be compiled here (no cargo in the image), so its extern block is checked against the header the
+    other way: every function it binds exists with the same number of parameters, pointer-ness and integer width per
+    position, and the constants it copies have the header's values."""
+    header = (ROOT / "include" / "qrusty_cuda.h").read_text()
+    rust = (ROOT / "rust" / "cuda.rs").read_text()
+    protos = _c_prototypes(header)
+    block = re.search(r'extern "C" \{(.*?)\n\}', rust, re.S).group(1)
+    bound = re.findall(r"fn (qr_\w+)\s*\((.*?)\)\s*(?:->\s*([^;]+))?;", block, re.S)
+    assert len(bound) >= 15
+    width = {"c_int": "int", "u32": "uint32_t", "u64": "uint64_t", "usize": "size_t", "f64": "double"}
+    for name, args, ret in bound:
+        assert name in protos, "rust/cuda.rs binds %s, which the header does not declare" % name
+        r_args = [a.strip() for a in args.split(",") if a.strip()]
+        c_args = protos[name]
+        assert len(r_args) == len(c_args), (name, r_args, c_args)
+        for ra, ca in zip(r_args, c_args):
+            r_type = ra.split(":", 1)[1].strip()
+            assert r_type.startswith("*") == ("*" in ca or "[" in ca), (name, ra, ca)
+            if not r_type.startswith("*"):
+                assert width[r_type] in ca, (name, ra, ca)
+    for const, value in re.findall(r"pub const (QR_\w+): \w+ = (\d+);", rust):
+        m = re.search(r"#define\s+%s\s+(\d+)" % const, header)
+        if m is None:                                                # status codes are an enum in the header
+            m = re.search(r"\b%s\s*=\s*(\d+)" % const, header)
+        assert m is not None and int(m.group(1)) == int(value), const
+
+
 def test_no_oracle_in_product():
     """The product must never import, link or call the oracle."""
     for f in (ROOT / "qrusty_b200").rglob("*"):
