@@ -488,13 +488,16 @@ def run_b200(args, rank, local_rank, world):
     call("qr_stream_synchronize", stream)
     # The K timed steps are recorded once into a CUDA graph and replayed with one launch: with 8 ranks
     # sharing one host the Python launch rate (4 ctypes calls per 95 us step) is otherwise what gets timed.
-    fill_ev = [(ev(), ev()) for _ in range(K)]                  # around every fill launch of the timed steps
-    graph, launches0 = None, _ffi.kernel_launches()
+    # Two graphs of the same K steps: the TIMED one holds nothing but the kernels (canonicalise and fill are chained by
+    # programmatic dependent launch, which an event record between them would break); the second one brackets every fill
+    # launch with events on the same stream and is replayed right after each timed region for the roofline figure.
+    fill_ev = [(ev(), ev()) for _ in range(K)]                  # around every fill launch of the instrumented steps
+    graph, graph_ev, launches0 = None, None, _ffi.kernel_launches()
     if not args.no_graph:
         try:
             call("qr_graph_begin_capture", stream)
             for i in range(K):
-                step(*fill_ev[i])
+                step()
             g = C.c_void_p()
             call("qr_graph_end_capture", stream, C.byref(g))
             graph = g
@@ -504,6 +507,15 @@ def run_b200(args, rank, local_rank, world):
             sys.stderr.write("bench.py: CUDA graph capture failed (%s); timing eager launches\n" % exc)
             graph = None
     launches_per_k = _ffi.kernel_launches() - launches0
+    if graph is not None:
+        call("qr_graph_begin_capture", stream)
+        for i in range(K):
+            step(*fill_ev[i])
+        g = C.c_void_p()
+        call("qr_graph_end_capture", stream, C.byref(g))
+        graph_ev = g
+        call("qr_graph_launch", graph_ev, stream)
+        call("qr_stream_synchronize", stream)
 
     def timed_k_steps():
         """exactly K steps between two events on `stream`, bracketed by barrier + synchronize -> (ms, mean fill ms, launches)"""
@@ -515,11 +527,18 @@ def run_b200(args, rank, local_rank, world):
             call("qr_graph_launch", graph, stream)
         else:
             for i in range(K):
-                step(*fill_ev[i])
+                step()
         call("qr_event_record", e1, stream)
         call("qr_stream_synchronize", stream)
         n_l = launches_per_k if graph is not None else _ffi.kernel_launches() - l0
         barrier()
+        # the same K steps once more, instrumented: per-launch duration of the fill kernel
+        if graph_ev is not None:
+            call("qr_graph_launch", graph_ev, stream)
+        else:
+            for i in range(K):
+                step(*fill_ev[i])
+        call("qr_stream_synchronize", stream)
         return elapsed(e0, e1), float(np.mean([elapsed(a, b) for a, b in fill_ev])), n_l
 
     sampler.start()
@@ -689,7 +708,8 @@ def run_b200(args, rank, local_rank, world):
             "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": config_dict(name, n, len(labels), G, world),
-            "run": {"launch": ("one CUDA graph holding the K steps" if graph is not None else "K eager step launches"),
+            "run": {"launch": ("one CUDA graph holding the K steps, canonicalise -> fill chained by programmatic dependent launch" if graph is not None else "K eager step launches"),
+                    "fill_timing": "events around every fill launch of an instrumented replay of the same K steps, right after each timed region",
                     "timed_regions": len(step_ms_runs),
                     "value_is": "median over the timed regions (each exactly K steps, max over ranks)",
                     "ms_per_step_runs": [round(v, 5) for v in step_ms_runs],

@@ -105,6 +105,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
 
     const uint32_t tid = threadIdx.x;
     const uint32_t T = p.n_terms;
+    // programmatic dependent launch: this kernel rewrites the tables the previous fill may still be reading, so it
+    // waits for its predecessor first; the fill that follows may be launched right away (it waits in turn)
+    pdl_wait();
+    pdl_launch_dependents();
 
     // ---- 0. payload = original index ------------------------------------------------------
     for (uint32_t i = tid; i < K1_WARPS * 256; i += K1_THREADS) (&sm.wcount[0][0])[i] = 0;
@@ -145,6 +149,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
     // sorted (x, idx) now in (kin, iin)
 
     // ---- 2. head flags -> groups; gather the sorted term table ------------------------------
+    // the masks also stay in shared memory (the sort's spare buffer) for the binary searches of step 3: done on the global
+    // copy each probe is an L2 round trip, 10 dependent ones per table entry -- a third of this kernel's 7 us on C2
+    uint32_t *sgx = (!merge_dups && T <= SMALL_T) ? kout : nullptr;
     uint32_t carry = 0;
     for (uint32_t tile = 0; tile < T; tile += K1_THREADS) {
         const uint32_t i = tile + tid;
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
         uint32_t total;
         const uint32_t excl = block_exclusive_scan(head, sm.scan_scratch, &total);
         if (valid) {
-            if (head) { p.gx[carry + excl] = key; p.goff[carry + excl] = i; }
+            if (head) { p.gx[carry + excl] = key; p.goff[carry + excl] = i; if (sgx) sgx[carry + excl] = key; }
             const uint32_t src = iin[i];
             p.perm[i] = src;
             p.tz[i] = (uint32_t)p.raw[src].z;
@@ -211,13 +218,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) canonicalise_kernel(PlanDev p, 
 
     // ---- 3. rank tables -----------------------------------------------------------------------
     const uint32_t nq = (uint32_t)p.n_qubits;
+    const uint32_t *gxs = sgx ? sgx : p.gx;
     for (uint32_t q = tid; q < G * 32u; q += K1_THREADS) {
         const uint32_t g = q >> 5, b = q & 31u;
         uint32_t c = 0;
         if (b < nq) {
             const uint32_t low = (1u << b) - 1u;
-            const uint32_t lo = (p.gx[g] ^ (1u << b)) & ~low;     // same prefix above b, bit b flipped
-            c = upper_bound_u32(p.gx, G, lo | low) - lower_bound_u32(p.gx, G, lo);
+            const uint32_t lo = (gxs[g] ^ (1u << b)) & ~low;      // same prefix above b, bit b flipped
+            c = upper_bound_u32(gxs, G, lo | low) - lower_bound_u32(gxs, G, lo);
         }
         p.cnt[q] = c;
         p.cnt_t[b * T + g] = c;

@@ -167,6 +167,10 @@ fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, u
     const uint32_t lane = threadIdx.x & 31u, gw = threadIdx.x >> 5;
     const uint64_t tile_base = tile_row0 + (uint64_t)blockIdx.x * R;
     const uint32_t tbase = (uint32_t)tile_base;
+    // launched ahead of the end of the canonicalisation (programmatic dependent launch): the plan tables are not to be
+    // read, nor the outputs written, before it has completed
+    pdl_wait();
+    pdl_launch_dependents();
     uint32_t r[E], od[E], oi[E];                                  // row, and where the row starts in sdat / sidx
 #pragma unroll
     for (int e = 0; e < E; e++) {

@@ -65,6 +65,12 @@ struct PlanDev {
     double2  *lt_c;      // lanes kernel: c' of those terms, [t][T], padded with -0.0
 };
 
+// Programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization): a kernel launched with the attribute
+// may start while its predecessor in the stream still runs; pdl_wait() blocks until that predecessor has completed and its
+// writes are visible, pdl_launch_dependents() lets the successor start early.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int LANE_TERMS = 6;   // terms a lane of the lanes kernel keeps in registers
 
 }  // namespace qr

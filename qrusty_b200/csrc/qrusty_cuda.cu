@@ -506,9 +506,30 @@ extern "C" uint64_t qr_kernel_launches(void) { return g_launches.load(); }
 // =====================================================================================
 // plan
 // =====================================================================================
+// Programmatic dependent launch for the canonicalise -> fill -> canonicalise -> ... chain (QR_PDL=1): each kernel is launched
+// while its predecessor still runs and waits for it on the device (griddepcontrol.wait, plan.cuh).  Off by default: measured
+// on the bench step inside a CUDA graph it changes nothing (85.5 against 85.0 us; profiles/r04_summary.md) -- the 10 us
+// round 1 attributed to the canonicalisation were the event-record nodes its bench put between the kernels.
+static bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = getenv("QR_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+static void pdl_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute &attr)
+{
+    if (!pdl_enabled()) return;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+}
+
 static int run_canonicalise(qr_plan *pl, cudaStream_t st)
 {
-    qr::canonicalise_kernel<<<1, qr::K1_THREADS, 0, st>>>(pl->dev, pl->merge_dups);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr;
+    cfg.gridDim = dim3(1, 1, 1); cfg.blockDim = dim3(qr::K1_THREADS, 1, 1); cfg.stream = st;
+    pdl_config(cfg, attr);
+    QR_CUDA(cudaLaunchKernelEx(&cfg, qr::canonicalise_kernel, pl->dev, pl->merge_dups));
     QR_LAUNCH_CHECK("canonicalise_kernel");
     return QR_OK;
 }
@@ -888,8 +909,12 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             // prefix / suffix rows that do not fill a tile
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
-            fn<<<(unsigned)tiles, 32 * cfg->gw, smem, st>>>(
-                pl->dev, (uint32_t)G, s0, row_lo, indptr_base, d_indptr, d_indices, d_data, row_hi - row_lo, ps);
+            cudaLaunchConfig_t lc = {};
+            cudaLaunchAttribute attr;
+            lc.gridDim = dim3((unsigned)tiles, 1, 1); lc.blockDim = dim3(32 * cfg->gw, 1, 1); lc.dynamicSmemBytes = smem; lc.stream = st;
+            if (s0 == row_lo) pdl_config(lc, attr);                  // no edge kernel between the canonicalisation and this launch
+            QR_CUDA(cudaLaunchKernelEx(&lc, fn, pl->dev, (uint32_t)G, s0, row_lo, indptr_base, d_indptr, d_indices, d_data,
+                                       (uint64_t)(row_hi - row_lo), ps));
             QR_LAUNCH_CHECK("fill_staged_kernel");
             lo = s1; hi = row_hi;
         }
