@@ -28,6 +28,7 @@ def main():
 
     rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
     kernel = line[hdr.index("Kernel Name")]
+    if kernel.startswith("void "): kernel = kernel[5:]
     dst = raw
     if len(sys.argv) > 3:
         dst = Path(sys.argv[3]); shutil.copyfile(raw, dst)
