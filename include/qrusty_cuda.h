@@ -95,6 +95,11 @@ QR_API int qr_plan_canonical_terms(const qr_plan *plan, uint64_t *count);
  * ("fill_staged_kernel", "fill_rows_kernel", "fill_lanes_kernel", "fill_blocked_kernel" or
  * "fill_direct_kernel"); a static string, for benchmarks and logs.  Never NULL. */
 QR_API const char *qr_plan_fill_kernel(const qr_plan *plan);
+/* Name of the kernel qr_apply_device / qr_apply_p2p launch for rows [row_lo, row_hi) of this plan with the
+ * default settings: "apply_fold_kernel" (term-rich operators: bucketed terms + in-register Walsh-Hadamard fold,
+ * rows in whole aligned blocks of 1024) or "apply_direct_kernel" (gather).  Builds the fold tables on first use.
+ * A static string; "" on error (qr_last_error). */
+QR_API const char *qr_plan_apply_kernel(qr_plan *plan, uint64_t row_lo, uint64_t row_hi);
 
 /* Re-runs the canonicalisation kernel from the raw term table already in HBM,
  * asynchronously on `stream` (a cudaStream_t, NULL = default stream).  Lets a

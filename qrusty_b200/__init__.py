@@ -131,6 +131,13 @@ class _Plan:
         """Name of the fill kernel an aligned row window of this plan is built with."""
         return (lib.qr_plan_fill_kernel(self.handle) or b"").decode()
 
+    def apply_kernel(self, row_lo=0, row_hi=None):
+        """Name of the kernel a matrix-free H.v on rows [row_lo, row_hi) of this plan runs."""
+        name = (lib.qr_plan_apply_kernel(self.handle, row_lo, self.dim if row_hi is None else row_hi) or b"").decode()
+        if not name:
+            raise _ffi.QrustyCudaError(_ffi.QR_ERR_INVALID, (lib.qr_last_error() or b"").decode())
+        return name
+
     def groups(self):
         x = np.zeros(self.n_groups, np.uint64)
         off = np.zeros(self.n_groups + 1, np.uint32)

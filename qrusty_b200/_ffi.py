@@ -116,7 +116,9 @@ lib.qr_last_d2h_bytes.restype = C.c_uint64
 lib.qr_last_d2h_bytes.argtypes = []
 lib.qr_plan_fill_kernel.restype = C.c_char_p
 lib.qr_plan_fill_kernel.argtypes = [_vp]
-EXPORTS = sorted(list(SIGNATURES) + ["qr_last_error", "qr_version", "qr_kernel_launches", "qr_plan_fill_kernel", "qr_last_d2h_bytes"])
+lib.qr_plan_apply_kernel.restype = C.c_char_p
+lib.qr_plan_apply_kernel.argtypes = [_vp, _u64, _u64]
+EXPORTS = sorted(list(SIGNATURES) + ["qr_last_error", "qr_version", "qr_kernel_launches", "qr_plan_fill_kernel", "qr_plan_apply_kernel", "qr_last_d2h_bytes"])
 
 
 def check(rc):

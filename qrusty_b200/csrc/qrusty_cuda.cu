@@ -25,6 +25,7 @@
 #include "../../include/qrusty_cuda.h"
 #include "apply.cuh"
 #include "apply_tile.cuh"
+#include "apply_fold.cuh"
 #include "canonicalise.cuh"
 #include "compact.cuh"
 #include "fill.cuh"
@@ -153,6 +154,14 @@ struct qr_plan {
     uint64_t n_terms_canonical = 0;
     // lazily allocated scratch
     double2 *dot_partials = nullptr;
+    // term-rich H.v (apply_fold.cuh): bucketed copy of the term table, built at the first apply
+    int fold_state = -1;                   // -1: not looked at yet, 0: the gather kernel serves this operator, 1: the fold kernel does
+    bool fold_blocked = false;             // a group too long for the bucket table: gather kernel only
+    void *fold_slab = nullptr;             // the tables (also read by the partner-tile kernel)
+    qr::FoldDev fold{};
+    // partner-tile H.v (apply_fold.cuh): segments of groups sharing x >> K, per tile size K
+    struct Ptile { void *slab = nullptr; qr::PtileDev dev{}; uint32_t n_seg = 0; };
+    std::map<int, Ptile> ptiles;
 };
 
 struct qr_comm {
@@ -630,6 +639,8 @@ extern "C" int qr_plan_destroy(qr_plan *pl)
     for (auto &kv : pl->tile_plans) if (kv.second.slab) cudaFree(kv.second.slab);
     if (pl->diag_cache) cudaFree(pl->diag_cache);
     if (pl->dot_partials) cudaFree(pl->dot_partials);
+    if (pl->fold_slab) cudaFree(pl->fold_slab);
+    for (auto &kv : pl->ptiles) if (kv.second.slab) cudaFree(kv.second.slab);
     if (pl->slab) cudaFree(pl->slab);
     delete pl;
     return QR_OK;
@@ -1640,6 +1651,162 @@ static uint32_t apply_cut_bit()
     return 21;
 }
 
+
+// ---- term-rich H.v (apply_fold.cuh): tables and kernel choice --------------------------------------
+// The fold kernel pays when the groups a row has to evaluate carry three or more terms on average (molecular
+// Hamiltonians: 5-6); spin chains and lattices (1-2 terms per off-diagonal group, diag(H) cached) stay with the gather
+// kernel.  QR_APPLY_FOLD=0 / 1 overrides (tests, A/B).  Tables: the plan's (z, c') bucketed per group by the three row
+// bits a thread of the kernel owns -- built on the host once per plan (T log T, T <= a few 10^4).
+static int ensure_fold_tables(qr_plan *pl, uint64_t *t_eval_out, uint64_t *g_eval_out)
+{
+    const size_t G = pl->n_groups, T = pl->n_terms_canonical;
+    std::vector<uint32_t> goff(G + 1), gflag(G), gx0(1);
+    QR_CUDA(cudaMemcpy(goff.data(), pl->dev.goff, (G + 1) * 4, cudaMemcpyDeviceToHost));
+    QR_CUDA(cudaMemcpy(gflag.data(), pl->dev.gflag, G * 4, cudaMemcpyDeviceToHost));
+    QR_CUDA(cudaMemcpy(gx0.data(), pl->dev.gx, 4, cudaMemcpyDeviceToHost));
+    uint64_t t_eval = 0, g_eval = 0;
+    for (size_t g = 0; g < G; g++) {
+        if (gflag[g] & 1u) continue;                              // row-independent: gconst
+        if (g == 0 && gx0[0] == 0 && goff[1] >= 3) continue;       // diag(H): cached (ensure_diag_cache)
+        t_eval += goff[g + 1] - goff[g]; g_eval++;
+    }
+    if (t_eval_out) *t_eval_out = t_eval;
+    if (g_eval_out) *g_eval_out = g_eval;
+    if (pl->fold_slab || pl->fold_blocked) return QR_OK;
+    for (size_t g = 0; g < G; g++)
+        if (goff[g + 1] - goff[g] > qr::FOLD_MAX_GROUP_TERMS) { pl->fold_blocked = true; pl->fold_state = 0; return QR_OK; }   // u16 bucket table: gather kernel
+    std::vector<uint32_t> tz(T);
+    std::vector<double2> tc(T);
+    QR_CUDA(cudaMemcpy(tz.data(), pl->dev.tz, T * 4, cudaMemcpyDeviceToHost));
+    QR_CUDA(cudaMemcpy(tc.data(), pl->dev.tc, T * 16, cudaMemcpyDeviceToHost));
+    const size_t o_im = T * 16, o_be = align_up(o_im + T * 8, 16), bytes = o_be + G * 16;
+    std::vector<unsigned char> host(bytes ? bytes : 16, 0);
+    uint32_t *zc = reinterpret_cast<uint32_t *>(host.data());
+    double *im = reinterpret_cast<double *>(host.data() + o_im);
+    uint16_t *be = reinterpret_cast<uint16_t *>(host.data() + o_be);
+    for (size_t g = 0; g < G; g++) {
+        const uint32_t t0 = goff[g], t1 = goff[g + 1];
+        uint32_t cnt[9] = {0};
+        for (uint32_t t = t0; t < t1; t++) cnt[((tz[t] >> qr::FOLD_B0) & 7u) + 1]++;
+        for (int q = 0; q < 8; q++) cnt[q + 1] += cnt[q];
+        for (int q = 0; q < 8; q++) be[g * 8 + q] = (uint16_t)cnt[q + 1];
+        uint32_t pos[8];
+        for (int q = 0; q < 8; q++) pos[q] = t0 + cnt[q];
+        for (uint32_t t = t0; t < t1; t++) {                       // stable: original order inside a bucket
+            const uint32_t d = pos[(tz[t] >> qr::FOLD_B0) & 7u]++;
+            uint64_t re_bits; memcpy(&re_bits, &tc[t].x, 8);
+            zc[4 * (size_t)d] = tz[t]; zc[4 * (size_t)d + 1] = (tz[t] >> qr::FOLD_B0) & 7u;
+            zc[4 * (size_t)d + 2] = (uint32_t)re_bits; zc[4 * (size_t)d + 3] = (uint32_t)(re_bits >> 32);
+            im[d] = tc[t].y;
+        }
+    }
+    QR_CUDA(cudaMalloc(&pl->fold_slab, host.size()));
+    QR_CUDA(cudaMemcpy(pl->fold_slab, host.data(), host.size(), cudaMemcpyHostToDevice));
+    unsigned char *base = static_cast<unsigned char *>(pl->fold_slab);
+    pl->fold.zc = reinterpret_cast<const uint4 *>(base);
+    pl->fold.im = reinterpret_cast<const double *>(base + o_im);
+    pl->fold.bend = reinterpret_cast<const uint4 *>(base + o_be);
+    return QR_OK;
+}
+static int ensure_fold(qr_plan *pl, bool *use)
+{
+    *use = false;
+    const char *env = getenv("QR_APPLY_FOLD");
+    if (env && env[0] == '0') return QR_OK;
+    const bool force = env && env[0] == '1';
+    if (pl->fold_state == 0 && !force) return QR_OK;
+    if (pl->fold_state == 1) { *use = true; return QR_OK; }
+    uint64_t t_eval = 0, g_eval = 0;
+    const int rc = ensure_fold_tables(pl, &t_eval, &g_eval);
+    if (rc != QR_OK) return rc;
+    if (pl->fold_blocked) return QR_OK;
+    if (!force && (g_eval == 0 || t_eval < 3 * g_eval)) { pl->fold_state = 0; return QR_OK; }
+    if (!force) pl->fold_state = 1;
+    *use = true;
+    return QR_OK;
+}
+// the fold kernel's rows: whole CTAs of FOLD_THREADS * FOLD_ROWS rows, aligned so that the three in-thread bits are free
+static bool fold_rows_ok(uint64_t row_lo, uint64_t row_hi)
+{
+    const uint64_t per_cta = (uint64_t)qr::FOLD_THREADS * qr::FOLD_ROWS;
+    return row_hi > row_lo && row_lo % per_cta == 0 && (row_hi - row_lo) % per_cta == 0 && (row_hi - row_lo) / per_cta <= 0x7fffffffull;
+}
+
+
+// ---- partner-tile H.v (apply_fold.cuh, K4c) ---------------------------------------------------------
+// Chosen when the rows are whole aligned tiles, the launch fills the GPU and the masks share their high bits: S segments
+// for G groups cost 16 B * S per row through L2 instead of 16 B * G.  QR_APPLY_PTILE=0 / 1 overrides the choice,
+// QR_APPLY_PTILE_K the tile (10..12 -> 16 / 32 / 64 KB).
+static int ptile_k()
+{
+    if (const char *env = getenv("QR_APPLY_PTILE_K")) { int k = atoi(env); if (k >= 10 && k <= 12) return k; }
+    return 12;
+}
+static int ensure_ptile(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint32_t shard_bits, int *K_out, qr_plan::Ptile **out)
+{
+    *out = nullptr;
+    const char *env = getenv("QR_APPLY_PTILE");
+    const bool force = env && env[0] == '1';
+    if (!force) return QR_OK;                  // opt-in: measured slower than the gather / fold kernels (profiles/r05_summary.md)
+    const int K = ptile_k();
+    *K_out = K;
+    const uint64_t tile = 1ull << K, rows = row_hi - row_lo;
+    if (row_hi <= row_lo || row_lo % tile || rows % tile || (rows >> K) > 0x7fffffffull || shard_bits < (uint32_t)K) return QR_OK;
+    if (!force && (rows >> K) < 2ull * (uint64_t)std::max(pl->n_sm, 1)) return QR_OK;      // too few tiles to fill the GPU
+    auto it = pl->ptiles.find(K);
+    if (it == pl->ptiles.end()) {
+        int rc = host_masks(pl);
+        if (rc != QR_OK) return rc;
+        rc = ensure_fold_tables(pl, nullptr, nullptr);
+        if (rc != QR_OK) return rc;
+        if (pl->fold_blocked) return QR_OK;
+        const uint32_t G = (uint32_t)pl->n_groups;
+        std::vector<uint32_t> g0, hs;
+        for (uint32_t g = 0; g < G; g++)
+            if (g == 0 || (pl->host_gx[g] >> K) != hs.back()) { g0.push_back(g); hs.push_back(pl->host_gx[g] >> K); }
+        g0.push_back(G);
+        qr_plan::Ptile pt;
+        pt.n_seg = (uint32_t)hs.size();
+        std::vector<uint32_t> host(g0);
+        host.insert(host.end(), hs.begin(), hs.end());
+        QR_CUDA(cudaMalloc(&pt.slab, host.size() * 4));
+        cudaError_t e = cudaMemcpy(pt.slab, host.data(), host.size() * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(pt.slab); return fail(QR_ERR_CUDA, std::string("ensure_ptile: ") + cudaGetErrorString(e)); }
+        pt.dev.seg_g0 = static_cast<const uint32_t *>(pt.slab);
+        pt.dev.seg_h = pt.dev.seg_g0 + g0.size();
+        pt.dev.n_seg = pt.n_seg;
+        it = pl->ptiles.emplace(K, pt).first;
+    }
+    // worth it when at least a quarter of the gathers disappear (C3: 1 259 segments for 1 500 groups -> gather)
+    if (!force && 4ull * it->second.n_seg > 3ull * pl->n_groups) return QR_OK;
+    *out = &it->second;
+    return QR_OK;
+}
+template <int K, int NBUF>
+static int launch_ptile_k(qr_plan *pl, const qr_plan::Ptile &pt, uint64_t row_lo, uint64_t row_hi, const double2 *v, double2 *y,
+                          const double2 *diag, const double *diag_re, const qr::ApplyPeerArgs &pa, cudaStream_t st)
+{
+    auto kern = qr::apply_ptile_kernel<K, NBUF>;
+    const size_t smem = (size_t)NBUF * (16u << K);
+    QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((row_hi - row_lo) >> K), 1 << (K - 3), smem, st>>>(pl->dev, pl->fold, pt.dev, row_lo, v, y, diag, diag_re, pa);
+    QR_LAUNCH_CHECK("apply_ptile_kernel");
+    return QR_OK;
+}
+static int launch_ptile(qr_plan *pl, int K, const qr_plan::Ptile &pt, uint64_t row_lo, uint64_t row_hi, const double2 *v, double2 *y,
+                        const double2 *diag, const double *diag_re, const qr::ApplyPeerArgs &pa, cudaStream_t st)
+{
+    int nbuf = 3;
+    if (const char *env = getenv("QR_APPLY_PTILE_NBUF")) { int b = atoi(env); if (b >= 2 && b <= 4) nbuf = b; }
+    if (K == 12) return nbuf == 2 ? launch_ptile_k<12, 2>(pl, pt, row_lo, row_hi, v, y, diag, diag_re, pa, st)
+                                  : launch_ptile_k<12, 3>(pl, pt, row_lo, row_hi, v, y, diag, diag_re, pa, st);
+    if (K == 11) return nbuf == 2 ? launch_ptile_k<11, 2>(pl, pt, row_lo, row_hi, v, y, diag, diag_re, pa, st)
+                                  : launch_ptile_k<11, 3>(pl, pt, row_lo, row_hi, v, y, diag, diag_re, pa, st);
+    return nbuf == 2 ? launch_ptile_k<10, 2>(pl, pt, row_lo, row_hi, v, y, diag, diag_re, pa, st)
+         : nbuf == 4 ? launch_ptile_k<10, 4>(pl, pt, row_lo, row_hi, v, y, diag, diag_re, pa, st)
+                     : launch_ptile_k<10, 3>(pl, pt, row_lo, row_hi, v, y, diag, diag_re, pa, st);
+}
+
 static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double2 *v, double2 *y, cudaStream_t st)
 {
     const uint64_t rows = row_hi - row_lo;
@@ -1696,9 +1863,35 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
             return launch_tile<false>(pl, *tb, a, row_lo, y, nullptr, nullptr, st);
         }
     }
+    {
+        int K = 0; qr_plan::Ptile *pt = nullptr;
+        rc = ensure_ptile(pl, row_lo, row_hi, 32u, &K, &pt);
+        if (rc != QR_OK) return rc;
+        if (pt) return launch_ptile(pl, K, *pt, row_lo, row_hi, v, y, diag, diag_re, qr::ApplyPeerArgs{}, st);
+    }
+    bool fold = false;
+    if (fold_rows_ok(row_lo, row_hi)) { rc = ensure_fold(pl, &fold); if (rc != QR_OK) return rc; }
+    if (fold) {
+        const uint64_t fctas = rows / ((uint64_t)qr::FOLD_THREADS * qr::FOLD_ROWS);
+        qr::apply_fold_kernel<<<(unsigned)fctas, qr::FOLD_THREADS, 0, st>>>(pl->dev, pl->fold, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re, qr::ApplyPeerArgs{});
+        QR_LAUNCH_CHECK("apply_fold_kernel");
+        return QR_OK;
+    }
     qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re, qr::ApplyPeerArgs{});
     QR_LAUNCH_CHECK("apply_direct_kernel");
     return QR_OK;
+}
+
+extern "C" const char *qr_plan_apply_kernel(qr_plan *pl, uint64_t row_lo, uint64_t row_hi)
+{
+    if (!pl || row_lo >= row_hi || row_hi > pl->dim) { fail(QR_ERR_INVALID, "qr_plan_apply_kernel: bad argument"); return ""; }
+    if (cudaSetDevice(pl->device) != cudaSuccess) { fail(QR_ERR_CUDA, "qr_plan_apply_kernel: cudaSetDevice"); return ""; }
+    int K = 0; qr_plan::Ptile *pt = nullptr;
+    if (ensure_ptile(pl, row_lo, row_hi, 32u, &K, &pt) != QR_OK) return "";
+    if (pt) return "apply_ptile_kernel";
+    bool fold = false;
+    if (fold_rows_ok(row_lo, row_hi) && ensure_fold(pl, &fold) != QR_OK) return "";
+    return fold ? "apply_fold_kernel" : "apply_direct_kernel";
 }
 
 extern "C" int qr_apply_device(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double *d_v, double *d_y, void *stream)
@@ -2201,11 +2394,26 @@ extern "C" int qr_apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_sha
         // every rank's shard is complete before anyone reads it ...
         QR_NCCL(nccl().AllReduce(cm->d_scratch, cm->d_scratch, 1, ncclDouble, ncclSum, cm->comm, st));
     }
-    const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
-    const uint64_t ctas = (shard + per_cta - 1) / per_cta;
-    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(
-        pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa);
-    QR_LAUNCH_CHECK("apply_direct_kernel(p2p)");
+    bool fold = false;
+    int ptK = 0; qr_plan::Ptile *ptp = nullptr;
+    rc = ensure_ptile(pl, row_lo, row_hi, m, &ptK, &ptp);
+    if (rc != QR_OK) return rc;
+    if (!ptp && fold_rows_ok(row_lo, row_hi)) { rc = ensure_fold(pl, &fold); if (rc != QR_OK) return rc; }
+    if (ptp) {                                                     // same choice, same kernel as apply_rows: the two forms agree bit for bit
+        rc = launch_ptile(pl, ptK, *ptp, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa, st);
+        if (rc != QR_OK) return rc;
+    } else if (fold) {
+        const uint64_t fctas = shard / ((uint64_t)qr::FOLD_THREADS * qr::FOLD_ROWS);
+        qr::apply_fold_kernel<<<(unsigned)fctas, qr::FOLD_THREADS, 0, st>>>(
+            pl->dev, pl->fold, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa);
+        QR_LAUNCH_CHECK("apply_fold_kernel(p2p)");
+    } else {
+        const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
+        const uint64_t ctas = (shard + per_cta - 1) / per_cta;
+        qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(
+            pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa);
+        QR_LAUNCH_CHECK("apply_direct_kernel(p2p)");
+    }
     // ... and nobody overwrites a shard while a peer may still be reading it
     if (flags) {
         qr::p2p_done_kernel<<<1, 32, 0, st>>>(cm->d_flags, cm->d_peer_flags, (uint32_t)P, (uint32_t)cm->rank, need_mask, epoch);

@@ -619,7 +619,10 @@ def test_apply_matrix_free(fixtures, name):
     rng = np.random.default_rng(4)
     v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
     ref = O.spmv(indptr, indices, data, v)
-    bound = O.spmv(indptr, indices, np.abs(data).astype(np.complex128), np.abs(v).astype(np.complex128)).real
+    # north_star's contract for a value: |d - d_ref| <= 1e-12 * sum_{t in group} |c'_t| (the term-rich kernels fold a group's
+    # terms in bucket order, so a value that cancels is accurate relative to the sum of its terms, not to itself)
+    pa = params.copy(); pa["re"] = np.hypot(params["re"], params["im"]); pa["im"] = 0.0; pa["z"] = 0
+    bound = O.spmv(*O.build_csr(pa, n), np.abs(v).astype(np.complex128)).real
     op = make_op(labels, coeffs)
     y = op.apply(v)
     assert np.all(np.abs(y - ref) <= 1e-12 * bound + 1e-300)
@@ -716,6 +719,93 @@ def test_apply_two_pass(fixtures, monkeypatch, name, cut):
         blk = dim // parts
         ys = np.concatenate([_apply_block(plan, p * blk, (p + 1) * blk, dv) for p in range(parts)])
         assert np.abs(ys - y0).max() <= tol, parts
+
+
+FOLD_OPS = {
+    "H6": lambda fx: fx["H6"], "H8": lambda fx: fx["H8"],
+    "random_n14": lambda fx: H.random_pauli_sum(14, 300, 200, 30, 11),           # complex coefficients, long groups
+    "random_n13_rich": lambda fx: H.random_pauli_sum(13, 4000, 150, 40, 5),       # ~27 terms per group
+    "xxz16": lambda fx: H.xxz_chain(16, 1.0, 0.7), "tfim_4x4": lambda fx: H.tfim_lattice(4, 4, 1.0, 3.0),
+}
+
+
+@pytest.mark.parametrize("name", list(FOLD_OPS))
+def test_apply_fold(fixtures, monkeypatch, name):
+    """Term-rich H.v (apply_fold.cuh: terms bucketed by the thread's three row bits, in-register Walsh-Hadamard
+    fold) against the gather kernel and the oracle, forced onto every operator shape: whole vector, aligned row
+    blocks of a full vector, and a window that is not a whole number of CTAs (must fall back to the gather kernel)."""
+    labels, coeffs = FOLD_OPS[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    dim = 1 << n
+    v = H.lanczos_start_vector(0, dim, seed=41)
+    dv = DeviceBuffer(dim * 16); dv.upload(v)
+    monkeypatch.setenv("QR_APPLY_PTILE", "0")
+    monkeypatch.setenv("QR_APPLY_FOLD", "0")
+    plan0 = make_op(labels, coeffs).plan()
+    assert plan0.apply_kernel() == "apply_direct_kernel"
+    y0 = _apply_block(plan0, 0, dim, dv)
+    monkeypatch.setenv("QR_APPLY_FOLD", "1")
+    plan = make_op(labels, coeffs).plan()
+    assert plan.apply_kernel() == "apply_fold_kernel"
+    assert plan.apply_kernel(0, dim - 512) == "apply_direct_kernel"
+    y1 = _apply_block(plan, 0, dim, dv)
+    absH = np.abs(params["re"] + 1j * params["im"]).sum()
+    tol = 1e-12 * absH * np.abs(v).max()
+    assert np.abs(y1 - y0).max() <= tol
+    rows = np.random.default_rng(14).integers(0, dim, 512).astype(np.uint64)
+    ref = O.apply_rows(params, rows, v)
+    assert np.abs(y1[rows.astype(np.int64)] - ref).max() <= tol
+    assert np.array_equal(u64(_apply_block(plan, 0, dim, dv)), u64(y1))            # deterministic
+    for parts in (2, 4):
+        blk = dim // parts
+        ys = np.concatenate([_apply_block(plan, p * blk, (p + 1) * blk, dv) for p in range(parts)])
+        assert np.array_equal(u64(ys), u64(y1)), parts                              # a row's value does not depend on the block it is in
+    lo, hi = 1024, dim - 512
+    assert np.abs(_apply_block(plan, lo, hi, dv) - y0[lo:hi]).max() <= tol
+
+
+@pytest.mark.parametrize("name", list(FOLD_OPS))
+@pytest.mark.parametrize("K,nbuf", [("10", "2"), ("10", "4"), ("11", "3"), ("12", "3"), ("12", "2")])
+def test_apply_ptile(fixtures, monkeypatch, name, K, nbuf):
+    """Partner-tile H.v (apply_fold.cuh, K4c): one TMA bulk load of the partner tile per segment of groups sharing
+    x >> K, values as the fold kernel's -- bit-identical to it, within tolerance of the gather kernel and the oracle;
+    whole vector and aligned row blocks of a full vector."""
+    labels, coeffs = FOLD_OPS[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    dim = 1 << n
+    v = H.lanczos_start_vector(0, dim, seed=43)
+    dv = DeviceBuffer(dim * 16); dv.upload(v)
+    monkeypatch.setenv("QR_APPLY_PTILE", "0")
+    monkeypatch.setenv("QR_APPLY_FOLD", "0")
+    y0 = _apply_block(make_op(labels, coeffs).plan(), 0, dim, dv)
+    monkeypatch.setenv("QR_APPLY_FOLD", "1")
+    yf = _apply_block(make_op(labels, coeffs).plan(), 0, dim, dv)
+    monkeypatch.setenv("QR_APPLY_PTILE", "1")
+    monkeypatch.setenv("QR_APPLY_PTILE_K", K)
+    monkeypatch.setenv("QR_APPLY_PTILE_NBUF", nbuf)
+    plan = make_op(labels, coeffs).plan()
+    assert plan.apply_kernel() == "apply_ptile_kernel"
+    assert plan.apply_kernel(0, dim - 512) != "apply_ptile_kernel"
+    y1 = _apply_block(plan, 0, dim, dv)
+    assert np.array_equal(u64(y1), u64(yf))                                        # same arithmetic as the fold kernel
+    absH = np.abs(params["re"] + 1j * params["im"]).sum()
+    tol = 1e-12 * absH * np.abs(v).max()
+    assert np.abs(y1 - y0).max() <= tol
+    rows = np.random.default_rng(15).integers(0, dim, 512).astype(np.uint64)
+    assert np.abs(y1[rows.astype(np.int64)] - O.apply_rows(params, rows, v)).max() <= tol
+    for parts in (2, 4):
+        blk = dim // parts
+        ys = np.concatenate([_apply_block(plan, p * blk, (p + 1) * blk, dv) for p in range(parts)])
+        assert np.array_equal(u64(ys), u64(y1)), parts
+
+
+def test_apply_fold_is_the_default_for_term_rich_operators(fixtures, monkeypatch):
+    monkeypatch.delenv("QR_APPLY_FOLD", raising=False)
+    assert make_op(*fixtures["H8"]).plan().apply_kernel() == "apply_fold_kernel"
+    assert make_op(*H.xxz_chain(16, 1.0, 0.7)).plan().apply_kernel() == "apply_direct_kernel"
+    assert make_op(*H.tfim_lattice(4, 4, 1.0, 3.0)).plan().apply_kernel() == "apply_direct_kernel"
+    assert make_op(*H.heisenberg_chain(18)).plan().apply_kernel() == "apply_direct_kernel"
+    assert make_op(*fixtures["H2"]).plan().apply_kernel() == "apply_direct_kernel"   # 16 rows: less than one CTA of the fold kernel
 
 
 # ---- accel.rs:374-393 (test_it.py:232-269, lib.rs:921-990) ------------------------------------
