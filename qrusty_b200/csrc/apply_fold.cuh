@@ -56,15 +56,17 @@ __device__ __forceinline__ void wht8(double (&S)[8])
 // (XOR of pre-shifted copies of z), and fma(+-1.0, c, S) is the sign flip and the addition in one instruction.  IM selects
 // the component: groups that are not real are swept twice (re, then im), so one set of 8 accumulators serves both.
 constexpr uint32_t FOLD_WHT_MIN = 12;      // groups with more terms go through the bucket sums + Walsh-Hadamard butterfly
+// `zcs` = the group's entries of FoldDev::zc (global memory, or the copy the fold kernel stages in shared memory),
+// `ims` = its entries of FoldDev::im.
 template <bool IM>
-__device__ __forceinline__ void fold_short_sweep(const FoldDev &f, uint32_t t0, uint32_t t1, uint32_t r0, double (&S)[8])
+__device__ __forceinline__ void fold_short_sweep(const uint4 *zcs, const double *ims, uint32_t n_t, uint32_t r0, double (&S)[8])
 {
 #pragma unroll
     for (int e = 0; e < 8; e++) S[e] = 0.0;
 #pragma unroll 2
-    for (uint32_t t = t0; t < t1; t++) {
-        const uint4 zc = __ldg(&f.zc[t]);
-        const double c = IM ? __ldg(&f.im[t]) : __hiloint2double((int)zc.w, (int)zc.z);
+    for (uint32_t t = 0; t < n_t; t++) {
+        const uint4 zc = zcs[t];
+        const double c = IM ? __ldg(&ims[t]) : __hiloint2double((int)zc.w, (int)zc.z);
         const uint32_t p0 = (uint32_t)__popc(r0 & zc.x);
         const uint32_t z1 = zc.x >> FOLD_B0, z2 = zc.x >> (FOLD_B0 + 1), z3 = zc.x >> (FOLD_B0 + 2);
 #pragma unroll
@@ -88,6 +90,7 @@ apply_fold_kernel(PlanDev p, FoldDev f, uint32_t G, uint64_t row_lo, uint64_t ro
     __shared__ GroupDesc sd[FOLD_BATCH];
     __shared__ uint4 sb[FOLD_BATCH];
     __shared__ const double2 *sv[FOLD_BATCH];
+    __shared__ uint4 sterm[FOLD_BATCH * FOLD_WHT_MIN];             // the short groups' terms: warp-uniform LDS instead of an L1 round trip per term
     const bool PEERS = pa.n_peers > 1u;
     // host-checked: row_lo and row_hi - row_lo are multiples of E * TH, so bits B0..B0+2 of r0 are clear
     const uint32_t r0 = (uint32_t)(row_lo + (uint64_t)blockIdx.x * (TH * E)) + threadIdx.x;
@@ -123,6 +126,11 @@ apply_fold_kernel(PlanDev p, FoldDev f, uint32_t G, uint64_t row_lo, uint64_t ro
             sv[i] = PEERS ? pa.peer[my_rank ^ (d.x >> pa.shard_bits)] : v;
         }
         __syncthreads();
+        for (uint32_t q = threadIdx.x; q < nb * FOLD_WHT_MIN; q += TH) {
+            const uint32_t i = q / FOLD_WHT_MIN, j = q - i * FOLD_WHT_MIN, t0 = sd[i].t0, n = sd[i].t1 - t0;
+            if (n <= FOLD_WHT_MIN && j < n && !(sd[i].flag & 1u)) sterm[q] = __ldg(&f.zc[t0 + j]);
+        }
+        __syncthreads();
         for (uint32_t k = 0; k < nb; k++) {
             const GroupDesc d = sd[k];
             const double2 *vb = sv[k];
@@ -144,11 +152,11 @@ apply_fold_kernel(PlanDev p, FoldDev f, uint32_t G, uint64_t row_lo, uint64_t ro
             for (int e = 0; e < E; e++) w[e] = ld_nc_double2(&vb[(r0 + ((uint32_t)e << B0)) ^ d.x]);
             double S[E];
             if (n_t <= FOLD_WHT_MIN) {
-                fold_short_sweep<false>(f, d.t0, d.t1, r0, S);
+                fold_short_sweep<false>(&sterm[k * FOLD_WHT_MIN], f.im + d.t0, n_t, r0, S);
 #pragma unroll
                 for (int e = 0; e < E; e++) { yr[e] = __fma_rn(S[e], w[e].x, yr[e]); yi[e] = __fma_rn(S[e], w[e].y, yi[e]); }
                 if (!real) {
-                    fold_short_sweep<true>(f, d.t0, d.t1, r0, S);
+                    fold_short_sweep<true>(&sterm[k * FOLD_WHT_MIN], f.im + d.t0, n_t, r0, S);
 #pragma unroll
                     for (int e = 0; e < E; e++) { yr[e] = __fma_rn(-S[e], w[e].y, yr[e]); yi[e] = __fma_rn(S[e], w[e].x, yi[e]); }
                 }
@@ -288,14 +296,14 @@ apply_ptile_kernel(PlanDev p, FoldDev f, PtileDev pt, uint64_t row_lo,
             }
             double S8[E];
             if (n_t <= FOLD_WHT_MIN) {
-                fold_short_sweep<false>(f, d.t0, d.t1, r0, S8);
+                fold_short_sweep<false>(f.zc + d.t0, f.im + d.t0, n_t, r0, S8);
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const double2 w = tb[pidx ^ ((uint32_t)e << B0)];
                     yr[e] = __fma_rn(S8[e], w.x, yr[e]); yi[e] = __fma_rn(S8[e], w.y, yi[e]);
                 }
                 if (!real) {
-                    fold_short_sweep<true>(f, d.t0, d.t1, r0, S8);
+                    fold_short_sweep<true>(f.zc + d.t0, f.im + d.t0, n_t, r0, S8);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         const double2 w = tb[pidx ^ ((uint32_t)e << B0)];
