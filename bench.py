@@ -635,7 +635,7 @@ def run_b200(args, rank, local_rank, world):
         if fx_path.exists():
             import gzip
             fxs = json.load(gzip.open(fx_path))
-            for key, log2_rows in (("H8", 16), ("H12", 18)):
+            for key, log2_rows in (("H8", 16), ("H10", 17), ("H12", 18)):
                 if key not in fxs:
                     continue
                 fx = fxs[key]
@@ -651,17 +651,28 @@ def run_b200(args, rank, local_rank, world):
                          "achieved_GBps": mbytes / ms / 1e6, "frac_of_peak": mbytes / ms / 1e6 / peak}
                 del m_ip, m_ix, m_dt
                 extras["molecular" if key == "H12" else "molecular_" + key] = entry
-                if key == "H12":
-                    # matrix-free H.v on the whole 2^24 vector: every group re-evaluates its terms per row (compute-bound)
+                if key in ("H10", "H12"):
+                    # matrix-free H.v on the whole vector (H10: 2^20, the 20-qubit operator of main10.rs; H12: 2^24): every
+                    # group re-evaluates its terms per row (compute-bound) -- apply_fold_kernel, with the gather kernel
+                    # (QR_APPLY_FOLD=0, a fresh plan) timed beside it
                     mdim = mplan.dim
                     d_v, d_y = DeviceBuffer(mdim * 16, device), DeviceBuffer(mdim * 16, device)
                     upload_start_vector(rig, H, d_v, 0, mdim)
                     ms = timed(lambda: call("qr_apply_device", mplan.handle, 0, mdim, d_v.ptr, d_y.ptr, stream), 3, warm=1)
                     n_m, mparams = O.make_params(fx["labels"], [complex(a, b) for a, b in fx["coeffs"]])
                     err = verify_hv(rig, H, mparams, 0, mdim, d_y, 64, 77)
-                    extras["hv_molecular"] = {"workload": "H12 fixture, full vector (2^24)", "n_terms": mplan.n_terms, "n_groups": mG, "ms": ms,
-                                              "gbs_compulsory": 32.0 * mdim / ms / 1e6, "term_row_evaluations_per_s": mplan.n_terms * mdim / ms * 1e3,
-                                              "max_rel_err": err}
+                    os.environ["QR_APPLY_FOLD"] = "0"
+                    try:
+                        gplan = Q.SparsePauliOp([Q.Pauli(l) for l in fx["labels"]], [complex(a, b) for a, b in fx["coeffs"]]).plan(device)
+                        ms_gather = timed(lambda: call("qr_apply_device", gplan.handle, 0, mdim, d_v.ptr, d_y.ptr, stream), 3, warm=1)
+                        del gplan
+                    finally:
+                        del os.environ["QR_APPLY_FOLD"]
+                    extras["hv_molecular" if key == "H12" else "hv_molecular_" + key] = {
+                        "workload": "%s fixture, full vector (2^%d)" % (key, n_m), "n_terms": mplan.n_terms, "n_groups": mG,
+                        "kernel": mplan.apply_kernel(), "ms": ms, "gather_kernel_ms": ms_gather,
+                        "gbs_compulsory": 32.0 * mdim / ms / 1e6, "term_row_evaluations_per_s": mplan.n_terms * mdim / ms * 1e3,
+                        "max_rel_err": err}
                     del d_v, d_y
                 del mplan, mop
 

@@ -92,7 +92,7 @@ QR_API int qr_plan_groups(const qr_plan *plan, uint64_t *xmask, uint32_t *group_
  * merged term i, for i < the returned count). */
 QR_API int qr_plan_canonical_terms(const qr_plan *plan, uint64_t *count);
 /* Name of the fill kernel qr_build_rows_device launches for an aligned row window of this plan
- * ("fill_staged_kernel", "fill_rows_kernel", "fill_lanes_kernel", "fill_blocked_kernel" or
+ * ("fill_staged_kernel", "fill_staged_swz_kernel", "fill_rows_kernel", "fill_lanes_kernel", "fill_blocked_kernel" or
  * "fill_direct_kernel"); a static string, for benchmarks and logs.  Never NULL. */
 QR_API const char *qr_plan_fill_kernel(const qr_plan *plan);
 /* Name of the kernel qr_apply_device / qr_apply_p2p launch for rows [row_lo, row_hi) of this plan with the
@@ -177,6 +177,15 @@ QR_API int qr_count_kept_device(uint64_t n_rows, uint64_t n_groups, const double
 QR_API int qr_compact_rows_device(uint64_t n_rows, uint64_t n_groups, const uint64_t *d_indices,
                            const double *d_data, double tol, const uint64_t *d_indptr,
                            uint64_t *d_indices_out, double *d_data_out, void *stream);
+/* The same two passes for ANY device-resident CSR (rows of any length: a matrix wrapped by SpMat::new_unchecked,
+ * pyqrusty/src/lib.rs:104-116, read back from disk, or already compacted) -- util::csmatrix_nz and
+ * csmatrix_eliminate_zeroes take any CsMat (util.rs:144-171).  d_indptr_in is the stored indptr (n_rows + 1 entries;
+ * its first entry may be a global offset), d_indptr_out receives the new local indptr. */
+QR_API int qr_csr_count_kept_device(uint64_t n_rows, const uint64_t *d_indptr_in, const double *d_data, double tol,
+                                    uint64_t *d_indptr_out, uint64_t *nnz_out, void *stream);
+QR_API int qr_csr_compact_device(uint64_t n_rows, const uint64_t *d_indptr_in, const uint64_t *d_indices, const double *d_data,
+                                 double tol, const uint64_t *d_indptr, uint64_t *d_indices_out, double *d_data_out,
+                                 void *stream);
 
 /* Fused drop-zeros build: the CSR that csmatrix_eliminate_zeroes (util.rs:154-171) produces from
  * rows [row_lo,row_hi) of the reference's build, without writing the explicit zeros first.

@@ -443,12 +443,24 @@ class SpMat:
                             % ("eliminate" if compact else "count"))
         kept_total, out = 0, []
         for s in shards:
-            if s.plan is None or getattr(s, "compacted", False):
-                raise Exception("zero elimination is implemented for matrices built from a SparsePauliOp")
-            rows, G = s.hi - s.lo, s.plan.n_groups
             call("qr_set_device", s.device)
+            rows = s.hi - s.lo
             indptr = DeviceBuffer((rows + 1) * 8, s.device)
             kept = C.c_uint64()
+            if s.plan is None or getattr(s, "compacted", False):
+                # any CSR (new_unchecked, read back from disk, already compacted): driven by the stored indptr
+                call("qr_csr_count_kept_device", rows, s.indptr.ptr, s.data.ptr, float(tolerance), indptr.ptr, C.byref(kept), None)
+                kept_total += kept.value
+                if compact:
+                    indices = DeviceBuffer(max(kept.value * 8, 16), s.device)
+                    data = DeviceBuffer(max(kept.value * 16, 16), s.device)
+                    call("qr_csr_compact_device", rows, s.indptr.ptr, s.indices.ptr, s.data.ptr, float(tolerance), indptr.ptr,
+                         indices.ptr, data.ptr, None)
+                    c = _Shard(s.plan, s.lo, s.hi, indptr, indices, data, off=s.off, local=True)
+                    c.nnz, c.compacted = kept.value, True
+                    out.append(c)
+                continue
+            G = s.plan.n_groups
             fused = s.data is None
             if fused:
                 call("qr_build_compact_count", s.plan.handle, s.lo, s.hi, float(tolerance), indptr.ptr, C.byref(kept), None)
@@ -471,19 +483,9 @@ class SpMat:
 
     def count_zeros(self, tolerance=1e-7):
         """Entries with norm <= tolerance (util.rs:144-152)."""
-        shards = self._live("cannot count zeroes of an exported sparse matrix")
-        if all(getattr(s, "compacted", False) for s in shards):
-            return self._count_zeros_compacted(tolerance)
+        self._live("cannot count zeroes of an exported sparse matrix")
         kept, _ = self._kept(tolerance, compact=False)
         return self.nnz() - kept
-
-    def _count_zeros_compacted(self, tolerance):
-        # an already compacted matrix: count on the stored values (generic sparse algebra, off the path)
-        n = 0
-        for s in self._shards:
-            d = s.data.download(np.empty(s.nnz, np.complex128)) if s.nnz else np.empty(0, np.complex128)
-            n += int(np.count_nonzero(np.hypot(d.real, d.imag) <= tolerance))
-        return n
 
     def eliminate_zeros(self, tolerance=1e-7):
         """New SpMat holding only entries with norm > tolerance (util.rs:154-171)."""

@@ -57,6 +57,8 @@ SIGNATURES = {
     "qr_build_rows_device": [_vp, _u64, _u64, _vp, _vp, _vp, _u32, _vp],
     "qr_build_host": [_vp, _u64, _u64, _vp, _vp, _vp, _u32],
     "qr_write_rawio": [_vp, _u64, _u64, C.c_char_p],
+    "qr_csr_count_kept_device": [_u64, _vp, _vp, C.c_double, _vp, C.POINTER(_u64), _vp],
+    "qr_csr_compact_device": [_u64, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp],
     "qr_apply_device": [_vp, _u64, _u64, _vp, _vp, _vp],
     "qr_apply_host": [_vp, _vp, _vp],
     "qr_diagonal_device": [_vp, _u64, _u64, _vp, _vp],

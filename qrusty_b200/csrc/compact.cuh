@@ -241,4 +241,49 @@ fill_compact_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, 
     }
 }
 
+// ---- any CSR (rows of any length: a matrix wrapped by SpMat::new_unchecked, read back from disk, or already compacted) --
+// util::csmatrix_nz / csmatrix_eliminate_zeroes (util.rs:144-171) take any CsMat.  Warp per row, driven by the stored
+// indptr (whose first entry may be a global offset): same keep rule, same order.
+__global__ void __launch_bounds__(K2_THREADS)
+csr_count_kept_kernel(uint64_t n_rows, const uint64_t *__restrict__ indptr_in, const double2 *__restrict__ data, double tol,
+                      uint64_t *__restrict__ counts)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = (uint64_t)gridDim.x * (K2_THREADS / 32), base = indptr_in[0];
+    for (uint64_t row = (uint64_t)blockIdx.x * (K2_THREADS / 32) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+        const uint64_t k1 = indptr_in[row + 1] - base;
+        uint32_t n = 0;
+        for (uint64_t k = indptr_in[row] - base + lane; k < k1; k += 32u) n += keep_entry(data[k], tol) ? 1u : 0u;
+        n = __reduce_add_sync(FULL_MASK, n);
+        if (lane == 0) counts[row + 1] = n;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
+}
+
+__global__ void __launch_bounds__(K2_THREADS)
+csr_compact_rows_kernel(uint64_t n_rows, const uint64_t *__restrict__ indptr_in, const uint64_t *__restrict__ indices_in,
+                        const double2 *__restrict__ data_in, double tol, const uint64_t *__restrict__ indptr,
+                        uint64_t *__restrict__ indices_out, double2 *__restrict__ data_out)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = (uint64_t)gridDim.x * (K2_THREADS / 32), base = indptr_in[0];
+    for (uint64_t row = (uint64_t)blockIdx.x * (K2_THREADS / 32) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+        uint64_t out = indptr[row];
+        const uint64_t k1 = indptr_in[row + 1] - base;
+        for (uint64_t k0 = indptr_in[row] - base; k0 < k1; k0 += 32u) {
+            const uint64_t k = k0 + lane;
+            double2 d = make_double2(0.0, 0.0);
+            if (k < k1) d = data_in[k];
+            const bool keep = k < k1 && keep_entry(d, tol);
+            const unsigned mask = __ballot_sync(FULL_MASK, keep);
+            if (keep) {
+                const uint64_t pos = out + __popc(mask & ((1u << lane) - 1u));
+                data_out[pos] = d;
+                indices_out[pos] = indices_in[k];
+            }
+            out += __popc(mask);
+        }
+    }
+}
+
 }  // namespace qr

@@ -230,6 +230,90 @@ fill_staged_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, u
 }
 
 // ---------------------------------------------------------------------------------
+// Staged kernel, swizzled tile (even G).  The lanes of a store hold one row each, G*16 bytes apart: with G even they
+// share shared-memory banks (2-way; 4-way for G = 4 mod 8: XXZ n = 19 at 0.72 of peak; 8-way for G = 0 mod 8).  Here the
+// tile is not the final byte order: it is cut into column boxes of 128 bytes per row (8 entries of data, 16 column ids)
+// laid out as the TMA's 128-byte swizzle wants them -- row i of a box at i * 128, its 16-byte chunk c at c ^ (i & 7) -- so
+// the eight lanes of a store phase always fall on eight different chunks, and the boxes leave through 2-D tensor maps of
+// the output arrays (cp.async.bulk.tensor.2d.global.shared::cta, SASS UTMASTG), which undo the swizzle on the way out.
+// The last box of a row may reach past column G: the TMA clips it.  Values, order and bytes written are the staged
+// kernel's.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tensor_store_2d(const void *tmap, int32_t x, int32_t y, const void *ssrc)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(tmap), "r"(x), "r"(y), "r"((uint32_t)__cvta_generic_to_shared(ssrc)) : "memory");
+}
+
+struct __align__(64) TensorMap { unsigned char bytes[128]; };      // a CUtensorMap, opaque to the device code
+
+template <int E, int GW>
+__global__ void __launch_bounds__(32 * GW)
+fill_staged_swz_kernel(PlanDev p, uint32_t G, uint64_t tile_row0, uint64_t row_lo, uint64_t indptr_base,
+                       uint64_t *__restrict__ indptr, uint64_t indptr_last_row,
+                       const __grid_constant__ TensorMap tm_data, const __grid_constant__ TensorMap tm_idx)
+{
+    constexpr uint32_t R = 32u * E, BOX = R * 128u;                // bytes of one box: R rows of 128 bytes
+    extern __shared__ unsigned char smem_dyn[];
+    // the swizzle pattern is a function of the shared-memory ADDRESS: boxes start on 1024-byte boundaries
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_dyn);
+    unsigned char *tile = smem_dyn + ((1024u - (s0 & 1023u)) & 1023u);
+    const uint32_t nbd = (G + 7u) >> 3, nbi = (G + 15u) >> 4;      // data / column-id boxes per row
+    unsigned char *sdat = tile, *sidx = tile + (size_t)nbd * BOX;
+
+    const uint32_t lane = threadIdx.x & 31u, gw = threadIdx.x >> 5;
+    const uint64_t tile_base = tile_row0 + (uint64_t)blockIdx.x * R;
+    const uint32_t tbase = (uint32_t)tile_base;
+    pdl_wait();
+    pdl_launch_dependents();
+    uint32_t r[E], ob[E];                                          // row, byte offset of the row inside a box
+#pragma unroll
+    for (int e = 0; e < E; e++) { r[e] = tbase + 32u * e + lane; ob[e] = (32u * e + lane) * 128u; }
+    const uint32_t sw = lane & 7u;                                 // (row & 7): 32 * e does not touch it
+
+    for (uint32_t g = gw; g < G; g += GW) {
+        const GroupDesc d = p.gdesc[g];
+        const uint32_t c = __ldg(&p.cnt[g * 32u + lane]);
+        const uint32_t lo = __ldg(&p.lr5[g * 32u + ((d.x ^ lane) & 31u)]);
+        double ar[E], ai[E];
+        if (d.flag & 1u) {
+#pragma unroll
+            for (int e = 0; e < E; e++) { ar[e] = d.cre; ai[e] = d.cim; }
+        } else {
+            group_values<E>(p, d.t0, d.t1, r, ar, ai);
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint32_t bit = ((d.x ^ (tbase + 32u * e)) >> lane) & 1u;
+            const uint32_t slot = __reduce_add_sync(0xffffffffu, (lane >= 5u && bit) ? c : 0u) + lo;
+            const uint32_t doff = (slot >> 3) * BOX + ob[e] + (((slot & 7u) ^ sw) << 4);
+            const uint32_t ioff = (slot >> 4) * BOX + ob[e] + (((((slot & 15u) >> 1) ^ sw) << 4) | ((slot & 1u) << 3));
+            *reinterpret_cast<double2 *>(sdat + doff) = make_double2(ar[e], ai[e]);
+            *reinterpret_cast<uint64_t *>(sidx + ioff) = (uint64_t)(r[e] ^ d.x);
+        }
+    }
+    if (gw == 0 && indptr != nullptr) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint64_t lr = tile_base + 32u * e + lane - row_lo;
+            indptr[lr] = indptr_base + lr * G;
+            if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (gw == 0) {
+        const int32_t y = (int32_t)(tile_base - row_lo);            // row coordinate in the output arrays (host-checked: < 2^31)
+        for (uint32_t b = lane; b < nbd + nbi; b += 32u) {
+            if (b < nbd) tensor_store_2d(&tm_data, (int32_t)(b * 16u), y, sdat + (size_t)b * BOX);       // 16 doubles = 8 entries
+            else tensor_store_2d(&tm_idx, (int32_t)((b - nbd) * 16u), y, sidx + (size_t)(b - nbd) * BOX); // 16 column ids
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Blocked kernel (large G).  Work item = (block of <= S groups, run of `strips_per_cta`
 // 32-row strips).  The block's tables (cnt, lr5, masks, term offsets) are copied to
 // shared memory once and reused for every strip.  For a strip:

@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>           // CUtensorMap types only: cuTensorMapEncodeTiled is looked up through the runtime
 #include <cuda_runtime.h>
 #include <nccl.h>   // types only; the library is dlopen'ed (see NcclApi)
 
@@ -190,6 +191,50 @@ const StagedCfg kStaged[] = {
     QR_STAGED(1, 4), QR_STAGED(1, 8), QR_STAGED(1, 16), QR_STAGED(2, 4), QR_STAGED(2, 8), QR_STAGED(2, 16),
     QR_STAGED(4, 4), QR_STAGED(4, 8), QR_STAGED(4, 16),
 };
+
+// ---- 2-D tensor maps of the output arrays (fill_staged_swz_kernel) --------------------------------------------
+// cuTensorMapEncodeTiled lives in libcuda; the library links only the runtime, so the entry point is asked for once.
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            ptr = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+// rows x (inner elements of 8 bytes), boxes of 16 elements (128 bytes) x box_rows, 128-byte swizzle
+bool make_tile_map(qr::TensorMap *out, void *base, CUtensorMapDataType type, uint64_t inner, uint64_t rows, uint32_t box_rows)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(qr::TensorMap), "CUtensorMap is 128 bytes");
+    const cuuint64_t dims[2] = {inner, rows}, strides[1] = {inner * 8};
+    const cuuint32_t box[2] = {16, box_rows}, estr[2] = {1, 1};
+    return enc(reinterpret_cast<CUtensorMap *>(out), type, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// the swizzled tile is the default where it measured ahead of the plain tile, the padded tile and the rows kernel
+bool swz_default(uint64_t G)
+{
+    if (const char *env = getenv("QR_FILL_SWZ")) return env[0] == '1';
+    return G % 4 == 0 && G <= 24 && encode_tiled() != nullptr;
+}
+using SwzFn = void (*)(qr::PlanDev, uint32_t, uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t, const qr::TensorMap, const qr::TensorMap);
+SwzFn find_swz(int rw, int gw)
+{
+#define QR_SWZ(E, GW) if (rw == E && gw == GW) return qr::fill_staged_swz_kernel<E, GW>;
+    QR_SWZ(1, 4) QR_SWZ(1, 8) QR_SWZ(1, 16) QR_SWZ(2, 4) QR_SWZ(2, 8) QR_SWZ(2, 16) QR_SWZ(4, 4) QR_SWZ(4, 8) QR_SWZ(4, 16)
+#undef QR_SWZ
+    return nullptr;
+}
 
 const StagedCfg *find_staged(int rw, int gw)
 {
@@ -479,10 +524,12 @@ void choose_staged(qr_plan *pl)
         // group, sub-batches) holds 6.2-6.9 TB/s (profiles/r03_rows_sweep.jsonl).  With heavy groups the rows kernel
         // takes over from G = 76 only (C2 / C4 / XXZ n = 24: 4.8-5.1 TB/s against 6.0-6.6 staged).
         const char *env = getenv("QR_FILL_ROWS");
-        // Chains whose G = n + 1 is a multiple of 4 hit 4- and 8-way bank conflicts in the staged tile (lanes G * 16 B
-        // apart): XXZ n = 23 / 27 (G = 24 / 28) 4.66 / 4.98 TB/s staged, 5.24 / 5.76 rows; G = 20 still favours staged (4.73 / 4.16).
+        // Chains whose G = n + 1 is a multiple of 4 hit 4- and 8-way bank conflicts in the plain staged tile (lanes G * 16 B
+        // apart).  Up to G = 24 the swizzled tile (fill_staged_swz_kernel) removes them: XXZ n = 19 / 23 (G = 20 / 24)
+        // 5.19 / 6.86 TB/s against 4.62 / 5.25 plain and 5.47 rows; from G = 28 the rows kernel is ahead of both
+        // (n = 27 / 31: 6.05 / 6.65 rows, 5.84 / 6.09 swizzled, 5.40 plain; profiles/r05_swz_sweep*.jsonl).
         if (G >= 24 && !(env && (env[0] == '0' || env[0] == '1')) && choose_rows(pl)) {
-            const bool no_long_group = G >= 32 && pl->rows_hv_cap == 0, long_rows = G > 75, conflicts = G % 4 == 0;
+            const bool no_long_group = G >= 32 && pl->rows_hv_cap == 0, long_rows = G > 75, conflicts = G % 4 == 0 && (G >= 28 || !swz_default(G));
             if (!(pl->rows_regt && (no_long_group || long_rows || conflicts))) pl->rows_th = 0;
         }
     } else {
@@ -682,7 +729,7 @@ extern "C" const char *qr_plan_fill_kernel(const qr_plan *pl)
     if (pl->rows_th) return "fill_rows_kernel";
     if (pl->lanes) return "fill_lanes_kernel";
     if (pl->block_s) return "fill_blocked_kernel";
-    if (pl->rw) return "fill_staged_kernel";
+    if (pl->rw) return swz_default(pl->n_groups) && pl->n_groups % 2 == 0 ? "fill_staged_swz_kernel" : "fill_staged_kernel";
     return "fill_direct_kernel";
 }
 
@@ -895,6 +942,28 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
     if (cfg) {
         const uint64_t R = 32ull * cfg->rw;
         const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
+        // Even G: lanes G*16 B apart share banks in the plain tile.  The swizzled tile leaves through 2-D tensor maps
+        // (fill_staged_swz_kernel); it needs an even G (16-byte row pitch of the column ids) and the driver's encoder.
+        bool swz = swz_default(G);
+        if (const char *env = getenv("QR_FILL_SWZ")) swz = env[0] == '1';
+        const size_t swz_smem = (size_t)(((G + 7) / 8 + (G + 15) / 16) * R * 128 + 1024);
+        if (swz && s1 > s0 && G % 2 == 0 && swz_smem <= MAX_SMEM && row_hi - row_lo < (1ull << 31) && (s1 - s0) / R <= 0x7fffffffull) {
+            qr::TensorMap tmd, tmi;
+            SwzFn fn = find_swz(cfg->rw, cfg->gw);
+            if (fn && make_tile_map(&tmd, d_data, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2 * G, row_hi - row_lo, (uint32_t)R) &&
+                make_tile_map(&tmi, d_indices, CU_TENSOR_MAP_DATA_TYPE_UINT64, G, row_hi - row_lo, (uint32_t)R)) {
+                QR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swz_smem));
+                int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+                if (rc != QR_OK) return rc;
+                cudaLaunchConfig_t lc = {};
+                cudaLaunchAttribute attr;
+                lc.gridDim = dim3((unsigned)((s1 - s0) / R), 1, 1); lc.blockDim = dim3(32 * cfg->gw, 1, 1); lc.dynamicSmemBytes = swz_smem; lc.stream = st;
+                if (s0 == row_lo) pdl_config(lc, attr);
+                QR_CUDA(cudaLaunchKernelEx(&lc, fn, pl->dev, (uint32_t)G, s0, row_lo, indptr_base, d_indptr, (uint64_t)(row_hi - row_lo), tmd, tmi));
+                QR_LAUNCH_CHECK("fill_staged_swz_kernel");
+                return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+            }
+        }
         // the bulk copies need 16-byte aligned global addresses: indices + (s0-row_lo)*G*8
         const bool aligned = (((s0 - row_lo) * G) & 1) == 0;
         if (s1 > s0 && aligned) {
@@ -2021,6 +2090,34 @@ extern "C" int qr_compact_rows_device(uint64_t n_rows, uint64_t G, const uint64_
         n_rows, (uint32_t)G, d_indices, reinterpret_cast<const double2 *>(d_data), tol, d_indptr, d_indices_out,
         reinterpret_cast<double2 *>(d_data_out));
     QR_LAUNCH_CHECK("compact_rows_kernel");
+    return QR_OK;
+}
+
+extern "C" int qr_csr_count_kept_device(uint64_t n_rows, const uint64_t *d_indptr_in, const double *d_data, double tol,
+                                        uint64_t *d_indptr_out, uint64_t *nnz_out, void *stream)
+{
+    if (!d_indptr_in || !d_data || !d_indptr_out || !nnz_out) return fail(QR_ERR_INVALID, "qr_csr_count_kept_device: NULL argument");
+    if (n_rows == 0) return fail(QR_ERR_INVALID, "qr_csr_count_kept_device: bad shape");
+    cudaStream_t st = as_stream(stream);
+    const uint64_t per_cta = qr::K2_THREADS / 32;
+    const uint64_t ctas = std::min<uint64_t>((n_rows + per_cta - 1) / per_cta, (uint64_t)current_sm_count() * 64);
+    qr::csr_count_kept_kernel<<<(unsigned)ctas, qr::K2_THREADS, 0, st>>>(n_rows, d_indptr_in, reinterpret_cast<const double2 *>(d_data), tol, d_indptr_out);
+    QR_LAUNCH_CHECK("csr_count_kept_kernel");
+    return scan_counts(n_rows, d_indptr_out, nnz_out, st, "qr_csr_count_kept_device");
+}
+
+extern "C" int qr_csr_compact_device(uint64_t n_rows, const uint64_t *d_indptr_in, const uint64_t *d_indices, const double *d_data,
+                                     double tol, const uint64_t *d_indptr, uint64_t *d_indices_out, double *d_data_out, void *stream)
+{
+    if (!d_indptr_in || !d_indices || !d_data || !d_indptr || !d_indices_out || !d_data_out)
+        return fail(QR_ERR_INVALID, "qr_csr_compact_device: NULL argument");
+    if (n_rows == 0) return fail(QR_ERR_INVALID, "qr_csr_compact_device: bad shape");
+    const uint64_t per_cta = qr::K2_THREADS / 32;
+    const uint64_t ctas = std::min<uint64_t>((n_rows + per_cta - 1) / per_cta, (uint64_t)current_sm_count() * 64);
+    qr::csr_compact_rows_kernel<<<(unsigned)ctas, qr::K2_THREADS, 0, as_stream(stream)>>>(
+        n_rows, d_indptr_in, d_indices, reinterpret_cast<const double2 *>(d_data), tol, d_indptr, d_indices_out,
+        reinterpret_cast<double2 *>(d_data_out));
+    QR_LAUNCH_CHECK("csr_compact_rows_kernel");
     return QR_OK;
 }
 

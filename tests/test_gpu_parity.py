@@ -191,6 +191,35 @@ def test_staged_padded_tiles(fixtures, monkeypatch, name, force):
             assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
 
 
+@pytest.mark.parametrize("cfg", ["2,8", "1,4", "4,16"])
+@pytest.mark.parametrize("name", ["xxz11", "xxz15", "xxz7", "xxz19", "xxz13", "tfim_3x3", "H2", "H4_rs"])
+def test_staged_swizzled_tiles(fixtures, monkeypatch, name, cfg):
+    """fill_staged_swz_kernel: the tile in the TMA's 128-byte swizzle, boxes of 8 entries x R rows leaving through 2-D
+    tensor maps of the output arrays (last box of a row clipped at column G).  Every even G (12, 16, 8, 20, 14, 10, 4, ...),
+    whole matrices and ragged row windows (edge rows by the direct kernel), local and global indptr."""
+    monkeypatch.setenv("QR_FILL_ROWS", "0")
+    monkeypatch.setenv("QR_FILL_SWZ", "1")
+    monkeypatch.setenv("QR_FILL_CFG", cfg)
+    labels, coeffs = H.xxz_chain(int(name[3:]), 1.0, 0.7) if name.startswith("xxz") else SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    plan = make_op(labels, coeffs).plan()
+    G, dim = plan.n_groups, 1 << n
+    if G % 2 or dim < 32 * int(cfg[0]):
+        pytest.skip("odd G or fewer rows than a tile")
+    R = 32 * int(cfg[0])
+    lo_hi = [(0, dim)] + ([(5, dim - 3), (R, 3 * R), (dim // 2 - 1, dim // 2 + R + 2)] if dim >= 4 * R else [])
+    if n > 16:                                                      # xxz19: windows, not 10^7 rows of oracle
+        lo_hi = [(dim // 2 + 5, dim // 2 + 4096 + 82), (dim // 2, dim // 2 + 8192), (dim - 4096, dim)]
+    for lo, hi in lo_hi:
+        ref = O.build_csr(params, n, lo, hi)
+        before = _ffi.kernel_launches()
+        ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
+        assert _ffi.kernel_launches() - before <= 3
+        assert np.array_equal(ix, ref[1]) and np.array_equal(u64(dt), u64(ref[2])), (lo, hi)
+        assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
+        assert_same(device_build(plan, lo, hi), ref, f"{name} [{lo},{hi}) local indptr")
+
+
 @pytest.mark.parametrize("E", [1, 2])
 @pytest.mark.parametrize("S", [32, 48, 64, 128])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2"])
@@ -385,10 +414,12 @@ def test_rows_kernel_selection(fixtures, monkeypatch):
         return make_op(labels, coeffs).plan().fill_kernel
     assert kernel_of(*H.xxz_chain(10, 1.0, 0.7)) == "fill_staged_kernel"
     assert kernel_of(*H.tfim_lattice(5, 6, 1.0, 3.0)) == "fill_staged_kernel"      # G = 31
-    assert kernel_of(*H.xxz_chain(23, 1.0, 0.7)) == "fill_rows_kernel"             # G = 24: bank conflicts in the staged tile
-    assert kernel_of(*H.xxz_chain(19, 1.0, 0.7)) == "fill_staged_kernel"           # G = 20
+    assert kernel_of(*H.xxz_chain(23, 1.0, 0.7)) == "fill_staged_swz_kernel"       # G = 24: bank conflicts in the plain tile -> swizzled tile
+    assert kernel_of(*H.xxz_chain(19, 1.0, 0.7)) == "fill_staged_swz_kernel"       # G = 20
+    assert kernel_of(*H.xxz_chain(27, 1.0, 0.7)) == "fill_rows_kernel"             # G = 28: the rows kernel is ahead of both tiles
     assert kernel_of(*H.random_pauli_sum(12, 60, 40, 5, 5)) == "fill_rows_kernel"  # G = 40, no long group
-    assert kernel_of(*H.random_pauli_sum(12, 30, 20, 5, 5)) == "fill_staged_kernel"
+    assert kernel_of(*H.random_pauli_sum(12, 30, 20, 5, 5)) == "fill_staged_swz_kernel"   # G = 20
+    assert kernel_of(*H.random_pauli_sum(12, 30, 21, 5, 5)) == "fill_staged_kernel"
     assert kernel_of(*fixtures["H4"]) == "fill_staged_kernel"                      # G = 51 with heavy groups
     assert kernel_of(*fixtures["H6"]) == "fill_rows_kernel"                        # G = 286
     big = H.random_pauli_sum(12, 1500, 1100, 50, 5)
@@ -914,6 +945,39 @@ def test_eliminate_zeros_tiny_values():
     assert m2.count_zeros() == 0 and m2.nnz() == 0
     shape, data, indices, indptr = m2.export()
     assert len(data) == 0 and np.array_equal(indptr, [0, 0, 0])
+
+
+def test_eliminate_zeros_any_csr(fixtures):
+    """util.rs:144-171 take any CsMat: a matrix wrapped by new_unchecked (ragged rows, empty rows, a global indptr
+    offset is not involved) and a matrix that is already compacted go through the indptr-driven kernels."""
+    rng = np.random.default_rng(21)
+    n_rows, n_cols = 300, 517
+    lens = rng.integers(0, 70, n_rows); lens[[0, 17, 299]] = 0; lens[5] = 200
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    indices = np.concatenate([np.sort(rng.choice(n_cols, int(k), replace=False)) for k in lens]).astype(np.uint64)
+    data = rng.standard_normal(len(indices)) + 1j * rng.standard_normal(len(indices))
+    small = rng.random(len(indices)) < 0.3
+    data[small] *= 1e-9
+    data[rng.random(len(indices)) < 0.05] = 0.0
+    m = Q.SpMat.new_unchecked((n_rows, n_cols), data, indices, indptr)
+    for tol in (1e-7, 0.0, 0.5):
+        want = O.eliminate_zeros(indptr, indices, data, tolerance=tol)
+        assert m.count_zeros(tol) == O.count_zeros(data, tol)
+        m2 = m.eliminate_zeros(tol)
+        assert m2.nnz() == len(want[2]) and m2.count_zeros(tol) == 0
+        # ... and once more on the compacted matrix, with a larger tolerance
+        want3 = O.eliminate_zeros(*want, tolerance=1.0)
+        m3 = m2.eliminate_zeros(1.0)
+        assert m2.count_zeros(1.0) == O.count_zeros(want[2], 1.0)
+        assert_same(m3.export()[:0:-1], want3, f"twice tol={tol}")
+        assert_same(m2.export()[:0:-1], want, f"tol={tol}")
+    # a plan-built matrix, compacted, then compacted again
+    labels, coeffs = SMALL["random_n10"](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.eliminate_zeros(*O.build_csr(params, n), tolerance=0.3)
+    mm = make_op(labels, coeffs).to_matrix().eliminate_zeros(0.3)
+    assert mm.count_zeros(0.9) == O.count_zeros(ref[2], 0.9)
+    assert_same(mm.eliminate_zeros(0.9).export()[:0:-1], O.eliminate_zeros(*ref, tolerance=0.9), "plan-built, twice")
 
 
 @pytest.mark.parametrize("name,lo,hi", [("H4", 3, 250), ("H4", 32, 96), ("xxz_n10", 1, 1023), ("H6", 100, 3001),

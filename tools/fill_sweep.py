@@ -46,7 +46,12 @@ def main():
                   "QR_FILL_LANES_PERSIST", "QR_FILL_BLOCK", "QR_FILL_BLOCK_E", "QR_FILL_ROWS", "QR_FILL_ROWS_REGT", "QR_FILL_ROWS_HVS", "QR_FILL_ROWS_SL", "QR_FILL_ROWS_CL", "QR_FILL_ROWS_SPLIT",
                   "QR_FILL_ROWS_Q", "QR_FILL_ROWS_R", "QR_FILL_ROWS_HV"):      # the ones a cfg string sets
             os.environ.pop(k, None)
-        if cfg == "direct":
+        os.environ.pop("QR_FILL_SWZ", None)
+        if cfg.split(":")[0] in ("swz", "noswz"):    # staged kernel with / without the swizzled tile (rows kernel off) [:RW,GW]
+            os.environ["QR_FILL_SWZ"] = "1" if cfg.startswith("swz") else "0"
+            os.environ["QR_FILL_ROWS"] = "0"
+            if ":" in cfg: os.environ["QR_FILL_CFG"] = cfg.split(":")[1]
+        elif cfg == "direct":
             flags = _ffi.QR_FILL_DIRECT
         elif cfg.startswith("rows"):                  # rows[:regt 0|1[:log2(rows per batch)[:log2(rows per run)[:heavy threshold[:log2 heavy strip[:log2 sub-batches[:cluster size[:split S]]]]]]]], "" = default
             parts = cfg.split(":")
@@ -65,7 +70,7 @@ def main():
             os.environ["QR_FILL_LANES"] = "0"
             os.environ["QR_FILL_BLOCK"] = parts[1] if len(parts) > 1 else "32"
             if len(parts) > 2: os.environ["QR_FILL_BLOCK_E"] = parts[2]
-        elif cfg != "auto":
+        elif cfg != "auto" and cfg.split(":")[0] not in ("swz", "noswz"):
             os.environ["QR_FILL_CFG"] = cfg
         op = Q.SparsePauliOp.from_terms(n, terms)
         plan = op.plan()
