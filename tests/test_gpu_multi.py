@@ -14,7 +14,7 @@ ROOT = Path(__file__).resolve().parent.parent
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("cfg", ["xxz16", "C1", "H6"])
+@pytest.mark.parametrize("cfg", ["xxz16", "C1", "H6", "H8", "xxz19"])
 def test_two_ranks(cfg):
     if _ffi.device_count() < 2:
         pytest.skip("needs 2 GPUs")
