@@ -1,7 +1,10 @@
 """One-process-per-GPU plumbing.  The CSR build shards by contiguous row blocks and needs no
 collective; the matrix-free H.v all-gathers the row-sharded vector with NCCL (qr_comm_*, inside
-the C library).  torch.distributed is used only as the rendezvous that carries the NCCL unique
-id and for barriers / max-over-ranks reductions; any backend works ("gloo" in the CPU tests).
+the C library).  The package imports no framework: every function takes the caller's rendezvous
+object `dist` -- anything with get_rank(), get_world_size(), broadcast_object_list(),
+all_gather_object() and barrier() (torch.distributed with any backend, "gloo" in the CPU tests, or a
+ten-line MPI shim) -- and uses it only to carry the NCCL unique id, the CUDA-IPC handles and a few
+Python floats.
 """
 import ctypes as C
 
@@ -31,10 +34,10 @@ def exchange_unique_id(dist, make_id, src=0):
 
 
 def max_over_ranks(dist, value, device=None):
-    import torch
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    """max of one Python float over the ranks (timings: device-timed on every rank, reduced here)."""
+    vals = [None] * dist.get_world_size()
+    dist.all_gather_object(vals, float(value))
+    return max(vals)
 
 
 def create_comm(dist, device):
