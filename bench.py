@@ -445,7 +445,13 @@ def run_baseline_config(rig, cfg, build_reps=5, hv_reps=20, lanczos_iters=50):
         res = qlz.lanczos(op, n_iter=lanczos_iters, device=device, dist=rig.dist, comm=comm)
         out.update(lanczos_iterations=int(res["iterations"]), lanczos_iter_ms=rig.max_over_ranks(float(res["iter_ms"])),
                    lanczos_hv_ms=rig.max_over_ranks(float(res["hv_ms"])),
-                   lanczos_ritz_min=float(qlz.ritz_values(res["alphas"], res["betas"])[0]))
+                   lanczos_ritz_min=float(qlz.ritz_values(res["alphas"], res["betas"])[0]),
+                   lanczos_form="2 passes per iteration: apply with <u, H u> folded in its epilogue (qr_apply_dot_device / qr_apply_p2p_dot), "
+                                "update fused with the norm on unnormalised vectors; scalars stay on the device (no host read inside an iteration)")
+        if lanczos_iters >= 20:                                        # the round-1 loop beside it: 4 passes, 2 host reads per iteration
+            old = qlz.lanczos(op, n_iter=lanczos_iters, device=device, dist=rig.dist, comm=comm, device_scalars=False)
+            out.update(lanczos_iter_ms_host_scalars=rig.max_over_ranks(float(old["iter_ms"])),
+                       lanczos_max_alpha_diff=float(np.abs(res["alphas"] - old["alphas"][:len(res["alphas"])]).max()))
     if comm is not None:
         call("qr_comm_destroy", comm)
     rig.barrier()

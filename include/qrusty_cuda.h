@@ -229,6 +229,24 @@ QR_API int qr_comm_destroy(qr_comm *comm);
  * d_y_shard: this rank's rows of H.v.  ncclAllGather then the local apply. */
 QR_API int qr_apply_distributed(qr_plan *plan, qr_comm *comm, const double *d_v_shard,
                          double *d_v_full, double *d_y_shard, void *stream);
+/* y = H v on rows [row_lo, row_hi) AND d_dot[0..1] = sum over those rows of conj(v_r) y_r, in one pass: the apply
+ * kernels fold <v, H v> per CTA in their epilogue and one CTA folds the partials (fixed order: deterministic).  A
+ * Lanczos / Davidson step then spends no separate pass on the Rayleigh quotient.  d_dot: device, 16-byte aligned.
+ * The sharded form reads the peers' shards like qr_apply_p2p; d_dot is this rank's part (all-reduce it). */
+QR_API int qr_apply_dot_device(qr_plan *plan, uint64_t row_lo, uint64_t row_hi, const double *d_v, double *d_y,
+                               double *d_dot, void *stream);
+QR_API int qr_apply_p2p_dot(qr_plan *plan, qr_comm *comm, const double *const *v_shards, double *d_y_shard,
+                            double *d_dot, void *stream);
+/* Lanczos with its scalars on the device -- no host round trip inside an iteration.  d_state: 16 + 2 K doubles,
+ * 16-byte aligned: [0,1] <u, H u> (written by qr_apply_*_dot)  [2,3] ||w||^2 (written by qr_lanczos_update_dev)
+ * [4] beta_{k-2}-scale  [5] ||u_k|| (initialise to 1 for a normalised start vector)  [6..8] coefficients
+ * [16 + k] alpha_k  [16 + K + k] beta_k.  The vectors stay unnormalised (u_{k+1} = w_k), so no rescale pass:
+ *   qr_lanczos_coef_device(state, k, K, 0)   after the apply (+ all-reduce of [0,1]):  alpha_k, coefficients
+ *   qr_lanczos_update_dev(n, state, y, u, u_prev, w)   w = (H u)/b - (alpha/b) u - (b/b') u_prev, [2] = ||w||^2
+ *   qr_lanczos_coef_device(state, k, K, 1)   after the update (+ all-reduce of [2]):   beta_k = sqrt([2]) */
+QR_API int qr_lanczos_coef_device(double *d_state, uint32_t k, uint32_t K, uint32_t phase, void *stream);
+QR_API int qr_lanczos_update_dev(uint64_t n, double *d_state, const double *d_y, const double *d_u, const double *d_u_prev,
+                                 double *d_w_out, void *stream);
 QR_API int qr_allreduce_sum_f64(qr_comm *comm, double *d_buf, size_t count, void *stream);
 
 /* Fused distributed H.v over peer memory: no all-gather and no full copy of v.  Every rank

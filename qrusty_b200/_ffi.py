@@ -79,6 +79,10 @@ SIGNATURES = {
     "qr_comm_destroy": [_vp],
     "qr_apply_distributed": [_vp, _vp, _vp, _vp, _vp, _vp],
     "qr_allreduce_sum_f64": [_vp, _vp, _sz, _vp],
+    "qr_apply_dot_device": [_vp, _u64, _u64, _vp, _vp, _vp, _vp],
+    "qr_apply_p2p_dot": [_vp, _vp, _vp, _vp, _vp, _vp],
+    "qr_lanczos_coef_device": [_vp, _u32, _u32, _u32, _vp],
+    "qr_lanczos_update_dev": [_u64, _vp, _vp, _vp, _vp, _vp, _vp],
     "qr_apply_p2p": [_vp, _vp, _vp, _vp, _vp],
     "qr_ipc_get_handle": [_vp, _vp],
     "qr_ipc_open_handle": [_vp, C.POINTER(_vp)],

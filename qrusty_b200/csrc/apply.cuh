@@ -91,6 +91,28 @@ __device__ __forceinline__ void cfma(double &yr, double &yi, double ar, double a
     if (!a_real) { yr = __fma_rn(-ai, w.y, yr); yi = __fma_rn(ai, w.x, yi); }
 }
 
+// <v, y> over the rows of a CTA, folded in a fixed order (warp shuffles, then warp 0..W-1 in sequence): the epilogue of
+// the apply kernels when the caller wants alpha = <v, H v> with the product (a Lanczos step then needs no separate pass
+// over v and y).  All threads of the CTA must call; out = one double2 per CTA.
+__device__ __forceinline__ void block_dot_store(double dr, double di, double2 *out)
+{
+    __shared__ double s_dre[32], s_dim[32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { dr += __shfl_xor_sync(0xffffffffu, dr, d); di += __shfl_xor_sync(0xffffffffu, di, d); }
+    if ((threadIdx.x & 31u) == 0u) { s_dre[threadIdx.x >> 5] = dr; s_dim[threadIdx.x >> 5] = di; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t w = 1; w < (blockDim.x + 31u) / 32u; w++) { dr += s_dre[w]; di += s_dim[w]; }
+        *out = make_double2(dr, di);
+    }
+}
+// conj(v) * y accumulated into (dr, di)
+__device__ __forceinline__ void cdot_acc(double &dr, double &di, double2 v, double yr, double yi)
+{
+    dr = __fma_rn(v.x, yr, dr); dr = __fma_rn(v.y, yi, dr);
+    di = __fma_rn(v.x, yi, di); di = __fma_rn(-v.y, yr, di);
+}
+
 // v0 (gather): thread <-> APPLY_ROWS rows (r, r+256, ...), so a warp's loads of v[r ^ x] stay one
 // permuted, fully coalesced 512-byte segment.  Group descriptors come through shared memory.
 // `diag` / `diag_re` (optional): cached values of the mask-0 group for rows [row_lo,row_hi) -- complex, or the real parts
@@ -107,7 +129,8 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
                     const double2 *__restrict__ v, double2 *__restrict__ y,
                     const double2 *__restrict__ diag, const double *__restrict__ diag_re,
                     const __grid_constant__ ApplyPeerArgs pa,
-                    const uint32_t *__restrict__ glist = nullptr, uint32_t n_list = 0)
+                    const uint32_t *__restrict__ glist = nullptr, uint32_t n_list = 0,
+                    double2 *__restrict__ dotp = nullptr)                 // optional: per-CTA partials of <v, y> over these rows
 {
     // glist (optional): apply only these groups (ascending ids; the mask-0 group, when cached in diag, first) --
     // the NEAR pass of the two-pass apply (apply_tile.cuh)
@@ -173,6 +196,13 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
 #pragma unroll
     for (int e = 0; e < E; e++)
         if (live[e]) __stcs(&y[(uint64_t)r[e] - row_lo], make_double2(yr[e], yi[e]));   // streaming store
+    if (dotp != nullptr) {                                         // CTA-uniform
+        double dr = 0.0, di = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            if (live[e]) cdot_acc(dr, di, ld_nc_double2(&v_own[r[e]]), yr[e], yi[e]);
+        block_dot_store(dr, di, &dotp[blockIdx.x]);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -393,6 +423,52 @@ lanczos_update_kernel(uint64_t n, double2 alpha, double2 beta, const double2 *w,
         const double re = c.x - (alpha.x * a.x - alpha.y * a.y) - (beta.x * b.x - beta.y * b.y);
         const double im = c.y - (alpha.x * a.y + alpha.y * a.x) - (beta.x * b.y + beta.y * b.x);
         w_out[i] = make_double2(re, im);
+        acc += re * re + im * im;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) sre[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) acc += sre[k];
+        partial[blockIdx.x] = make_double2(acc, 0.0);
+    }
+}
+
+// ---- Lanczos with the scalars on the device (no host round trip inside an iteration) ----------------------------
+// The vectors are kept UNNORMALISED: u_{k+1} = w_k, v_{k+1} = u_{k+1} / beta_k, so no pass is spent on a rescale:
+//   alpha_k = <u_k, H u_k> / bcur^2                      bcur = ||u_k|| (1 for the start vector)
+//   w_k     = (H u_k) / bcur - (alpha_k / bcur) u_k - (bcur / bprev) u_{k-1}
+//   beta_k  = ||w_k||
+// state (doubles): [0,1] <u, H u> (re, im)   [2,3] ||w||^2 (, 0)   [4] bprev   [5] bcur   [6] ca   [7] cb   [8] cc
+//                  [16 + k] alpha_k          [16 + K + k] beta_k
+constexpr int LZ_STATE_HEAD = 16;
+__global__ void lanczos_coef_kernel(double *st, uint32_t k, uint32_t K, uint32_t phase)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (phase == 0u) {                                             // after the apply: alpha_k and the update's coefficients
+        const double bcur = st[5], bprev = st[4];
+        const double alpha = st[0] / (bcur * bcur);
+        st[6] = 1.0 / bcur; st[7] = alpha / bcur; st[8] = k == 0u ? 0.0 : bcur / bprev;
+        st[LZ_STATE_HEAD + k] = alpha;
+    } else {                                                       // after the update: beta_k, and u_{k+1}'s scale
+        const double beta = sqrt(st[2]);
+        st[LZ_STATE_HEAD + K + k] = beta;
+        st[4] = st[5]; st[5] = beta;
+    }
+}
+// w_out = ca * y - cb * u - cc * u_prev (real coefficients read from the device state), partial[b] = sum |w_out|^2
+__global__ void __launch_bounds__(256)
+lanczos_update_dev_kernel(uint64_t n, const double *__restrict__ st, const double2 *__restrict__ y, const double2 *__restrict__ u,
+                          const double2 *__restrict__ u_prev, double2 *__restrict__ w_out, double2 *__restrict__ partial)
+{
+    __shared__ double sre[8];
+    const double ca = st[6], cb = st[7], cc = st[8];
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        const double2 a = y[i], b = u[i], c = u_prev ? u_prev[i] : make_double2(0.0, 0.0);
+        const double re = ca * a.x - cb * b.x - cc * c.x, im = ca * a.y - cb * b.y - cc * c.y;
+        __stcs(&w_out[i], make_double2(re, im));
         acc += re * re + im * im;
     }
 #pragma unroll

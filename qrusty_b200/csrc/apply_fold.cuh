@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 4)
 apply_fold_kernel(PlanDev p, FoldDev f, uint32_t G, uint64_t row_lo, uint64_t row_hi,
                   const double2 *__restrict__ v, double2 *__restrict__ y,
                   const double2 *__restrict__ diag, const double *__restrict__ diag_re,
-                  const __grid_constant__ ApplyPeerArgs pa)
+                  const __grid_constant__ ApplyPeerArgs pa, double2 *__restrict__ dotp)
 {
     constexpr int E = FOLD_ROWS, TH = FOLD_THREADS, B0 = FOLD_B0;
     __shared__ GroupDesc sd[FOLD_BATCH];
@@ -197,6 +197,12 @@ apply_fold_kernel(PlanDev p, FoldDev f, uint32_t G, uint64_t row_lo, uint64_t ro
     }
 #pragma unroll
     for (int e = 0; e < E; e++) __stcs(&y[(uint64_t)(r0 + ((uint32_t)e << B0)) - row_lo], make_double2(yr[e], yi[e]));
+    if (dotp != nullptr) {                                         // per-CTA partial of <v, y> (apply.cuh)
+        double dr = 0.0, di = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; e++) cdot_acc(dr, di, ld_nc_double2(&v_own[r0 + ((uint32_t)e << B0)]), yr[e], yi[e]);
+        block_dot_store(dr, di, &dotp[blockIdx.x]);
+    }
 }
 
 // ---------------------------------------------------------------------------------

@@ -154,7 +154,8 @@ struct qr_plan {
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
     uint64_t n_terms_canonical = 0;
     // lazily allocated scratch
-    double2 *dot_partials = nullptr;
+    double2 *dot_partials = nullptr;       // per-CTA partials of <v, H v> (qr_apply_dot_device / qr_apply_p2p_dot)
+    uint64_t dot_cap = 0;
     // term-rich H.v (apply_fold.cuh): bucketed copy of the term table, built at the first apply
     int fold_state = -1;                   // -1: not looked at yet, 0: the gather kernel serves this operator, 1: the fold kernel does
     bool fold_blocked = false;             // a group too long for the bucket table: gather kernel only
@@ -1876,7 +1877,24 @@ static int launch_ptile(qr_plan *pl, int K, const qr_plan::Ptile &pt, uint64_t r
                      : launch_ptile_k<10, 3>(pl, pt, row_lo, row_hi, v, y, diag, diag_re, pa, st);
 }
 
-static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double2 *v, double2 *y, cudaStream_t st)
+// <v, H v> with the product: the apply kernels leave one partial per CTA in pl->dot_partials, one CTA folds them
+static int dot_partials(qr_plan *pl, uint64_t n_ctas, cudaStream_t st)
+{
+    if (pl->dot_cap >= n_ctas) return QR_OK;
+    if (pl->dot_partials) { QR_CUDA(cudaStreamSynchronize(st)); cudaFree(pl->dot_partials); pl->dot_partials = nullptr; pl->dot_cap = 0; }
+    QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&pl->dot_partials), n_ctas * sizeof(double2)));
+    pl->dot_cap = n_ctas;
+    return QR_OK;
+}
+static int dot_fold(qr_plan *pl, uint64_t n_ctas, double2 *dot_out, cudaStream_t st)
+{
+    qr::dotc_final_kernel<<<1, qr::DOT_THREADS, 0, st>>>((uint32_t)n_ctas, pl->dot_partials, dot_out);
+    QR_LAUNCH_CHECK("dotc_final_kernel");
+    return QR_OK;
+}
+
+static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double2 *v, double2 *y, cudaStream_t st,
+                      double2 *dot_out = nullptr)
 {
     const uint64_t rows = row_hi - row_lo;
     const double2 *diag = nullptr;
@@ -1885,7 +1903,7 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
     const bool pow2 = (rows & (rows - 1)) == 0 && (row_lo & (rows - 1)) == 0;
     const char *mode = getenv("QR_APPLY_V0");
     const int K = apply_tile_bits();
-    const bool tiled = pow2 && rows >= (1ull << K) && mode && mode[0] == '0';
+    const bool tiled = pow2 && rows >= (1ull << K) && mode && mode[0] == '0' && !dot_out;   // the dot epilogue lives in the default kernels
     int rc = ensure_diag_cache(pl, row_lo, row_hi, st, &diag, tiled ? nullptr : &diag_re);
     if (rc != QR_OK) return rc;
     if (tiled) {
@@ -1909,7 +1927,7 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
     const uint32_t m_blk = pow2 ? (uint32_t)(63 - __builtin_clzll(rows)) : 0u;
     uint32_t min_m = 20;
     if (const char *env = getenv("QR_APPLY_TILE_MIN")) { int v = atoi(env); if (v >= 9 && v <= 32) min_m = (uint32_t)v; }   // tests
-    if (pow2 && m_blk >= min_m && !(mode && mode[0] == '1') && tile_env && tile_env[0] == '1') {
+    if (pow2 && m_blk >= min_m && !(mode && mode[0] == '1') && tile_env && tile_env[0] == '1' && !dot_out) {
         const uint32_t blk = (uint32_t)(row_lo >> m_blk), d0 = apply_cut_bit();
         const bool use_diag = diag != nullptr || diag_re != nullptr;
         TilePlan *tb = nullptr, *ta = nullptr;
@@ -1932,7 +1950,7 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
             return launch_tile<false>(pl, *tb, a, row_lo, y, nullptr, nullptr, st);
         }
     }
-    {
+    if (!dot_out) {
         int K = 0; qr_plan::Ptile *pt = nullptr;
         rc = ensure_ptile(pl, row_lo, row_hi, 32u, &K, &pt);
         if (rc != QR_OK) return rc;
@@ -1942,13 +1960,17 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
     if (fold_rows_ok(row_lo, row_hi)) { rc = ensure_fold(pl, &fold); if (rc != QR_OK) return rc; }
     if (fold) {
         const uint64_t fctas = rows / ((uint64_t)qr::FOLD_THREADS * qr::FOLD_ROWS);
-        qr::apply_fold_kernel<<<(unsigned)fctas, qr::FOLD_THREADS, 0, st>>>(pl->dev, pl->fold, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re, qr::ApplyPeerArgs{});
+        if (dot_out) { rc = dot_partials(pl, fctas, st); if (rc != QR_OK) return rc; }
+        qr::apply_fold_kernel<<<(unsigned)fctas, qr::FOLD_THREADS, 0, st>>>(pl->dev, pl->fold, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re,
+                                                                            qr::ApplyPeerArgs{}, dot_out ? pl->dot_partials : nullptr);
         QR_LAUNCH_CHECK("apply_fold_kernel");
-        return QR_OK;
+        return dot_out ? dot_fold(pl, fctas, dot_out, st) : QR_OK;
     }
-    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re, qr::ApplyPeerArgs{});
+    if (dot_out) { rc = dot_partials(pl, ctas, st); if (rc != QR_OK) return rc; }
+    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re, qr::ApplyPeerArgs{},
+                                                                          nullptr, 0u, dot_out ? pl->dot_partials : nullptr);
     QR_LAUNCH_CHECK("apply_direct_kernel");
-    return QR_OK;
+    return dot_out ? dot_fold(pl, ctas, dot_out, st) : QR_OK;
 }
 
 extern "C" const char *qr_plan_apply_kernel(qr_plan *pl, uint64_t row_lo, uint64_t row_hi)
@@ -1970,6 +1992,16 @@ extern "C" int qr_apply_device(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, co
     if (((uintptr_t)d_v | (uintptr_t)d_y) & 15) return fail(QR_ERR_INVALID, "qr_apply_device: vectors must be 16-byte aligned");
     QR_CUDA(cudaSetDevice(pl->device));
     return apply_rows(pl, row_lo, row_hi, reinterpret_cast<const double2 *>(d_v), reinterpret_cast<double2 *>(d_y), as_stream(stream));
+}
+
+extern "C" int qr_apply_dot_device(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const double *d_v, double *d_y, double *d_dot, void *stream)
+{
+    if (!pl || !d_v || !d_y || !d_dot) return fail(QR_ERR_INVALID, "qr_apply_dot_device: NULL argument");
+    if (row_lo >= row_hi || row_hi > pl->dim) return fail(QR_ERR_INVALID, "qr_apply_dot_device: bad row range");
+    if (((uintptr_t)d_v | (uintptr_t)d_y | (uintptr_t)d_dot) & 15) return fail(QR_ERR_INVALID, "qr_apply_dot_device: vectors and the result must be 16-byte aligned");
+    QR_CUDA(cudaSetDevice(pl->device));
+    return apply_rows(pl, row_lo, row_hi, reinterpret_cast<const double2 *>(d_v), reinterpret_cast<double2 *>(d_y), as_stream(stream),
+                      reinterpret_cast<double2 *>(d_dot));
 }
 
 extern "C" int qr_apply_host(qr_plan *pl, const double *v, double *y)
@@ -2269,6 +2301,31 @@ extern "C" int qr_lanczos_update_device(uint64_t n, const double alpha[2], const
     return QR_OK;
 }
 
+extern "C" int qr_lanczos_coef_device(double *d_state, uint32_t k, uint32_t K, uint32_t phase, void *stream)
+{
+    if (!d_state || k >= K || phase > 1u) return fail(QR_ERR_INVALID, "qr_lanczos_coef_device: bad argument");
+    qr::lanczos_coef_kernel<<<1, 32, 0, as_stream(stream)>>>(d_state, k, K, phase);
+    QR_LAUNCH_CHECK("lanczos_coef_kernel");
+    return QR_OK;
+}
+
+extern "C" int qr_lanczos_update_dev(uint64_t n, double *d_state, const double *d_y, const double *d_u, const double *d_u_prev,
+                                     double *d_w_out, void *stream)
+{
+    if (!d_state || !d_y || !d_u || !d_w_out) return fail(QR_ERR_INVALID, "qr_lanczos_update_dev: NULL argument");
+    if ((uintptr_t)d_state & 15) return fail(QR_ERR_INVALID, "qr_lanczos_update_dev: the state must be 16-byte aligned");
+    double2 *partials = nullptr;
+    int rc = reduce_scratch(&partials, nullptr);
+    if (rc != QR_OK) return rc;
+    qr::lanczos_update_dev_kernel<<<kReduceGrid, 256, 0, as_stream(stream)>>>(
+        n, d_state, reinterpret_cast<const double2 *>(d_y), reinterpret_cast<const double2 *>(d_u),
+        reinterpret_cast<const double2 *>(d_u_prev), reinterpret_cast<double2 *>(d_w_out), partials);
+    QR_LAUNCH_CHECK("lanczos_update_dev_kernel");
+    qr::dotc_final_kernel<<<1, qr::DOT_THREADS, 0, as_stream(stream)>>>(kReduceGrid, partials, reinterpret_cast<double2 *>(d_state + 2));
+    QR_LAUNCH_CHECK("dotc_final_kernel");
+    return QR_OK;
+}
+
 extern "C" int qr_dotc_device(uint64_t n, const double *x, const double *y, double *d_out, void *stream)
 {
     if (!x || !y || !d_out) return fail(QR_ERR_INVALID, "qr_dotc_device: NULL argument");
@@ -2423,7 +2480,17 @@ extern "C" int qr_apply_distributed(qr_plan *pl, qr_comm *cm, const double *d_v_
                       reinterpret_cast<double2 *>(d_y_shard), as_stream(stream));
 }
 
+static int apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_shards, double *d_y_shard, double2 *dot_out, void *stream);
 extern "C" int qr_apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_shards, double *d_y_shard, void *stream)
+{
+    return apply_p2p(pl, cm, v_shards, d_y_shard, nullptr, stream);
+}
+extern "C" int qr_apply_p2p_dot(qr_plan *pl, qr_comm *cm, const double *const *v_shards, double *d_y_shard, double *d_dot, void *stream)
+{
+    if (!d_dot || ((uintptr_t)d_dot & 15)) return fail(QR_ERR_INVALID, "qr_apply_p2p_dot: d_dot must be a 16-byte aligned device pointer");
+    return apply_p2p(pl, cm, v_shards, d_y_shard, reinterpret_cast<double2 *>(d_dot), stream);
+}
+static int apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_shards, double *d_y_shard, double2 *dot_out, void *stream)
 {
     if (!pl || !cm || !v_shards || !d_y_shard) return fail(QR_ERR_INVALID, "qr_apply_p2p: NULL argument");
     const uint64_t P = (uint64_t)cm->n_ranks;
@@ -2443,7 +2510,7 @@ extern "C" int qr_apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_sha
     // Tiled path: remote runs pulled by TMA into shared memory while the local groups are gathered; ranks
     // synchronise through epoch flags in IPC-mapped memory, no NCCL call (apply_tile.cuh).
     const char *tile_env = getenv("QR_P2P_TILE");
-    if (cm->flags_ok && P <= (uint64_t)qr::TILE_MAX_PEERS && tile_env && tile_env[0] == '1') {
+    if (cm->flags_ok && P <= (uint64_t)qr::TILE_MAX_PEERS && tile_env && tile_env[0] == '1' && !dot_out) {
         TilePlan *tp = nullptr;
         rc = make_tile_plan(pl, m, (uint32_t)cm->rank, m, TILE_P2P, diag != nullptr || diag_re != nullptr, nullptr, &tp);
         if (rc != QR_OK) return rc;
@@ -2493,7 +2560,7 @@ extern "C" int qr_apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_sha
     }
     bool fold = false;
     int ptK = 0; qr_plan::Ptile *ptp = nullptr;
-    rc = ensure_ptile(pl, row_lo, row_hi, m, &ptK, &ptp);
+    if (!dot_out) rc = ensure_ptile(pl, row_lo, row_hi, m, &ptK, &ptp);
     if (rc != QR_OK) return rc;
     if (!ptp && fold_rows_ok(row_lo, row_hi)) { rc = ensure_fold(pl, &fold); if (rc != QR_OK) return rc; }
     if (ptp) {                                                     // same choice, same kernel as apply_rows: the two forms agree bit for bit
@@ -2501,15 +2568,21 @@ extern "C" int qr_apply_p2p(qr_plan *pl, qr_comm *cm, const double *const *v_sha
         if (rc != QR_OK) return rc;
     } else if (fold) {
         const uint64_t fctas = shard / ((uint64_t)qr::FOLD_THREADS * qr::FOLD_ROWS);
+        if (dot_out) { rc = dot_partials(pl, fctas, st); if (rc != QR_OK) return rc; }
         qr::apply_fold_kernel<<<(unsigned)fctas, qr::FOLD_THREADS, 0, st>>>(
-            pl->dev, pl->fold, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa);
+            pl->dev, pl->fold, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa,
+            dot_out ? pl->dot_partials : nullptr);
         QR_LAUNCH_CHECK("apply_fold_kernel(p2p)");
+        if (dot_out) { rc = dot_fold(pl, fctas, dot_out, st); if (rc != QR_OK) return rc; }
     } else {
         const uint64_t per_cta = (uint64_t)qr::APPLY_THREADS * qr::APPLY_ROWS;
         const uint64_t ctas = (shard + per_cta - 1) / per_cta;
+        if (dot_out) { rc = dot_partials(pl, ctas, st); if (rc != QR_OK) return rc; }
         qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(
-            pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa);
+            pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, nullptr, reinterpret_cast<double2 *>(d_y_shard), diag, diag_re, pa,
+            nullptr, 0u, dot_out ? pl->dot_partials : nullptr);
         QR_LAUNCH_CHECK("apply_direct_kernel(p2p)");
+        if (dot_out) { rc = dot_fold(pl, ctas, dot_out, st); if (rc != QR_OK) return rc; }
     }
     // ... and nobody overwrites a shard while a peer may still be reading it
     if (flags) {

@@ -1,10 +1,16 @@
 """Lanczos-style iteration on device-resident, row-sharded vectors -- the loop BASELINE config 4 is
 defined by: w = H v; alpha = <v,w>; w -= alpha v + beta v_prev; beta = ||w||.
 
-Everything stays in HBM: matrix-free H.v (qr_apply_device, or the fused peer-memory
-qr_apply_p2p when sharded), <v,w> (qr_dotc_device), the three-term update fused with the norm
-(qr_lanczos_update_device), the rescale (qr_ax_device).  Per iteration the host reads back two
-scalars.  Sharded runs all-reduce the two scalars with NCCL (qr_allreduce_sum_f64).
+Everything stays in HBM.  Default (device_scalars=True): two passes per iteration and no host round trip --
+  1. y = H u and <u, y> in ONE kernel (qr_apply_dot_device, or the fused peer-memory qr_apply_p2p_dot when
+     sharded: the apply kernels fold the Rayleigh quotient per CTA in their epilogue);
+  2. w = (H u)/b - (alpha/b) u - (b/b') u_prev fused with ||w||^2 (qr_lanczos_update_dev), the coefficients read
+     from a device-resident state that two one-thread kernels maintain (qr_lanczos_coef_device); the vectors stay
+     unnormalised (u_{k+1} = w_k), so no pass is spent on a rescale.
+Sharded runs all-reduce the two scalars in place on the device (qr_allreduce_sum_f64, stream-ordered).  The host
+reads alphas and betas once, after the last iteration.
+device_scalars=False is the round-1 loop: apply, <v,w> (qr_dotc_device), update fused with the norm
+(qr_lanczos_update_device), rescale (qr_ax_device) -- four passes and two host reads per iteration.
 
 The reference leaves this loop to scipy/PRIMME calling spmat_dot_densevec + axpby/axpy/ax
 (pyqrusty/sandbox/test1.py:60-87, qrusty/src/accel.rs:338-393).
@@ -25,7 +31,7 @@ def _c2(a):
     return (C.c_double * 2)(a.real, a.imag)
 
 
-def lanczos(op, n_iter=50, device=0, seed=25, dist=None, comm=None, fused_p2p=True, v0=None):
+def lanczos(op, n_iter=50, device=0, seed=25, dist=None, comm=None, fused_p2p=True, v0=None, device_scalars=True):
     """-> dict(alphas, betas, hv_ms, iter_ms).  `dist`/`comm` given: this rank owns rows
     dist.row_block(rank, world, dim) and `comm` is a qr_comm (dist.create_comm)."""
     from . import dist as qd
@@ -66,6 +72,14 @@ def lanczos(op, n_iter=50, device=0, seed=25, dist=None, comm=None, fused_p2p=Tr
 
     def ev():
         e = C.c_void_p(); call("qr_event_create", C.byref(e)); return e
+
+    if device_scalars and (world == 1 or fused_p2p):
+        res = _lanczos_device_scalars(plan, n_iter, lo, hi, rows, bufs, shared, world, dist, comm, stream, allreduce, ev, qd)
+        if shared:
+            for _, opened in shared:
+                qd.close_shards(opened)
+        call("qr_stream_destroy", stream)
+        return res
     e0, e1 = ev(), ev()
     alphas, betas, hv_ms = [], [], 0.0
     beta = 0.0
@@ -109,6 +123,53 @@ def lanczos(op, n_iter=50, device=0, seed=25, dist=None, comm=None, fused_p2p=Tr
     n_done = len(alphas)
     return {"alphas": np.array(alphas), "betas": np.array(betas), "iterations": n_done,
             "hv_ms": hv_ms / n_done, "iter_ms": total_ms / n_done}
+
+
+def _lanczos_device_scalars(plan, K, lo, hi, rows, bufs, shared, world, dist, comm, stream, allreduce, ev, qd):
+    """The two-pass loop with the scalars on the device (module docstring).  bufs[1] holds the normalised start vector."""
+    head = 16
+    state = np.zeros(head + 2 * K, np.float64)
+    state[5] = 1.0                                          # ||u_0||
+    d_state = DeviceBuffer(state.nbytes, plan.device)
+    d_state.upload(state)
+    events = [(ev(), ev()) for _ in range(K)]
+    i_prev, i_u, i_y = 0, 1, 2
+    if dist is not None:
+        dist.barrier()
+    call("qr_stream_synchronize", stream)
+    t_start = time.perf_counter()
+    for k in range(K):
+        e0, e1 = events[k]
+        call("qr_event_record", e0, stream)
+        if world == 1:
+            call("qr_apply_dot_device", plan.handle, lo, hi, bufs[i_u].ptr, bufs[i_y].ptr, d_state.ptr, stream)
+        else:
+            call("qr_apply_p2p_dot", plan.handle, comm, qd.pointer_array(shared[i_u][0]), bufs[i_y].ptr, d_state.ptr, stream)
+        call("qr_event_record", e1, stream)
+        allreduce(d_state.ptr, 2)
+        call("qr_lanczos_coef_device", d_state.ptr, k, K, 0, stream)
+        # w overwrites y in place (element i is read before it is written by the same thread)
+        call("qr_lanczos_update_dev", rows, d_state.ptr, bufs[i_y].ptr, bufs[i_u].ptr, bufs[i_prev].ptr if k > 0 else None,
+             bufs[i_y].ptr, stream)
+        allreduce(d_state.ptr + 16, 1)
+        call("qr_lanczos_coef_device", d_state.ptr, k, K, 1, stream)
+        i_prev, i_u, i_y = i_u, i_y, i_prev
+    call("qr_stream_synchronize", stream)
+    total_ms = (time.perf_counter() - t_start) * 1e3
+    if dist is not None:
+        dist.barrier()
+    d_state.download(state)
+    hv_ms = 0.0
+    for e0, e1 in events:
+        ms = C.c_float(); call("qr_event_elapsed_ms", e0, e1, C.byref(ms)); hv_ms += ms.value
+    alphas, betas = state[head:head + K].copy(), state[head + K:head + 2 * K].copy()
+    n_done = K
+    dead = np.flatnonzero(~(betas > 0.0))                   # breakdown (beta = 0) or what follows it (nan): cut there
+    if len(dead):
+        n_done = int(dead[0]) + 1
+        alphas, betas = alphas[:n_done], betas[:n_done]
+    return {"alphas": alphas, "betas": betas, "iterations": n_done, "hv_ms": hv_ms / K, "iter_ms": total_ms / K,
+            "passes_per_iteration": 2, "host_reads_per_iteration": 0}
 
 
 def ritz_values(alphas, betas):

@@ -883,7 +883,10 @@ def test_lanczos_matches_numpy(fixtures):
     n, params = O.make_params(labels, coeffs)
     indptr, indices, data = O.build_csr(params, n)
     A = sps.csr_matrix((data, indices.astype(np.int64), indptr.astype(np.int64)), shape=(1 << n, 1 << n))
-    res = L.lanczos(make_op(labels, coeffs), n_iter=30)
+    res = L.lanczos(make_op(labels, coeffs), n_iter=30)                  # two passes, scalars on the device
+    old = L.lanczos(make_op(labels, coeffs), n_iter=30, device_scalars=False)   # round-1 loop: four passes, host scalars
+    assert res["passes_per_iteration"] == 2
+    assert np.allclose(res["alphas"], old["alphas"], rtol=1e-10, atol=1e-10) and np.allclose(res["betas"], old["betas"], rtol=1e-10, atol=1e-10)
     v = H.lanczos_start_vector(0, 1 << n); v /= np.linalg.norm(v)
     v_prev, beta, al, be = np.zeros_like(v), 0.0, [], []
     for _ in range(30):
@@ -897,6 +900,29 @@ def test_lanczos_matches_numpy(fixtures):
     exact = np.linalg.eigvalsh(A.toarray())[0]
     assert L.ritz_values(res["alphas"], res["betas"])[0] >= exact - 1e-9
     assert res["hv_ms"] > 0 and res["iterations"] == 30
+
+
+@pytest.mark.parametrize("name", ["C1", "H6", "xxz16", "random_n10"])
+def test_apply_dot(fixtures, name):
+    """qr_apply_dot_device: y is the plain apply's bit for bit, the fused <v, H v> equals the vdot of the downloaded
+    vectors to rounding (both apply kernels: gather and fold; whole vector and a row block)."""
+    labels, coeffs = H.xxz_chain(16, 1.0, 0.7) if name == "xxz16" else SMALL[name](fixtures)
+    plan = make_op(labels, coeffs).plan()
+    dim = plan.dim
+    v = H.lanczos_start_vector(0, dim, seed=51)
+    dv = DeviceBuffer(dim * 16); dv.upload(v)
+    for lo, hi in [(0, dim), (dim // 4, dim // 2), (3, dim - 5)]:
+        y0 = _apply_block(plan, lo, hi, dv)
+        dy = DeviceBuffer((hi - lo) * 16); dd = DeviceBuffer(16)
+        _ffi.call("qr_apply_dot_device", plan.handle, lo, hi, dv.ptr, dy.ptr, dd.ptr, None)
+        y1 = dy.download(np.empty(hi - lo, np.complex128))
+        dot = dd.download(np.empty(1, np.complex128))[0]
+        assert np.array_equal(u64(y1), u64(y0)), (lo, hi)
+        want = np.vdot(v[lo:hi], y0)
+        assert abs(dot - want) <= 1e-12 * np.abs(v[lo:hi]).dot(np.abs(y0)) + 1e-300, (lo, hi, dot, want)
+        dot2 = DeviceBuffer(16)
+        _ffi.call("qr_apply_dot_device", plan.handle, lo, hi, dv.ptr, dy.ptr, dot2.ptr, None)
+        assert np.array_equal(u64(dot2.download(np.empty(1, np.complex128))), u64(np.array([dot])))   # deterministic
 
 
 def test_dotc():
