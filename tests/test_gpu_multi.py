@@ -27,3 +27,18 @@ def test_two_ranks(cfg):
     assert out["n_gpus"] == 2 and out["rows_bad"] == 0
     assert out["hv_max_rel_err"] < 1e-12
     assert out["hv_p2p_equals_allgather"] is True
+
+
+@pytest.mark.parametrize("cfg", ["xxz16", "H8"])
+def test_two_ranks_lanczos(cfg):
+    """The two-pass Lanczos loop (qr_apply_p2p_dot + device scalars, all-reduced in place) against the round-1 loop over the
+    all-gather apply (host scalars) on two ranks: same alphas to rounding."""
+    if _ffi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29579", str(ROOT / "tools" / "lanczos_bench.py"), cfg, "20"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert res.returncode == 0 and lines, res.stdout[-2000:] + res.stderr[-2000:]
+    out = json.loads(lines[-1])
+    assert out["n_gpus"] == 2 and out["max_alpha_diff"] < 1e-9 * max(1.0, abs(out["beta0"]))
