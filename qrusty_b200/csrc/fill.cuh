@@ -724,7 +724,7 @@ fill_lanes_kernel(PlanDev p, uint32_t G, uint32_t n_light, uint32_t log2R, uint3
 // is exact, so this is the __dadd_rn fold of accel.rs:191-205 bit for bit, signed zeros included.
 //
 // Dynamic shared memory (host: rows_smem): [2][tile] double2 data | [2][tile] u64 column ids | term table
-// (c' then z) | s_hv [hv_cap][2^hv_log2] double2 | s_h0c [hv_cap] double2 | s_hd [hv_cap] uint4 | s_cnt (CS).
+// (c' then z) | s_hv [hv_cap][2^hv_log2] double2 | s_h0c [hv_cap] double2 | s_hd [hv_cap] uint4 | s_ord [hv_cap] | s_cnt (CS).
 // ---------------------------------------------------------------------------------
 // ---- thread-block cluster helpers (rows kernel, CL > 1) ----
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -805,8 +805,8 @@ __device__ __forceinline__ void rows_heavy_item(const uint4 d, const double2 c0,
 // the warps, (group, 32 rows) items are spread over the warps instead.
 template <int TH>
 __device__ __forceinline__ void rows_heavy_phase(const uint4 *s_hd, const double2 *s_h0c, double2 *s_hv, const uint32_t *s_ez,
-                                                 const double2 *s_ec, uint32_t n_heavy, uint32_t HS, uint32_t hv_log2,
-                                                 uint32_t sbase)
+                                                 const double2 *s_ec, const uint32_t *s_ord, uint32_t n_heavy, uint32_t HS,
+                                                 uint32_t hv_log2, uint32_t sbase)
 {
     constexpr uint32_t NW = TH / 32u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -823,22 +823,26 @@ __device__ __forceinline__ void rows_heavy_phase(const uint4 *s_hd, const double
         return;
     }
     if (2u * n_heavy >= NW) {
-        // at least half as many heavy groups as warps: one group per warp visit, up to 4 rows per lane
-        for (uint32_t q = warp; q < n_heavy; q += NW) {
-            const uint4 d = s_hd[q];
-            const double2 c0 = s_h0c[q];
-            double hre[4], him[4];
-#pragma unroll
-            for (uint32_t e = 0; e < 4u; e++) {
-                const uint32_t s = (uint32_t)(__popc((sbase + lane + 32u * e) & d.z) & 1) << 31;
-                hre[e] = flip_sign(c0.x, s); him[e] = flip_sign(c0.y, s);
+        // at least half as many heavy groups as warps (molecular Hamiltonians: a 100-300-term Z-only group, a few dozen of
+        // 13-140 terms).  Items = (group, 64 rows: 2 rows per lane, two independent chains per component hide the FP64
+        // latency), dealt to the warps longest first and in snake order (s_ord: the groups sorted by term count), so that
+        // no warp is left with the two longest folds while fifteen wait at the barrier (ncu, H12: 30 % of the warp
+        // cycles were barrier stalls when group q simply went to warp q mod 16).
+        if (HS >= 64u) {
+            const uint32_t n_chunks = HS >> 6, n_items = n_heavy * n_chunks;
+            for (uint32_t round = 0, base = 0; base < n_items; round++, base += NW) {
+                const uint32_t item = base + ((round & 1u) ? NW - 1u - warp : warp);
+                if (item >= n_items) continue;
+                const uint32_t q = s_ord[item / n_chunks], ch = item % n_chunks;
+                rows_heavy_item<2>(s_hd[q], s_h0c[q], s_hv + (q << hv_log2) + (ch << 6), s_ez, s_ec, sbase + (ch << 6) + lane, lane);
             }
-            if (HS > 64u) rows_heavy_fold<4>(s_ez + d.x, s_ec + d.x, d.y, sbase + lane, hre, him);
-            else if (HS > 32u) rows_heavy_fold<2>(s_ez + d.x, s_ec + d.x, d.y, sbase + lane, hre, him);
-            else rows_heavy_fold<1>(s_ez + d.x, s_ec + d.x, d.y, sbase + lane, hre, him);
-#pragma unroll
-            for (uint32_t e = 0; e < 4u; e++)
-                if (lane + 32u * e < HS) s_hv[(q << hv_log2) + lane + 32u * e] = make_double2(hre[e], him[e]);
+        } else {
+            for (uint32_t round = 0, base = 0; base < n_heavy; round++, base += NW) {
+                const uint32_t item = base + ((round & 1u) ? NW - 1u - warp : warp);
+                if (item >= n_heavy) continue;
+                const uint32_t q = s_ord[item];
+                rows_heavy_item<1>(s_hd[q], s_h0c[q], s_hv + (q << hv_log2), s_ez, s_ec, sbase + lane, lane);
+            }
         }
         return;
     }
@@ -880,6 +884,12 @@ struct RowsSplit {
     uint32_t g0[33];               // subtree s = sorted groups [g0[s], g0[s + 1])
     uint32_t level[32];            // its groups share the mask bits >= level[s]
     uint32_t cta0[33];             // CTAs [cta0[s], cta0[s + 1]) work on subtree s
+    // whole-row variants (CL == 1), terms in registers: thread slot gl owns group perm[gl] (0xffffffff: none) instead of
+    // group gl.  The host sorts the groups by term count and deals warp-sized chunks to the warps so that every warp's
+    // longest groups add up to about the same (a warp folds to its LONGEST group; with the groups in mask order a few
+    // warps fold 6 + 6 terms while most could do with 4 + 4, and the batch barrier waits for them).
+    const uint32_t *perm;
+    uint32_t perm_n;
 };
 
 template <int NG, int Q, int TH, bool REGT, bool HEAVY, bool CS, int CL>
@@ -919,7 +929,8 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
     double2 *s_hv = reinterpret_cast<double2 *>(smem_raw + (((size_t)tile_n * 48u + (size_t)n_extra * 20u + 15u) & ~(size_t)15u));   // [hv_cap][2^hv_log2]
     double2 *s_h0c = s_hv + ((size_t)hv_cap << hv_log2);                                 // [hv_cap]
     uint4 *s_hd = reinterpret_cast<uint4 *>(s_h0c + hv_cap);                             // [hv_cap]
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_hd + hv_cap);                       // [n_qubits][G] when CS
+    uint32_t *s_ord = reinterpret_cast<uint32_t *>(s_hd + hv_cap);                       // [hv_cap] heavy groups, longest first
+    uint32_t *s_cnt = s_ord + hv_cap;                                                    // [n_qubits][G] when CS
     __shared__ uint32_t s_nheavy, s_hterms;
     __shared__ uint32_t s_cb[32];                                  // SPLIT: cnt[g0][b] for b >= level (else 0), x of g0 in s_cb_x
     __shared__ uint32_t s_cb_x;
@@ -937,13 +948,16 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
     __syncthreads();
 
     // ---- once per CTA: this thread's groups ------------------------------------------------------
-    uint32_t x[NG], z[NG][NT], eb[NG], ee[NG], off[NG], hidx[NG];
+    uint32_t x[NG], z[NG][NT], eb[NG], ee[NG], off[NG], hidx[NG], gid[NG];
     int32_t sd[NG][NS];
     double cr[NG][NT], ci[NG][NT];
 #pragma unroll
     for (int k = 0; k < NG; k++) {
-        const uint32_t gl = tg + (uint32_t)k * GP, g = gbase + gl;          // slot inside the CTA, group
-        const bool mine = gl < Gn && g < G;
+        const uint32_t gl = tg + (uint32_t)k * GP;                          // slot inside the CTA
+        uint32_t g = gbase + gl;                                            // ... and its group
+        bool mine = gl < Gn && g < G;
+        if (CL == 1 && sp.perm != nullptr) { g = gl < sp.perm_n ? __ldg(&sp.perm[gl]) : NOT_HEAVY; mine = g < G; }
+        gid[k] = mine ? g : NOT_HEAVY;
         const uint32_t gg = g < G ? g : G - 1u;
         const uint32_t t0 = __ldg(&p.goff[gg]), t1 = __ldg(&p.goff[gg + 1]);
         x[k] = __ldg(&p.gx[gg]);
@@ -991,6 +1005,16 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
     }
     __syncthreads();
 
+    if constexpr (HEAVY) {
+        const uint32_t nh = min(s_nheavy, hv_cap);
+        for (uint32_t h = threadIdx.x; h < nh; h += TH) {
+            const uint32_t mine_t = s_hd[h].y;
+            uint32_t rank = 0;
+            for (uint32_t o = 0; o < nh; o++) { const uint32_t t = s_hd[o].y; rank += (t > mine_t || (t == mine_t && o < h)) ? 1u : 0u; }
+            s_ord[rank] = h;
+        }
+        __syncthreads();
+    }
     if constexpr (CL > 1) cluster_barrier();                       // every CTA of the cluster is resident before the first remote store
     if (HEAVY && sl != 0u) {
         // sub-batches > 0 own the same groups as sub-batch 0: look the heavy index up in the descriptor table
@@ -999,7 +1023,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
         for (int k = 0; k < NG; k++)
             if (sub != 0u) {
                 hidx[k] = NOT_HEAVY;
-                for (uint32_t h = 0; h < nh; h++) if (s_hd[h].w == gbase + tg + (uint32_t)k * GP) hidx[k] = h;
+                for (uint32_t h = 0; h < nh; h++) if (s_hd[h].w == gid[k]) hidx[k] = h;
             }
     }
     const uint32_t R = 1u << log2R, n_batches = R >> QB;
@@ -1018,7 +1042,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
         // slot of every group in the first row this thread handles in the run's first batch
 #pragma unroll
         for (int k = 0; k < NG; k++) {
-            const uint32_t g = gbase + tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u, xr = x[k] ^ (r0 + (sub << Q));   // the thread's first row
+            const uint32_t g = gid[k], gg = g < G ? g : G - 1u, xr = x[k] ^ (r0 + (sub << Q));   // the thread's first row
             uint32_t o = 0;
             for (uint32_t b = 0; b < nq; b++) {
                 const uint32_t cb = CS ? s_cnt[b * G + gg] : __ldg(&p.cnt_t[b * T + gg]);
@@ -1044,7 +1068,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
                     if (b == QB) s = sd[k][Q];
                     else if (b == QB + 1u) s = sd[k][Q + 1];
                     else {
-                        const uint32_t g = gbase + tg + (uint32_t)k * GP, gg = g < G ? g : G - 1u;
+                        const uint32_t g = gid[k], gg = g < G ? g : G - 1u;
                         const int32_t cb = (int32_t)(CS ? s_cnt[b * G + gg] : __ldg(&p.cnt_t[b * T + gg]));
                         s = ((x[k] >> b) & 1u) ? -cb : cb;
                     }
@@ -1057,7 +1081,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
                 // The barrier that ended the previous batch also retired the last reader of s_hv.
                 // A lane folds rows lane, lane + 32, ... of the strip together: the fold is one dependent chain per
                 // row, so the rows of a lane are what hides the FP64 latency of the longest group.
-                rows_heavy_phase<TH>(s_hd, s_h0c, s_hv, s_ez, s_ec, n_heavy, HS, hv_log2, rb & ~(HS - 1u));
+                rows_heavy_phase<TH>(s_hd, s_h0c, s_hv, s_ez, s_ec, s_ord, n_heavy, HS, hv_log2, rb & ~(HS - 1u));
                 __syncthreads();
             }
             double2 *bd = sdat + parity * tile_n;
@@ -1065,7 +1089,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
             const uint32_t rt = rb + (sub << Q);                   // first of this thread's RT rows (bits < Q are 0)
 #pragma unroll
             for (int k = 0; k < NG; k++) {
-                if (tg + (uint32_t)k * GP < Gn && gbase + tg + (uint32_t)k * GP < G) {
+                if (gid[k] != NOT_HEAVY) {
                     double re[RT], im[RT];
                     if (HEAVY && hidx[k] != NOT_HEAVY) {
 #pragma unroll

@@ -149,6 +149,7 @@ struct qr_plan {
     int rows_cl = 1;                                       // > 1: thread-block cluster of rows_cl CTAs per run of rows; 0: split mode
     qr::RowsSplit rows_split{};                            // split mode: trie subtrees of <= 1024 groups, CTAs per subtree
     uint32_t rows_gc = 0;                                  // groups per CTA of the cluster
+    uint32_t *rows_perm = nullptr;                         // thread slot -> group table of the whole-row register variant (RowsSplit::perm)
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -264,14 +265,71 @@ constexpr size_t ROWS_SMEM_CAP = MAX_SMEM - 1024;           // the kernel's stat
 constexpr uint32_t ROWS_HEAVY_TERMS = 6;                 // groups with more terms than this are "heavy"
 size_t rows_smem(uint64_t G, uint64_t n_extra, int q, uint64_t n_heavy = 0, int hv_log2 = 5)
 {
-    return (size_t)align_up((G << q) * 48 + n_extra * 20, 16) + (size_t)n_heavy * ((16ull << hv_log2) + 32);
+    return (size_t)align_up((G << q) * 48 + n_extra * 20, 16) + (size_t)n_heavy * ((16ull << hv_log2) + 36);
 }
 
 bool choose_rows_shape(qr_plan *pl);
 
 // choose_rows_shape picks the variant; the rank-table columns are staged in shared memory on top when they are small
 // (short rows: G * n_qubits words <= 24 KB) and still fit
+// Whole-row variant with the terms in registers: which group each thread slot owns.  A warp folds to its LONGEST light
+// group, so the groups are sorted by term count (heavy ones, folded elsewhere, count 1) and dealt in warp-sized chunks:
+// every chunk to the warp whose chunks so far add up to the least (longest chunk first).  H12: 16 warps x 2 chunks, the five
+// chunks of 6-term groups end up alone or with a 4-term chunk instead of two to a warp.  QR_FILL_ROWS_PERM=0: mask order.
+void build_rows_perm(qr_plan *pl)
+{
+    if (pl->rows_perm) { cudaFree(pl->rows_perm); pl->rows_perm = nullptr; }
+    pl->rows_split.perm = nullptr; pl->rows_split.perm_n = 0;
+    const char *env = getenv("QR_FILL_ROWS_PERM");
+    if ((env && env[0] == '0') || !pl->rows_regt || pl->rows_cl != 1 || pl->rows_th != 512) return;
+    const uint32_t G = (uint32_t)pl->n_groups, GP = 512u >> pl->rows_sl, NG = (uint32_t)pl->rows_ng, n_warps = GP / 32u;
+    if (n_warps == 0 || NG == 0 || (uint64_t)NG * GP < G) return;
+    std::vector<uint32_t> goff(G + 1);
+    if (cudaMemcpy(goff.data(), pl->dev.goff, (G + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return; }
+    auto cost = [&](uint32_t g) { const uint32_t t = goff[g + 1] - goff[g]; return t > pl->rows_hv_thr ? 1u : t; };
+    std::vector<uint32_t> order(G);
+    for (uint32_t g = 0; g < G; g++) order[g] = g;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
+    const uint32_t n_chunks = (G + 31u) / 32u;
+    std::vector<uint32_t> load(n_warps, 0), used(n_warps, 0), perm((size_t)NG * GP, 0xffffffffu);
+    for (uint32_t c = 0; c < n_chunks; c++) {                       // chunks come longest first
+        uint32_t w = n_warps;
+        for (uint32_t v = 0; v < n_warps; v++) if (used[v] < NG && (w == n_warps || load[v] < load[w])) w = v;
+        if (w == n_warps) return;                                    // cannot happen: NG * GP >= G
+        const uint32_t k = used[w]++;
+        load[w] += cost(order[c * 32u]);
+        for (uint32_t l = 0; l < 32u && c * 32u + l < G; l++) perm[(size_t)k * GP + w * 32u + l] = order[c * 32u + l];
+    }
+    // worth it only when it shortens the longest warp by 15 % or more against mask order (molecular Hamiltonians: H8 4.21 ->
+    // 4.61 TB/s); with uniform groups it only perturbs the lane <-> slot pattern of the stores (XXZ n = 27: 6.06 -> 5.47)
+    uint32_t max_perm = 0, max_id = 0;
+    for (uint32_t w = 0; w < n_warps; w++) {
+        max_perm = std::max(max_perm, load[w]);
+        uint32_t id = 0;
+        for (uint32_t k = 0; k < NG; k++) {
+            uint32_t m = 0;
+            for (uint32_t l = 0; l < 32u; l++) { const uint64_t g = (uint64_t)k * GP + w * 32u + l; if (g < G) m = std::max(m, cost((uint32_t)g)); }
+            id += m;
+        }
+        max_id = std::max(max_id, id);
+    }
+    if (!(env && env[0] == '1') && 100u * max_perm > 85u * max_id) return;
+    if (cudaMalloc(reinterpret_cast<void **>(&pl->rows_perm), perm.size() * 4) != cudaSuccess) { cudaGetLastError(); pl->rows_perm = nullptr; return; }
+    if (cudaMemcpy(pl->rows_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(pl->rows_perm); pl->rows_perm = nullptr; return;
+    }
+    pl->rows_split.perm = pl->rows_perm; pl->rows_split.perm_n = (uint32_t)perm.size();
+}
+
+bool choose_rows_shape(qr_plan *pl);
+bool choose_rows_inner(qr_plan *pl);
 bool choose_rows(qr_plan *pl)
+{
+    const bool ok = choose_rows_inner(pl);
+    if (ok) build_rows_perm(pl);
+    return ok;
+}
+bool choose_rows_inner(qr_plan *pl)
 {
     pl->rows_cnt_smem = 0; pl->rows_cl = 1; pl->rows_gc = 0; pl->rows_split = qr::RowsSplit{};
     if (!choose_rows_shape(pl)) return false;
@@ -394,7 +452,7 @@ bool choose_rows_shape(qr_plan *pl)
             }
             const uint64_t si = (gmax + 3) & ~1ull;                // pitch of a buffered row of column ids
             for (int q = q_forced ? std::min(q_forced, 2) : 2; ok && q >= (q_forced ? std::min(q_forced, 2) : 1); q--) {
-                auto smem_d = [&](int hl) { return (size_t)align_up((si << q) * 48 + hx_max * 20, 16) + (size_t)nh_max * ((16ull << hl) + 32); };
+                auto smem_d = [&](int hl) { return (size_t)align_up((si << q) * 48 + hx_max * 20, 16) + (size_t)nh_max * ((16ull << hl) + 36); };
                 int hl = 5;
                 if (smem_d(hl) > ROWS_SMEM_CAP) continue;
                 while (hl < 7 && nh_max != 0 && smem_d(hl + 1) <= ROWS_SMEM_CAP) hl++;
@@ -447,7 +505,7 @@ bool choose_rows_shape(qr_plan *pl)
                 if (goff[g + 1] - goff[g] > thr0) { nh++; hx += goff[g + 1] - goff[g] - 1; }
             nh_max = std::max(nh_max, nh); hx_max = std::max(hx_max, hx);
         }
-        auto smem_c = [&](int hl) { return (size_t)align_up(rows_own * G * 48 + hx_max * 20, 16) + (size_t)nh_max * ((16ull << hl) + 32); };
+        auto smem_c = [&](int hl) { return (size_t)align_up(rows_own * G * 48 + hx_max * 20, 16) + (size_t)nh_max * ((16ull << hl) + 36); };
         int hl = 5;
         if (smem_c(hl) > ROWS_SMEM_CAP) continue;
         while (hl < 7 && nh_max != 0 && smem_c(hl + 1) <= ROWS_SMEM_CAP) hl++;
@@ -688,6 +746,7 @@ extern "C" int qr_plan_destroy(qr_plan *pl)
     if (pl->diag_cache) cudaFree(pl->diag_cache);
     if (pl->dot_partials) cudaFree(pl->dot_partials);
     if (pl->fold_slab) cudaFree(pl->fold_slab);
+    if (pl->rows_perm) cudaFree(pl->rows_perm);
     for (auto &kv : pl->ptiles) if (kv.second.slab) cudaFree(kv.second.slab);
     if (pl->slab) cudaFree(pl->slab);
     delete pl;
