@@ -153,28 +153,20 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
         yr[e] = 0.0; yi[e] = 0.0;
     }
     const uint32_t G_main = G;
-    // With the dot epilogue the cached diagonal is applied LAST: its v[r] is then the value the dot needs, read once (read
-    // first, the row's own element is long evicted when the epilogue comes: +0.06 ms on C4 for a second pass over v).
-    // y then differs from the plain apply in the rounding of one addition per row.
-    const bool diag_last = dotp != nullptr && (diag_re != nullptr || diag != nullptr);
     uint32_t g_first = 0;
     if (diag_re != nullptr) {                                      // real diagonal (every c' of the mask-0 group is real): 8 B per row
         g_first = 1;
-        if (!diag_last) {
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const double d = __ldcs(&diag_re[(uint64_t)r[e] - row_lo]);     // evict-first: keep L2 for v
-                cfma(yr[e], yi[e], d, 0.0, ld_nc_double2(&v_own[r[e]]), true);
-            }
+        for (int e = 0; e < E; e++) {
+            const double d = __ldcs(&diag_re[(uint64_t)r[e] - row_lo]);     // evict-first: keep L2 for v
+            cfma(yr[e], yi[e], d, 0.0, ld_nc_double2(&v_own[r[e]]), true);
         }
     } else if (diag != nullptr) {
         g_first = 1;
-        if (!diag_last) {
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const double2 d = __ldcs(&diag[(uint64_t)r[e] - row_lo]);      // evict-first: keep L2 for v
-                cfma(yr[e], yi[e], d.x, d.y, ld_nc_double2(&v_own[r[e]]), false);
-            }
+        for (int e = 0; e < E; e++) {
+            const double2 d = __ldcs(&diag[(uint64_t)r[e] - row_lo]);      // evict-first: keep L2 for v
+            cfma(yr[e], yi[e], d.x, d.y, ld_nc_double2(&v_own[r[e]]), false);
         }
     }
     for (uint32_t g0 = g_first; g0 < G_main; g0 += APPLY_BATCH) {
@@ -201,22 +193,16 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
             }
         }
     }
-    if (dotp != nullptr) {                                         // CTA-uniform
-        double dr = 0.0, di = 0.0;
-#pragma unroll
-        for (int e = 0; e < E; e++) {
-            const double2 w = ld_nc_double2(&v_own[r[e]]);
-            if (diag_last) {
-                if (diag_re != nullptr) cfma(yr[e], yi[e], __ldcs(&diag_re[(uint64_t)r[e] - row_lo]), 0.0, w, true);
-                else { const double2 d = __ldcs(&diag[(uint64_t)r[e] - row_lo]); cfma(yr[e], yi[e], d.x, d.y, w, false); }
-            }
-            if (live[e]) cdot_acc(dr, di, w, yr[e], yi[e]);
-        }
-        block_dot_store(dr, di, &dotp[blockIdx.x]);
-    }
 #pragma unroll
     for (int e = 0; e < E; e++)
         if (live[e]) __stcs(&y[(uint64_t)r[e] - row_lo], make_double2(yr[e], yi[e]));   // streaming store
+    if (dotp != nullptr) {                                         // CTA-uniform
+        double dr = 0.0, di = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            if (live[e]) cdot_acc(dr, di, ld_nc_double2(&v_own[r[e]]), yr[e], yi[e]);
+        block_dot_store(dr, di, &dotp[blockIdx.x]);
+    }
 }
 
 // ---------------------------------------------------------------------------------

@@ -100,25 +100,20 @@ apply_fold_kernel(PlanDev p, FoldDev f, uint32_t G, uint64_t row_lo, uint64_t ro
 #pragma unroll
     for (int e = 0; e < E; e++) { yr[e] = 0.0; yi[e] = 0.0; }
     uint32_t g_first = 0;
-    const bool diag_last = dotp != nullptr && (diag_re != nullptr || diag != nullptr);   // as apply_direct_kernel: v[r] read once, at the end
     if (diag_re != nullptr) {
         g_first = 1;
-        if (!diag_last) {
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const uint32_t r = r0 + ((uint32_t)e << B0);
-                cfma(yr[e], yi[e], __ldcs(&diag_re[(uint64_t)r - row_lo]), 0.0, ld_nc_double2(&v_own[r]), true);
-            }
+        for (int e = 0; e < E; e++) {
+            const uint32_t r = r0 + ((uint32_t)e << B0);
+            cfma(yr[e], yi[e], __ldcs(&diag_re[(uint64_t)r - row_lo]), 0.0, ld_nc_double2(&v_own[r]), true);
         }
     } else if (diag != nullptr) {
         g_first = 1;
-        if (!diag_last) {
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const uint32_t r = r0 + ((uint32_t)e << B0);
-                const double2 d = __ldcs(&diag[(uint64_t)r - row_lo]);
-                cfma(yr[e], yi[e], d.x, d.y, ld_nc_double2(&v_own[r]), false);
-            }
+        for (int e = 0; e < E; e++) {
+            const uint32_t r = r0 + ((uint32_t)e << B0);
+            const double2 d = __ldcs(&diag[(uint64_t)r - row_lo]);
+            cfma(yr[e], yi[e], d.x, d.y, ld_nc_double2(&v_own[r]), false);
         }
     }
     for (uint32_t g0 = g_first; g0 < G; g0 += FOLD_BATCH) {
@@ -200,22 +195,14 @@ apply_fold_kernel(PlanDev p, FoldDev f, uint32_t G, uint64_t row_lo, uint64_t ro
             }
         }
     }
+#pragma unroll
+    for (int e = 0; e < E; e++) __stcs(&y[(uint64_t)(r0 + ((uint32_t)e << B0)) - row_lo], make_double2(yr[e], yi[e]));
     if (dotp != nullptr) {                                         // per-CTA partial of <v, y> (apply.cuh)
         double dr = 0.0, di = 0.0;
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            const uint32_t r = r0 + ((uint32_t)e << B0);
-            const double2 w = ld_nc_double2(&v_own[r]);
-            if (diag_last) {
-                if (diag_re != nullptr) cfma(yr[e], yi[e], __ldcs(&diag_re[(uint64_t)r - row_lo]), 0.0, w, true);
-                else { const double2 d = __ldcs(&diag[(uint64_t)r - row_lo]); cfma(yr[e], yi[e], d.x, d.y, w, false); }
-            }
-            cdot_acc(dr, di, w, yr[e], yi[e]);
-        }
+        for (int e = 0; e < E; e++) cdot_acc(dr, di, ld_nc_double2(&v_own[r0 + ((uint32_t)e << B0)]), yr[e], yi[e]);
         block_dot_store(dr, di, &dotp[blockIdx.x]);
     }
-#pragma unroll
-    for (int e = 0; e < E; e++) __stcs(&y[(uint64_t)(r0 + ((uint32_t)e << B0)) - row_lo], make_double2(yr[e], yi[e]));
 }
 
 // ---------------------------------------------------------------------------------

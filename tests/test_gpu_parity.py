@@ -904,14 +904,11 @@ def test_lanczos_matches_numpy(fixtures):
 
 @pytest.mark.parametrize("name", ["C1", "H6", "xxz16", "random_n10"])
 def test_apply_dot(fixtures, name):
-    """qr_apply_dot_device: y is the plain apply's up to the rounding of one addition per row (the cached diagonal is
-    applied last, so that the row's own element is read once for both the product and the dot), the fused <v, H v>
-    equals the vdot of the downloaded vectors to rounding (both apply kernels: gather and fold; whole vector, row blocks)."""
+    """qr_apply_dot_device: y is the plain apply's bit for bit, the fused <v, H v> equals the vdot of the downloaded
+    vectors to rounding (both apply kernels: gather and fold; whole vector and a row block)."""
     labels, coeffs = H.xxz_chain(16, 1.0, 0.7) if name == "xxz16" else SMALL[name](fixtures)
     plan = make_op(labels, coeffs).plan()
     dim = plan.dim
-    n_a, params_a = O.make_params(labels, coeffs)
-    absH = np.abs(params_a["re"] + 1j * params_a["im"]).sum()
     v = H.lanczos_start_vector(0, dim, seed=51)
     dv = DeviceBuffer(dim * 16); dv.upload(v)
     for lo, hi in [(0, dim), (dim // 4, dim // 2), (3, dim - 5)]:
@@ -920,9 +917,9 @@ def test_apply_dot(fixtures, name):
         _ffi.call("qr_apply_dot_device", plan.handle, lo, hi, dv.ptr, dy.ptr, dd.ptr, None)
         y1 = dy.download(np.empty(hi - lo, np.complex128))
         dot = dd.download(np.empty(1, np.complex128))[0]
-        assert np.abs(y1 - y0).max() <= 1e-15 * absH * np.abs(v).max(), (lo, hi)
-        want = np.vdot(v[lo:hi], y1)
-        assert abs(dot - want) <= 1e-12 * np.abs(v[lo:hi]).dot(np.abs(y1)) + 1e-300, (lo, hi, dot, want)
+        assert np.array_equal(u64(y1), u64(y0)), (lo, hi)
+        want = np.vdot(v[lo:hi], y0)
+        assert abs(dot - want) <= 1e-12 * np.abs(v[lo:hi]).dot(np.abs(y0)) + 1e-300, (lo, hi, dot, want)
         dot2 = DeviceBuffer(16)
         _ffi.call("qr_apply_dot_device", plan.handle, lo, hi, dv.ptr, dy.ptr, dot2.ptr, None)
         assert np.array_equal(u64(dot2.download(np.empty(1, np.complex128))), u64(np.array([dot])))   # deterministic
