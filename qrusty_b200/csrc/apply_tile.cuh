@@ -57,24 +57,7 @@ struct ApplyTileArgs {
     uint32_t n_peers, need_mask;          // ranks whose shards this rank reads
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
+// smem_u32, mbar_init, mbar_expect_tx, mbar_wait: fill.cuh (shared with the rows kernel)
 // global (local HBM or a peer's memory behind NVLink) -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_load_global_to_smem(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {

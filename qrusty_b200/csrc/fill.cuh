@@ -128,6 +128,26 @@ fill_direct_kernel(PlanDev p, uint32_t G, uint64_t lo, uint64_t hi, uint64_t out
     }
 }
 
+// ---- mbarrier helpers (also used by the tiled H.v kernels, apply_tile.cuh / apply_fold.cuh) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 // ---------------------------------------------------------------------------------
 // Staged kernel: a CTA owns a tile of R = 32*E whole rows (aligned to R).  The
 // tile's R*G entries are contiguous in BOTH output arrays, so the CTA assembles
@@ -888,11 +908,57 @@ struct RowsSplit {
     // group gl.  The host sorts the groups by term count and deals warp-sized chunks to the warps so that every warp's
     // longest groups add up to about the same (a warp folds to its LONGEST group; with the groups in mask order a few
     // warps fold 6 + 6 terms while most could do with 4 + 4, and the batch barrier waits for them).
+    // Split mode: the same per subtree, perm[s * perm_n + gl] (perm_n slots per subtree).
     const uint32_t *perm;
     uint32_t perm_n;
+    // EXTERNAL heavy values (split mode on term-rich operators): the groups of more than hv_thr terms are folded by
+    // heavy_values_kernel for a chunk of rows before this launch -- ext_hv[h * ext_rows + (row - ext_row0)], h =
+    // ext_hidx[group] -- instead of by the CTA that owns them, so that no subtree's CTAs carry the 100-300-term groups
+    // of the mask-0 neighbourhood, no shared memory goes to heavy tables and there is no heavy phase (and barrier).
+    const double2 *ext_hv;
+    const uint32_t *ext_hidx;
+    uint32_t ext_rows, ext_row0;
+    uint32_t dec_block;            // DEC: 1 = the warp that hands a batch over waits for the TMA's read at once (else after its next batch)
 };
 
-template <int NG, int Q, int TH, bool REGT, bool HEAVY, bool CS, int CL>
+// Values of the heavy groups for rows [row0, row0 + n_rows): warp <-> (heavy group, 32 * E rows), lane <-> E rows, the
+// reference's left-to-right fold (group_values: bit-exact).  heavy_g is sorted longest first, so the long folds start
+// first.  out[h * n_rows + (row - row0)]: a warp's stores are contiguous.
+template <int E>
+__global__ void __launch_bounds__(256)
+heavy_values_kernel(PlanDev p, const uint32_t *__restrict__ heavy_g, uint32_t nh, uint64_t row0, uint32_t n_rows,
+                    double2 *__restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31u, blocks_per_h = n_rows / (32u * E);
+    const uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (item >= (uint64_t)nh * blocks_per_h) return;
+    const uint32_t h = (uint32_t)(item / blocks_per_h), rb = (uint32_t)(item % blocks_per_h);
+    const uint32_t g = __ldg(&heavy_g[h]);
+    uint32_t r[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) r[e] = (uint32_t)row0 + rb * 32u * E + 32u * e + lane;
+    double ar[E], ai[E];
+    group_values<E>(p, __ldg(&p.goff[g]), __ldg(&p.goff[g + 1]), r, ar, ai);
+#pragma unroll
+    for (int e = 0; e < E; e++) out[(size_t)h * n_rows + (r[e] - (uint32_t)row0)] = make_double2(ar[e], ai[e]);
+}
+
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)     // release.cta: the arriving thread's earlier writes are visible to the waiter
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// DEC = true  : DECOUPLED warps (CL <= 1).  The batch barrier of the plain variant makes every warp wait for the slowest one
+//               of every batch (ncu, H12 / H10 split: 30-35 % of the warp cycles are barrier stalls at 16 warps per SM, and
+//               while the last warps of a batch finish, their schedulers have nothing else to issue).  Here the two batch
+//               buffers are handed over through mbarriers: a warp arrives on full[b] when its entries of the batch are in
+//               buffer b and goes straight on to the next batch as soon as empty[b ^ 1] says that the TMA has read the other
+//               buffer out.  The warp that arrives FIRST -- the one with time to spare -- takes the batch's hand-over: it
+//               waits for full[b], gives the buffer to the TMA, waits for the read and arrives on empty[b] (a bulk group can
+//               only be waited for by the thread that committed it, and a 17th warp would cost every thread 32 registers).
+//               A fast warp runs up to one batch ahead of the slowest.  The in-CTA heavy phase keeps two named barriers per strip.
+template <int NG, int Q, int TH, bool REGT, bool HEAVY, bool CS, int CL, bool DEC = false>
 __global__ void __launch_bounds__(TH, 1)
 fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t log2R, uint32_t sl, uint32_t n_runs,
                  uint32_t hv_thr, uint32_t hv_cap, uint32_t hv_log2, uint64_t tile_row0, uint64_t row_lo,
@@ -934,9 +1000,19 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
     __shared__ uint32_t s_nheavy, s_hterms;
     __shared__ uint32_t s_cb[32];                                  // SPLIT: cnt[g0][b] for b >= level (else 0), x of g0 in s_cb_x
     __shared__ uint32_t s_cb_x;
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];       // DEC: buffer b written by every warp / read out by the TMA
+    __shared__ uint32_t s_arrived[2];                              // DEC: warps that have arrived on full[b] (the first one hands over)
+    static_assert(!DEC || CL <= 1, "decoupled variant: one CTA per row run or split mode");
     const uint32_t T = p.n_terms, nq = (uint32_t)p.n_qubits;
     constexpr uint32_t NOT_HEAVY = 0xffffffffu;
-    if (threadIdx.x == 0) { s_nheavy = 0; s_hterms = 0; }
+    if (threadIdx.x == 0) {
+        s_nheavy = 0; s_hterms = 0;
+        if constexpr (DEC) {
+            s_arrived[0] = 0; s_arrived[1] = 0;
+            mbar_init(&s_full[0], TH / 32u); mbar_init(&s_full[1], TH / 32u); mbar_init(&s_empty[0], 1u); mbar_init(&s_empty[1], 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     if (SPLIT && threadIdx.x < 32u) {
         s_cb[threadIdx.x] = (threadIdx.x >= level && threadIdx.x < nq) ? __ldg(&p.cnt_t[threadIdx.x * T + gbase]) : 0u;
         if (threadIdx.x == 0) s_cb_x = __ldg(&p.gx[gbase]);
@@ -957,6 +1033,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
         uint32_t g = gbase + gl;                                            // ... and its group
         bool mine = gl < Gn && g < G;
         if (CL == 1 && sp.perm != nullptr) { g = gl < sp.perm_n ? __ldg(&sp.perm[gl]) : NOT_HEAVY; mine = g < G; }
+        if (SPLIT && sp.perm != nullptr) { g = gl < sp.perm_n ? __ldg(&sp.perm[sid * sp.perm_n + gl]) : NOT_HEAVY; mine = g < G; }
         gid[k] = mine ? g : NOT_HEAVY;
         const uint32_t gg = g < G ? g : G - 1u;
         const uint32_t t0 = __ldg(&p.goff[gg]), t1 = __ldg(&p.goff[gg + 1]);
@@ -964,7 +1041,9 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
         // heavy groups (more than hv_thr terms: the Z-only group of a molecular Hamiltonian, a few dozen others)
         // are evaluated lane <-> row for a strip of rows at a time by the whole CTA, not inside their owner's lane
         hidx[k] = NOT_HEAVY;
-        if (HEAVY && mine && sub == 0u && t1 - t0 > hv_thr) {
+        if (HEAVY && sp.ext_hv != nullptr) {                       // heavy values come from heavy_values_kernel
+            if (mine && t1 - t0 > hv_thr) hidx[k] = __ldg(&sp.ext_hidx[gg]);
+        } else if (HEAVY && mine && sub == 0u && t1 - t0 > hv_thr) {
             const uint32_t h = atomicAdd(&s_nheavy, 1u);
             if (h < hv_cap) {
                 hidx[k] = h;
@@ -1016,7 +1095,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
         __syncthreads();
     }
     if constexpr (CL > 1) cluster_barrier();                       // every CTA of the cluster is resident before the first remote store
-    if (HEAVY && sl != 0u) {
+    if (HEAVY && sl != 0u && sp.ext_hv == nullptr) {
         // sub-batches > 0 own the same groups as sub-batch 0: look the heavy index up in the descriptor table
         const uint32_t nh = min(s_nheavy, hv_cap);
 #pragma unroll
@@ -1030,6 +1109,8 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
     const uint32_t n_heavy = HEAVY ? min(s_nheavy, hv_cap) : 0u;
     const uint32_t HS = min(R, 1u << hv_log2), SB = HS >> QB;      // rows / batches per heavy strip (HS >= 2^QB; host-checked)
     uint32_t parity = 0;                                           // buffer of the current batch
+    uint32_t use = 0;                                              // DEC: batches done so far (buffer use = use >> 1)
+    uint32_t pending = 2u;                                         // DEC: buffer this warp handed to the TMA and has not yet declared empty
     for (uint32_t run = jcta; run < n_runs; run += n_share) {
         const uint64_t r0_64 = tile_row0 + ((uint64_t)run << log2R);   // first row of the run (aligned to R)
         const uint32_t r0 = (uint32_t)r0_64;
@@ -1040,6 +1121,8 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
                 if (lr + 1 == indptr_last_row) indptr[lr + 1] = indptr_base + (lr + 1) * G;
             }
         // slot of every group in the first row this thread handles in the run's first batch
+        // (summing the NEXT run's slots one rank-table word per batch during the current run was measured: H10 / H11 -4 %,
+        // H8 -1 %, profiles/r06_summary.md -- the loop below is not where the time goes)
 #pragma unroll
         for (int k = 0; k < NG; k++) {
             const uint32_t g = gid[k], gg = g < G ? g : G - 1u, xr = x[k] ^ (r0 + (sub << Q));   // the thread's first row
@@ -1081,21 +1164,46 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
                 // The barrier that ended the previous batch also retired the last reader of s_hv.
                 // A lane folds rows lane, lane + 32, ... of the strip together: the fold is one dependent chain per
                 // row, so the rows of a lane are what hides the FP64 latency of the longest group.
+                if constexpr (DEC) lanes_barrier(TH);              // no batch barrier here: retire the readers of the previous strip
                 rows_heavy_phase<TH>(s_hd, s_h0c, s_hv, s_ez, s_ec, s_ord, n_heavy, HS, hv_log2, rb & ~(HS - 1u));
-                __syncthreads();
+                if constexpr (DEC) lanes_barrier(TH); else __syncthreads();
             }
+            if (HEAVY && sp.ext_hv != nullptr && i + 1u < n_batches) {
+                // external heavy values of the NEXT batch -> L1 (RT rows = one 16 * RT-byte piece per heavy group): the load
+                // that feeds the store below otherwise waits a full L2 round trip in every batch
+                const uint32_t rn = (rb ^ (1u << (QB + (uint32_t)__ffs((int)(i + 1u)) - 1u))) + (sub << Q);
+#pragma unroll
+                for (int k = 0; k < NG; k++)
+                    if (hidx[k] != NOT_HEAVY)
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(sp.ext_hv + (size_t)hidx[k] * sp.ext_rows + (rn - sp.ext_row0)));
+            }
+            if constexpr (DEC) mbar_wait(&s_empty[parity], ((use >> 1) & 1u) ^ 1u);   // the TMA has read this buffer's previous batch out
             double2 *bd = sdat + parity * tile_n;
             uint64_t *bi = sidx + parity * tile_n;
             const uint32_t rt = rb + (sub << Q);                   // first of this thread's RT rows (bits < Q are 0)
+            // SPLIT: where slot 0 of the row would sit in segment j of the batch buffer (CTA-uniform, once per batch):
+            // data j * GW - base; ids j * SI - base + the parity of the segment's first entry ((rt + j - row_lo) * G + base)
+            uint32_t seg_d[RT], seg_i[RT];
+            if constexpr (SPLIT) {
+                const uint32_t par0 = (uint32_t)(((uint64_t)rt - row_lo) * G + base) & 1u;
+#pragma unroll
+                for (uint32_t j = 0; j < RT; j++) { seg_d[j] = j * GW - base; seg_i[j] = j * SI - base + (par0 ^ (j & G & 1u)); }
+            }
 #pragma unroll
             for (int k = 0; k < NG; k++) {
                 if (gid[k] != NOT_HEAVY) {
                     double re[RT], im[RT];
                     if (HEAVY && hidx[k] != NOT_HEAVY) {
+                        if (sp.ext_hv != nullptr) {
+                            const double2 *src = sp.ext_hv + (size_t)hidx[k] * sp.ext_rows + (rt - sp.ext_row0);
 #pragma unroll
-                        for (uint32_t j = 0; j < RT; j++) {
-                            const double2 v = s_hv[(hidx[k] << hv_log2) + ((rt + j) & (HS - 1u))];
-                            re[j] = v.x; im[j] = v.y;
+                            for (uint32_t j = 0; j < RT; j++) { const double2 v = __ldg(&src[j]); re[j] = v.x; im[j] = v.y; }
+                        } else {
+#pragma unroll
+                            for (uint32_t j = 0; j < RT; j++) {
+                                const double2 v = s_hv[(hidx[k] << hv_log2) + ((rt + j) & (HS - 1u))];
+                                re[j] = v.x; im[j] = v.y;
+                            }
                         }
                     } else {
                         // rt has no bits below Q, so popc((rt + j) & z) = popc(rt & z) + popc(j & z): one POPC per term
@@ -1140,10 +1248,9 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
 #pragma unroll
                         for (int b = 0; b < Q; b++) if ((j >> b) & 1u) o += (uint32_t)sd[k][b];
                         if constexpr (SPLIT) {                     // segment-local slot; ids shifted by the parity of the segment start
-                            const uint32_t local = o - j * G - base;
-                            const uint32_t par = (uint32_t)(((uint64_t)(rt + j) - row_lo) * G + base) & 1u;
-                            bd[j * GW + local] = make_double2(re[j], im[j]);
-                            bi[j * SI + par + local] = (uint64_t)((rt + j) ^ x[k]);
+                            const uint32_t slot = o - j * G;       // = off[k] + the steps of row j's low bits (sub == 0 here)
+                            bd[seg_d[j] + slot] = make_double2(re[j], im[j]);
+                            bi[seg_i[j] + slot] = (uint64_t)((rt + j) ^ x[k]);
                         } else if constexpr (CL > 1) {                    // row j belongs to CTA j / ROWS_OWN of the cluster
                             const uint32_t owner = j / ROWS_OWN;
                             st_cluster_f64x2(mapa_shared((uint32_t)__cvta_generic_to_shared(bd + o), owner), re[j], im[j]);
@@ -1161,6 +1268,51 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
                 asm volatile("fence.proxy.async;" ::: "memory");           // this thread's (remote) writes -> async proxy
                 if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 cluster_barrier();                                         // release / acquire across the cluster
+            } else if constexpr (DEC) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const uint32_t lane = threadIdx.x & 31u;
+                if (pending != 2u) {                               // warp-uniform: the batch this warp handed over last time
+                    if (lane < (SPLIT ? RT : 1u)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0u) mbar_arrive(&s_empty[pending]);
+                    pending = 2u;
+                }
+                __syncwarp();
+                uint32_t first = 0;
+                if (lane == 0u) { first = atomicAdd(&s_arrived[parity], 1u) == 0u ? 1u : 0u; mbar_arrive(&s_full[parity]); }
+                first = __shfl_sync(0xffffffffu, first, 0);
+                if (first) {                                       // warp-uniform: this warp hands the batch over
+                    mbar_wait(&s_full[parity], (use >> 1) & 1u);
+                    if (lane == 0u) s_arrived[parity] = 0u;        // nobody arrives here again before empty[parity]
+                    if constexpr (SPLIT) {
+                        if (lane < RT) {                           // one lane per row segment
+                            const uint32_t j = lane;
+                            const uint64_t gs = ((uint64_t)(rb + j) - row_lo) * G + base;
+                            const uint32_t par = (uint32_t)gs & 1u, n_al = (Gn - par) & ~1u;
+                            bulk_store_smem_to_global(data + gs, bd + j * GW, Gn * 16u);
+                            if (n_al) bulk_store_smem_to_global(indices + gs + par, bi + j * SI + 2u * par, n_al * 8u);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            if (par) indices[gs] = bi[j * SI + 1u];
+                            if ((Gn - par) & 1u) indices[gs + Gn - 1u] = bi[j * SI + par + Gn - 1u];
+                        }
+                    } else if (lane == 0u) {
+                        const uint64_t o = ((uint64_t)rb - row_lo) * G;
+                        bulk_store_smem_to_global(data + o, bd, tile_n * 16u);
+                        bulk_store_smem_to_global(indices + o, bi, tile_n * 8u);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    // the buffer is free once the TMA has read it: waited for after this warp's NEXT batch (by then the read
+                    // is normally over; waiting here would serialise the copy with this warp's share of the next batch)
+                    pending = parity;
+                    if (sp.dec_block) {
+                        if (lane < (SPLIT ? RT : 1u)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0u) mbar_arrive(&s_empty[parity]);
+                        pending = 2u;
+                    }
+                }
+                parity ^= 1u; use++;
+                continue;
             } else {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 if (threadIdx.x < (SPLIT ? RT : 1u)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1187,7 +1339,7 @@ fill_rows_kernel(PlanDev p, uint32_t G, uint32_t Gc, uint32_t n_extra, uint32_t 
             parity ^= 1u;
         }
     }
-    if (threadIdx.x < (SPLIT ? RT : 1u)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (DEC || threadIdx.x < (SPLIT ? RT : 1u)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if constexpr (CL > 1) cluster_barrier();                       // nobody leaves while a peer could still address its memory
 }
 

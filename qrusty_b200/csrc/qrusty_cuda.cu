@@ -150,6 +150,13 @@ struct qr_plan {
     qr::RowsSplit rows_split{};                            // split mode: trie subtrees of <= 1024 groups, CTAs per subtree
     uint32_t rows_gc = 0;                                  // groups per CTA of the cluster
     uint32_t *rows_perm = nullptr;                         // thread slot -> group table of the whole-row register variant (RowsSplit::perm)
+    // split mode with EXTERNAL heavy values (heavy_values_kernel, fill.cuh): the heavy groups longest first, group -> index,
+    // and the values of one chunk of rows
+    bool rows_ext_heavy = false;
+    uint32_t ext_nh = 0;
+    uint32_t *ext_heavy_g = nullptr, *ext_hidx = nullptr;
+    double2 *ext_hv = nullptr;
+    uint64_t ext_hv_rows = 0;
     uint32_t n_const = 0;                  // groups whose value does not depend on the row
     uint32_t max_group_terms = 0;          // longest term list of a group
     uint32_t merge_dups = 0;               // QR_PLAN_MERGE_DUPLICATES
@@ -281,44 +288,75 @@ void build_rows_perm(qr_plan *pl)
     if (pl->rows_perm) { cudaFree(pl->rows_perm); pl->rows_perm = nullptr; }
     pl->rows_split.perm = nullptr; pl->rows_split.perm_n = 0;
     const char *env = getenv("QR_FILL_ROWS_PERM");
-    if ((env && env[0] == '0') || !pl->rows_regt || pl->rows_cl != 1 || pl->rows_th != 512) return;
+    const bool split = pl->rows_cl == 0;
+    if ((env && env[0] == '0') || !pl->rows_regt || (pl->rows_cl != 1 && !split) || pl->rows_th != 512) return;
     const uint32_t G = (uint32_t)pl->n_groups, GP = 512u >> pl->rows_sl, NG = (uint32_t)pl->rows_ng, n_warps = GP / 32u;
-    if (n_warps == 0 || NG == 0 || (uint64_t)NG * GP < G) return;
+    if (n_warps == 0 || NG == 0 || (!split && (uint64_t)NG * GP < G)) return;
     std::vector<uint32_t> goff(G + 1);
     if (cudaMemcpy(goff.data(), pl->dev.goff, (G + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return; }
     auto cost = [&](uint32_t g) { const uint32_t t = goff[g + 1] - goff[g]; return t > pl->rows_hv_thr ? 1u : t; };
-    std::vector<uint32_t> order(G);
-    for (uint32_t g = 0; g < G; g++) order[g] = g;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
-    const uint32_t n_chunks = (G + 31u) / 32u;
-    std::vector<uint32_t> load(n_warps, 0), used(n_warps, 0), perm((size_t)NG * GP, 0xffffffffu);
-    for (uint32_t c = 0; c < n_chunks; c++) {                       // chunks come longest first
-        uint32_t w = n_warps;
-        for (uint32_t v = 0; v < n_warps; v++) if (used[v] < NG && (w == n_warps || load[v] < load[w])) w = v;
-        if (w == n_warps) return;                                    // cannot happen: NG * GP >= G
-        const uint32_t k = used[w]++;
-        load[w] += cost(order[c * 32u]);
-        for (uint32_t l = 0; l < 32u && c * 32u + l < G; l++) perm[(size_t)k * GP + w * 32u + l] = order[c * 32u + l];
+    // split mode: one table per subtree (groups [g0[s], g0[s + 1])), the same dealing inside each
+    const uint32_t n_sub = split ? pl->rows_split.n : 1u, slots = NG * GP;
+    std::vector<uint32_t> perm((size_t)n_sub * slots, 0xffffffffu);
+    uint64_t sum_perm = 0, sum_id = 0;                              // longest warp, summed over the subtrees: dealt / mask order
+    for (uint32_t sb = 0; sb < n_sub; sb++) {
+        const uint32_t g_lo = split ? pl->rows_split.g0[sb] : 0u, g_hi = split ? pl->rows_split.g0[sb + 1] : G, Gs = g_hi - g_lo;
+        if ((uint64_t)slots < Gs) return;
+        std::vector<uint32_t> order(Gs);
+        for (uint32_t g = 0; g < Gs; g++) order[g] = g_lo + g;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
+        const uint32_t n_chunks = (Gs + 31u) / 32u;
+        std::vector<uint32_t> load(n_warps, 0), used(n_warps, 0);
+        for (uint32_t c = 0; c < n_chunks; c++) {                       // chunks come longest first
+            uint32_t w = n_warps;
+            for (uint32_t v = 0; v < n_warps; v++) if (used[v] < NG && (w == n_warps || load[v] < load[w])) w = v;
+            if (w == n_warps) return;                                    // cannot happen: NG * GP >= Gs
+            const uint32_t k = used[w]++;
+            load[w] += cost(order[c * 32u]);
+            for (uint32_t l = 0; l < 32u && c * 32u + l < Gs; l++) perm[(size_t)sb * slots + (size_t)k * GP + w * 32u + l] = order[c * 32u + l];
+        }
+        uint32_t max_perm = 0, max_id = 0;
+        for (uint32_t w = 0; w < n_warps; w++) {
+            max_perm = std::max(max_perm, load[w]);
+            uint32_t id = 0;
+            for (uint32_t k = 0; k < NG; k++) {
+                uint32_t m = 0;
+                for (uint32_t l = 0; l < 32u; l++) { const uint64_t g = (uint64_t)k * GP + w * 32u + l; if (g < Gs) m = std::max(m, cost(g_lo + (uint32_t)g)); }
+                id += m;
+            }
+            max_id = std::max(max_id, id);
+        }
+        sum_perm += max_perm; sum_id += max_id;
     }
     // worth it only when it shortens the longest warp by 15 % or more against mask order (molecular Hamiltonians: H8 4.21 ->
     // 4.61 TB/s); with uniform groups it only perturbs the lane <-> slot pattern of the stores (XXZ n = 27: 6.06 -> 5.47)
-    uint32_t max_perm = 0, max_id = 0;
-    for (uint32_t w = 0; w < n_warps; w++) {
-        max_perm = std::max(max_perm, load[w]);
-        uint32_t id = 0;
-        for (uint32_t k = 0; k < NG; k++) {
-            uint32_t m = 0;
-            for (uint32_t l = 0; l < 32u; l++) { const uint64_t g = (uint64_t)k * GP + w * 32u + l; if (g < G) m = std::max(m, cost((uint32_t)g)); }
-            id += m;
-        }
-        max_id = std::max(max_id, id);
-    }
-    if (!(env && env[0] == '1') && 100u * max_perm > 85u * max_id) return;
+    if (!(env && env[0] == '1') && 100u * sum_perm > 85u * sum_id) return;
     if (cudaMalloc(reinterpret_cast<void **>(&pl->rows_perm), perm.size() * 4) != cudaSuccess) { cudaGetLastError(); pl->rows_perm = nullptr; return; }
     if (cudaMemcpy(pl->rows_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaGetLastError(); cudaFree(pl->rows_perm); pl->rows_perm = nullptr; return;
     }
-    pl->rows_split.perm = pl->rows_perm; pl->rows_split.perm_n = (uint32_t)perm.size();
+    pl->rows_split.perm = pl->rows_perm; pl->rows_split.perm_n = slots;
+}
+
+// tables of the external-heavy path: heavy groups longest first, group -> heavy index
+bool setup_ext_heavy(qr_plan *pl, const std::vector<uint32_t> &goff, uint32_t thr)
+{
+    const uint32_t G = (uint32_t)pl->n_groups;
+    std::vector<uint32_t> hg, hidx(G, 0xffffffffu);
+    for (uint32_t g = 0; g < G; g++) if (goff[g + 1] - goff[g] > thr) hg.push_back(g);
+    std::stable_sort(hg.begin(), hg.end(), [&](uint32_t a, uint32_t b) { return goff[a + 1] - goff[a] > goff[b + 1] - goff[b]; });
+    for (uint32_t h = 0; h < hg.size(); h++) hidx[hg[h]] = h;
+    if (pl->ext_heavy_g) { cudaFree(pl->ext_heavy_g); pl->ext_heavy_g = nullptr; }
+    if (pl->ext_hidx) { cudaFree(pl->ext_hidx); pl->ext_hidx = nullptr; }
+    if (hg.empty()) return false;
+    bool ok = cudaMalloc(reinterpret_cast<void **>(&pl->ext_heavy_g), hg.size() * 4) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void **>(&pl->ext_hidx), (size_t)G * 4) == cudaSuccess &&
+              cudaMemcpy(pl->ext_heavy_g, hg.data(), hg.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(pl->ext_hidx, hidx.data(), (size_t)G * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); return false; }
+    pl->ext_nh = (uint32_t)hg.size();
+    pl->rows_ext_heavy = true;
+    return true;
 }
 
 bool choose_rows_shape(qr_plan *pl);
@@ -331,7 +369,7 @@ bool choose_rows(qr_plan *pl)
 }
 bool choose_rows_inner(qr_plan *pl)
 {
-    pl->rows_cnt_smem = 0; pl->rows_cl = 1; pl->rows_gc = 0; pl->rows_split = qr::RowsSplit{};
+    pl->rows_cnt_smem = 0; pl->rows_cl = 1; pl->rows_gc = 0; pl->rows_split = qr::RowsSplit{}; pl->rows_ext_heavy = false;
     if (!choose_rows_shape(pl)) return false;
     const size_t cnt_bytes = (size_t)pl->n_groups * pl->n_qubits * 4;
     const char *env = getenv("QR_FILL_ROWS_CNT");
@@ -411,6 +449,7 @@ bool choose_rows_shape(qr_plan *pl)
         if (v >= 32 && v <= 1024) split_s = (uint32_t)v;
     }
     if (const char *env = getenv("QR_FILL_ROWS_CL")) if (atoi(env) > 1) want_split = 0;
+    bool ext_heavy = false;
     if (want_split) {
         qr::partition_kernel<<<1, qr::K1_THREADS>>>(pl->dev, split_s);
         uint32_t meta[8] = {0};
@@ -437,17 +476,20 @@ bool choose_rows_shape(qr_plan *pl)
             }
             // Where it pays (profiles/r03_rows_sweep.jsonl): balanced tries of light groups -- random operators with
             // G = 1500..4000: 4.1-5.3 TB/s against 1.9-4.8 with the lanes kernel.  Molecular Hamiltonians keep their long
-            // groups in the subtree around mask 0 and have small side subtrees: a third of the CTAs then folds all the
-            // heavy terms of every row and 100-group subtrees make 10 KB batches (H10 1.9-2.2 TB/s against 2.5 lanes;
-            // H12 cut at 512: 1.4 against 4.9 whole) -- those stay where they were.
-            if (!getenv("QR_FILL_ROWS_SPLIT") && (gmin < 256 || hx_all * 100 > pl->n_terms_canonical * 20)) ok = false;
+            // groups in the subtree around mask 0: with the heavy groups folded inside the CTAs that own them a third of
+            // the CTAs folds all the heavy terms of every row (H10 1.9-2.2 TB/s against 2.5 lanes).  Their heavy groups
+            // are therefore folded by a kernel of their own, one chunk of rows ahead of the fill (heavy_values_kernel:
+            // EXTERNAL heavy values), and the split kernel reads them like any other value.  QR_FILL_ROWS_EXTHV=0: in-CTA.
+            const char *xenv = getenv("QR_FILL_ROWS_EXTHV");
+            ext_heavy = hx_all != 0 && !(xenv && xenv[0] == '0');
+            if (!getenv("QR_FILL_ROWS_SPLIT") && (gmin < 256 || (!ext_heavy && hx_all * 100 > pl->n_terms_canonical * 20))) ok = false;
         }
         if (ok) {
             uint64_t gmax = 0, nh_max = 0, hx_max = 0;
             for (uint32_t b = 0; b < nb; b++) {
                 uint64_t nh = 0, hx = 0;
                 for (uint64_t g = bs[b]; g < bs[b + 1]; g++)
-                    if (goff[g + 1] - goff[g] > thr0) { nh++; hx += goff[g + 1] - goff[g] - 1; }
+                    if (!ext_heavy && goff[g + 1] - goff[g] > thr0) { nh++; hx += goff[g + 1] - goff[g] - 1; }
                 gmax = std::max<uint64_t>(gmax, bs[b + 1] - bs[b]); nh_max = std::max(nh_max, nh); hx_max = std::max(hx_max, hx);
             }
             const uint64_t si = (gmax + 3) & ~1ull;                // pitch of a buffered row of column ids
@@ -463,7 +505,11 @@ bool choose_rows_shape(qr_plan *pl)
                 // n_sm in all
                 std::vector<uint64_t> w(nb);
                 uint64_t w_all = 0;
-                for (uint32_t b = 0; b < nb; b++) { w[b] = (uint64_t)(goff[bs[b + 1]] - goff[bs[b]]) + (bs[b + 1] - bs[b]); w_all += w[b]; }
+                for (uint32_t b = 0; b < nb; b++) {
+                    w[b] = bs[b + 1] - bs[b];
+                    for (uint64_t g = bs[b]; g < bs[b + 1]; g++) { const uint32_t t = goff[g + 1] - goff[g]; w[b] += (ext_heavy && t > thr0) ? 1u : t; }
+                    w_all += w[b];
+                }
                 uint32_t given = 0;
                 std::vector<uint32_t> cnt(nb);
                 for (uint32_t b = 0; b < nb; b++) { cnt[b] = std::max<uint32_t>(1, (uint32_t)(w[b] * n_sm / w_all)); given += cnt[b]; }
@@ -479,6 +525,7 @@ bool choose_rows_shape(qr_plan *pl)
                 pl->rows_th = 512; pl->rows_ng = (int)((gmax + 511) / 512); pl->rows_q = q; pl->rows_sl = 0; pl->rows_log2r = r ? std::max(r, q) : 0;
                 pl->rows_hv_thr = thr0; pl->rows_hv_cap = (uint32_t)nh_max; pl->rows_hv_log2 = hl; pl->rows_regt = 1;
                 pl->rows_smem_bytes = smem_d(hl); pl->rows_table_terms = hx_max; pl->rows_cl = 0; pl->rows_gc = (uint32_t)gmax;
+                if (ext_heavy && !setup_ext_heavy(pl, goff, thr0)) return false;
                 return true;
             }
         }
@@ -747,6 +794,9 @@ extern "C" int qr_plan_destroy(qr_plan *pl)
     if (pl->dot_partials) cudaFree(pl->dot_partials);
     if (pl->fold_slab) cudaFree(pl->fold_slab);
     if (pl->rows_perm) cudaFree(pl->rows_perm);
+    if (pl->ext_heavy_g) cudaFree(pl->ext_heavy_g);
+    if (pl->ext_hidx) cudaFree(pl->ext_hidx);
+    if (pl->ext_hv) cudaFree(pl->ext_hv);
     for (auto &kv : pl->ptiles) if (kv.second.slab) cudaFree(kv.second.slab);
     if (pl->slab) cudaFree(pl->slab);
     delete pl;
@@ -847,7 +897,7 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
         const uint64_t s0 = align_up(row_lo, R), s1 = row_hi / R * R;
         // the bulk copies need 16-byte aligned global addresses: indices + (s0 - row_lo) * G * 8
         const bool aligned = pl->rows_cl == 0 || (((s0 - row_lo) * G) & 1) == 0;    // split mode handles odd segment starts itself
-        if (s1 > s0 && aligned && (s1 - s0) / R <= 0xffffffffull) {
+        if (s1 > s0 && aligned && (s1 - s0) / R <= 0xffffffffull && (!pl->rows_ext_heavy || R % 32 == 0)) {
             const uint64_t n_runs = (s1 - s0) / R, n_extra = pl->rows_table_terms;
             const size_t smem = pl->rows_smem_bytes;
             using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
@@ -876,12 +926,31 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
 #undef QR_ROWS_CL
             // split mode: a CTA per trie subtree of <= 1024 groups
 #define QR_ROWS_SPLIT(NG_, HV_) \
-            if (pl->rows_cl == 0 && pl->rows_ng == NG_ && (pl->rows_hv_cap != 0) == HV_) \
+            if (pl->rows_cl == 0 && pl->rows_ng == NG_ && (pl->rows_hv_cap != 0 || pl->rows_ext_heavy) == HV_) \
                 kern = q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, 512, true, HV_, false, 0> : (RowsFn)qr::fill_rows_kernel<NG_, 1, 512, true, HV_, false, 0>;
             QR_ROWS_SPLIT(1, false) QR_ROWS_SPLIT(1, true) QR_ROWS_SPLIT(2, false) QR_ROWS_SPLIT(2, true)
 #undef QR_ROWS_SPLIT
 #undef QR_ROWS_Q
 #undef QR_ROWS_CASE
+            // decoupled warps (fill.cuh, DEC): whole rows (NG = 1, 2) and split mode, Q = 1, 2
+            {
+                const char *denv = getenv("QR_FILL_ROWS_DEC");
+                // measured (profiles/r06_summary.md): split mode H10 2.49 -> 3.06 TB/s, H11 2.37 -> 2.89, random G = 3000 4.96 -> 5.4;
+                // whole rows H8 4.52 -> 4.37, H12 5.17 -> 5.05 (their limit is the slowest warp's chain, not the barrier): split only
+                const bool want = denv ? denv[0] != '0' : pl->rows_cl == 0;
+                pl->rows_split.dec_block = denv && denv[0] == '2';
+                const bool hv = pl->rows_hv_cap != 0 || pl->rows_ext_heavy;
+                if (want && q >= 1 && q <= 2 && pl->rows_th == 512 && pl->rows_regt && !pl->rows_cnt_smem && (pl->rows_cl == 0 || pl->rows_cl == 1) &&
+                    (pl->rows_ng == 1 || pl->rows_ng == 2)) {
+#define QR_ROWS_DEC(NG_, Q_, HV_, CL_) \
+                    if (pl->rows_ng == NG_ && q == Q_ && hv == HV_ && pl->rows_cl == CL_) kern = (RowsFn)qr::fill_rows_kernel<NG_, Q_, 512, true, HV_, false, CL_, true>;
+                    QR_ROWS_DEC(1, 1, false, 1) QR_ROWS_DEC(1, 1, true, 1) QR_ROWS_DEC(1, 2, false, 1) QR_ROWS_DEC(1, 2, true, 1)
+                    QR_ROWS_DEC(2, 1, false, 1) QR_ROWS_DEC(2, 1, true, 1) QR_ROWS_DEC(2, 2, false, 1) QR_ROWS_DEC(2, 2, true, 1)
+                    QR_ROWS_DEC(1, 1, false, 0) QR_ROWS_DEC(1, 1, true, 0) QR_ROWS_DEC(1, 2, false, 0) QR_ROWS_DEC(1, 2, true, 0)
+                    QR_ROWS_DEC(2, 1, false, 0) QR_ROWS_DEC(2, 1, true, 0) QR_ROWS_DEC(2, 2, false, 0) QR_ROWS_DEC(2, 2, true, 0)
+#undef QR_ROWS_DEC
+                }
+            }
             if (!kern) return fail(QR_ERR_UNSUPPORTED, "fill_rows: no kernel instance for this plan");
             QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const uint32_t cl = (uint32_t)pl->rows_cl, gc = cl != 1 ? pl->rows_gc : (uint32_t)G;
@@ -914,6 +983,34 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             cfg.gridDim = dim3((unsigned)ctas, 1, 1);
             int rc = launch_direct(pl, row_lo, s0, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
             if (rc != QR_OK) return rc;
+            if (pl->rows_ext_heavy) {
+                // chunks of rows: the heavy groups' values for the chunk (heavy_values_kernel), then the split fill reads them.
+                // 2^16 rows (or the window) per chunk: enough runs for every CTA of every subtree, nh MB of values
+                const uint64_t chunk = std::max<uint64_t>(R, std::min<uint64_t>(s1 - s0, 1ull << 16)) / R * R;
+                if (!pl->ext_hv || pl->ext_hv_rows < chunk) {
+                    if (pl->ext_hv) { QR_CUDA(cudaStreamSynchronize(st)); cudaFree(pl->ext_hv); pl->ext_hv = nullptr; pl->ext_hv_rows = 0; }
+                    QR_CUDA(cudaMalloc(reinterpret_cast<void **>(&pl->ext_hv), (size_t)pl->ext_nh * chunk * sizeof(double2)));
+                    pl->ext_hv_rows = chunk;
+                }
+                qr::RowsSplit sp = pl->rows_split;
+                sp.ext_hv = pl->ext_hv; sp.ext_hidx = pl->ext_hidx;
+                for (uint64_t c0 = s0; c0 < s1; c0 += chunk) {
+                    const uint64_t len = std::min(chunk, s1 - c0);
+                    const bool e4 = len % 128 == 0;
+                    const uint64_t items = (uint64_t)pl->ext_nh * (len / (e4 ? 128 : 32));
+                    const uint64_t hctas = (items + 7) / 8;
+                    if (hctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "fill_rows: heavy-value chunk too large");
+                    if (e4) qr::heavy_values_kernel<4><<<(unsigned)hctas, 256, 0, st>>>(pl->dev, pl->ext_heavy_g, pl->ext_nh, c0, (uint32_t)len, pl->ext_hv);
+                    else qr::heavy_values_kernel<1><<<(unsigned)hctas, 256, 0, st>>>(pl->dev, pl->ext_heavy_g, pl->ext_nh, c0, (uint32_t)len, pl->ext_hv);
+                    QR_LAUNCH_CHECK("heavy_values_kernel");
+                    sp.ext_rows = (uint32_t)len; sp.ext_row0 = (uint32_t)c0;
+                    QR_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->dev, (uint32_t)G, gc, (uint32_t)n_extra, (uint32_t)k, (uint32_t)pl->rows_sl, (uint32_t)(len / R),
+                                               pl->rows_hv_thr, pl->rows_hv_cap, (uint32_t)pl->rows_hv_log2, c0, row_lo, indptr_base, d_indptr,
+                                               d_indices, d_data, row_hi - row_lo, sp));
+                    QR_LAUNCH_CHECK("fill_rows_kernel");
+                }
+                return launch_direct(pl, s1, row_hi, row_lo, row_hi, indptr_base, d_indptr, d_indices, d_data, st);
+            }
             QR_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->dev, (uint32_t)G, gc, (uint32_t)n_extra, (uint32_t)k, (uint32_t)pl->rows_sl, (uint32_t)n_runs,
                                        pl->rows_hv_thr, pl->rows_hv_cap, (uint32_t)pl->rows_hv_log2, s0, row_lo, indptr_base, d_indptr,
                                        d_indices, d_data, row_hi - row_lo, pl->rows_split));

@@ -317,6 +317,34 @@ def test_rows_kernel(fixtures, monkeypatch, name, REGT, Q, R, SL, HV):
             assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
 
 
+@pytest.mark.parametrize("dec", ["1", "2"])
+@pytest.mark.parametrize("Q,R,HV", [(1, 1, None), (2, 5, None), (1, 4, "2"), (2, 7, "2"), (2, 3, "0"), (1, 6, None)])
+@pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
+def test_rows_kernel_decoupled_whole_rows(fixtures, monkeypatch, name, Q, R, HV, dec):
+    """The decoupled hand-over (DEC, see test_rows_kernel_split) forced on the whole-row register variant, where the default
+    keeps the batch barrier: in-CTA heavy phase between two named barriers, first-arriver hand-over of whole batches."""
+    monkeypatch.setenv("QR_FILL_ROWS", "1")
+    monkeypatch.setenv("QR_FILL_ROWS_DEC", dec)
+    monkeypatch.setenv("QR_FILL_ROWS_REGT", "1")
+    monkeypatch.setenv("QR_FILL_ROWS_SL", "0")
+    monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
+    monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
+    if HV is not None:
+        monkeypatch.setenv("QR_FILL_ROWS_HV", HV)
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, n)
+    plan = make_op(labels, coeffs).plan()
+    assert plan.fill_kernel == "fill_rows_kernel"
+    G, dim = plan.n_groups, 1 << n
+    assert_same(device_build(plan, 0, dim), ref, f"{name} Q={Q} R={R} HV={HV} dec={dec}")
+    if dim >= 128:
+        for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 33)]:
+            ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
+            assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G])), (lo, hi)
+            assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
+
+
 @pytest.mark.parametrize("G,T,REGT,Q", [(1100, 1500, 0, 1), (1100, 1500, 0, 2), (2200, 2600, 0, 1), (600, 2400, 0, 2), (600, 2400, 1, 2),
                                         (1000, 3000, 1, 1), (1000, 3000, 0, 1), (450, 500, None, 0), (700, 3000, None, 0), (400, 900, 1, 3),
                                         (200, 300, None, 0), (160, 700, None, 0), (100, 250, 1, 3), (60, 200, 1, 2)])
@@ -368,13 +396,19 @@ def test_rows_kernel_clusters(fixtures, monkeypatch, name, R, CL):
             assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
 
 
+@pytest.mark.parametrize("exthv,dec", [("1", "1"), ("0", "1"), ("1", "0"), ("0", "0"), ("1", "2"), ("0", "2")])
 @pytest.mark.parametrize("S", [32, 64, 1024])
 @pytest.mark.parametrize("R", [1, 2, 7])
 @pytest.mark.parametrize("name", ["random_n10", "H6", "tfim_3x3", "H2", "H4", "C1", "xxz_n10"])
-def test_rows_kernel_split(fixtures, monkeypatch, name, R, S):
+def test_rows_kernel_split(fixtures, monkeypatch, name, R, S, exthv, dec):
     """Split mode of the rows kernel forced on small cases: the sorted masks are cut into trie subtrees of <= S groups, a
-    CTA owns one subtree and writes its segment of every row (odd segment starts: shifted id buffer + edge stores)."""
+    CTA owns one subtree and writes its segment of every row (odd segment starts: shifted id buffer + edge stores).
+    exthv = 1: the heavy groups' values come from heavy_values_kernel (the default), 0: folded inside the owning CTA.
+    dec = 1: decoupled warps (the batch buffers handed over through mbarriers, the first warp to arrive gives the batch to the
+    TMA; the split-mode default), 2: the same with the hand-over waiting for the TMA's read at once, 0: one CTA barrier per batch."""
     monkeypatch.setenv("QR_FILL_ROWS", "1")
+    monkeypatch.setenv("QR_FILL_ROWS_EXTHV", exthv)
+    monkeypatch.setenv("QR_FILL_ROWS_DEC", dec)
     monkeypatch.setenv("QR_FILL_ROWS_SPLIT", str(S))
     monkeypatch.setenv("QR_FILL_ROWS_R", str(R))
     labels, coeffs = SMALL[name](fixtures)
@@ -405,6 +439,25 @@ def test_rows_kernel_split_large_G(G, T, n):
     ip, ix, dt = device_build(plan, lo, hi)
     assert np.array_equal(ix, ref[1][lo * G:hi * G]) and np.array_equal(u64(dt), u64(ref[2][lo * G:hi * G]))
     assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
+
+
+@pytest.mark.parametrize("name,lo_hi", [("H10", [(1 << 19, (1 << 19) + 1024), ((1 << 19) + 77, (1 << 19) + 1500)]),
+                                        ("H11", [(3 << 20, (3 << 20) + 512)])])
+def test_split_external_heavy_on_molecular_operators(fixtures, name, lo_hi):
+    """H10 / H11 (20 / 22 qubits, G = 2 536 / 3 792, the reference's perf_giant.py operators): split mode with the heavy
+    groups (91 / 111 of them, up to 254 terms) folded by heavy_values_kernel -- row windows against the oracle, bit for bit."""
+    if name not in fixtures:
+        pytest.skip("fixture not in the golden file")
+    labels, coeffs = fixtures[name]
+    n, params = O.make_params(labels, coeffs)
+    plan = make_op(labels, coeffs).plan()
+    assert plan.fill_kernel == "fill_rows_kernel"
+    G = plan.n_groups
+    for lo, hi in lo_hi:
+        ref = O.build_csr(params, n, lo, hi)
+        ip, ix, dt = device_build(plan, lo, hi)
+        assert np.array_equal(ix, ref[1]) and np.array_equal(u64(dt), u64(ref[2])), (lo, hi)
+        assert np.array_equal(ip, np.arange(hi - lo + 1, dtype=np.uint64) * G)
 
 
 def test_rows_kernel_selection(fixtures, monkeypatch):

@@ -5,13 +5,13 @@
 # (files under qrusty_b200/lib/ travel to the GPU box with gpurun and stay out of git).
 OTHER=${1:-/root/repo/qrusty_b200/lib/libqrusty_cuda_prev.so}
 mkdir -p gpurun_out
-S=gpurun_out/ab_sweep.jsonl; : > $S
+S=gpurun_out/${TAG:-ab}_sweep.jsonl; : > $S
 for rep in 1 2; do
 for lib in "" "$OTHER"; do
   export QRUSTY_CUDA_LIB=$lib; [ -z "$lib" ] && unset QRUSTY_CUDA_LIB
-  for w in "H8" "H12 --rows 18" "C3 --rows 18 --max-gb 10" "rand:22:96:64 --rows 20"; do
-    timeout 200 python tools/fill_sweep.py $w --reps 20 --cfgs "auto" | sed "s|\"cfg\": \"auto\"|\"cfg\": \"auto lib=${lib##*/}\"|" >> $S 2>/dev/null
+  for w in "H8" "H12 --rows 18" "H10 --rows 17" "H11 --rows 16" "C3 --rows 18 --max-gb 10" "rand:22:96:64 --rows 20" "rand:24:6000:3000 --rows 16" "rand:20:1200:600 --rows 17"; do
+    timeout 200 python tools/fill_sweep.py $w --reps 20 --cfgs "auto" 2>/dev/null | sed "s|\"cfg\": \"auto\"|\"cfg\": \"auto lib=${lib##*/}\"|" >> $S
   done
 done
 done
-cat $S | cut -c1-60,100-260
+cat $S | cut -c1-75,100-260
