@@ -423,18 +423,40 @@ bool choose_rows_shape(qr_plan *pl)
         int sl_hi = 0;
         while (sl_hi < 4 && (512u >> (sl_hi + 1)) >= G) sl_hi++;
         if (const char *env = getenv("QR_FILL_ROWS_SL")) { int v = atoi(env); if (v >= 0 && v <= sl_hi) sl_hi = v; }
-        for (int sl = sl_hi; sl >= 0; sl--)
+        // EXTERNAL heavy values (heavy_values_kernel, as in split mode): no heavy tables and no side buffer in shared memory,
+        // so a batch can hold more rows -- H8 (G = 981, 57 heavy groups with 1 817 terms): 4-row batches instead of 2-row ones.
+        // Default: when that is what it buys; QR_FILL_ROWS_EXTHV = 1 / 0: whenever there is a heavy group / never.
+        const char *xenv = getenv("QR_FILL_ROWS_EXTHV");
+        int in_q = -1, in_sl = -1, in_hl = 5;
+        for (int sl = sl_hi; sl >= 0 && in_q < 0; sl--)
             for (int q = q_forced ? q_forced : q_hi; q >= (q_forced ? q_forced : 1); q--) {
                 const int qb = q + sl;
                 if (rows_smem(G, hx, qb, nh) > ROWS_SMEM_CAP) continue;
                 int hl = std::max(strip_log2(hx, qb, nh), qb);             // a heavy strip holds whole batches
                 if (hl > 7 || rows_smem(G, hx, qb, nh, hl) > ROWS_SMEM_CAP) continue;
-                pl->rows_th = 512; pl->rows_ng = (int)((G + 511) / 512); pl->rows_q = q; pl->rows_sl = sl;
-                pl->rows_log2r = r ? std::max(r, qb) : 0;
-                pl->rows_hv_thr = thr0; pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = hl; pl->rows_regt = 1;
-                pl->rows_smem_bytes = rows_smem(G, hx, qb, nh, hl); pl->rows_table_terms = hx;
-                return true;
+                in_q = q; in_sl = sl; in_hl = hl;
+                break;
             }
+        int ex_q = -1, ex_sl = -1;
+        if (nh != 0 && !(xenv && xenv[0] == '0'))
+            for (int sl = sl_hi; sl >= 0 && ex_q < 0; sl--)
+                for (int q = q_forced ? q_forced : q_hi; q >= (q_forced ? q_forced : 1); q--)
+                    if (rows_smem(G, 0, q + sl) <= ROWS_SMEM_CAP) { ex_q = q; ex_sl = sl; break; }
+        const bool use_ext = ex_q >= 0 && ((xenv && xenv[0] == '1') || in_q < 0 || ex_q + ex_sl > in_q + in_sl);
+        if (use_ext || in_q >= 0) {
+            const int q = use_ext ? ex_q : in_q, sl = use_ext ? ex_sl : in_sl, qb = q + sl;
+            pl->rows_th = 512; pl->rows_ng = (int)((G + 511) / 512); pl->rows_q = q; pl->rows_sl = sl;
+            pl->rows_log2r = r ? std::max(r, qb) : 0;
+            pl->rows_hv_thr = thr0; pl->rows_regt = 1;
+            if (use_ext) {
+                pl->rows_hv_cap = 0; pl->rows_hv_log2 = std::max(5, qb); pl->rows_smem_bytes = rows_smem(G, 0, qb); pl->rows_table_terms = 0;
+                if (!setup_ext_heavy(pl, goff, thr0)) return false;
+            } else {
+                pl->rows_hv_cap = (uint32_t)nh; pl->rows_hv_log2 = in_hl;
+                pl->rows_smem_bytes = rows_smem(G, hx, qb, nh, in_hl); pl->rows_table_terms = hx;
+            }
+            return true;
+        }
     }
 
     // (d) SPLIT: rows of any length.  K1b cuts the sorted masks into trie subtrees of <= 1024 groups; a CTA owns one subtree
@@ -903,16 +925,17 @@ int build_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint64_t *d_indptr
             using RowsFn = void (*)(qr::PlanDev, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
                                     uint64_t, uint64_t, uint64_t, uint64_t *, uint64_t *, double2 *, uint64_t, const qr::RowsSplit);
             RowsFn kern = nullptr;
+            const bool hv_any = pl->rows_hv_cap != 0 || pl->rows_ext_heavy;    // HEAVY instances: in-CTA heavy phase or external values
 #define QR_ROWS_Q(NG_, TH_, RG_, HV_) \
             (q == 2 ? (RowsFn)qr::fill_rows_kernel<NG_, 2, TH_, RG_, HV_, false, 1> : (RowsFn)qr::fill_rows_kernel<NG_, 1, TH_, RG_, HV_, false, 1>)
 #define QR_ROWS_CASE(NG_, TH_, RG_) \
             if (q <= 2 && pl->rows_cl == 1 && !pl->rows_cnt_smem && pl->rows_ng == NG_ && pl->rows_th == TH_ && pl->rows_regt == (RG_ ? 1 : 0)) \
-                kern = pl->rows_hv_cap ? QR_ROWS_Q(NG_, TH_, RG_, true) : QR_ROWS_Q(NG_, TH_, RG_, false);
+                kern = hv_any ? QR_ROWS_Q(NG_, TH_, RG_, true) : QR_ROWS_Q(NG_, TH_, RG_, false);
             QR_ROWS_CASE(1, 1024, false) QR_ROWS_CASE(2, 1024, false) QR_ROWS_CASE(3, 1024, false)
             QR_ROWS_CASE(1, 512, true) QR_ROWS_CASE(2, 512, true)
             // one group per thread, terms in registers: 8-row batches and the rank table in shared memory exist here only
 #define QR_ROWS_ONE(Q_, HV_, CS_) \
-            if (pl->rows_cl == 1 && pl->rows_ng == 1 && pl->rows_regt && q == Q_ && (pl->rows_hv_cap != 0) == HV_ && (pl->rows_cnt_smem != 0) == CS_) \
+            if (pl->rows_cl == 1 && pl->rows_ng == 1 && pl->rows_regt && q == Q_ && hv_any == HV_ && (pl->rows_cnt_smem != 0) == CS_) \
                 kern = (RowsFn)qr::fill_rows_kernel<1, Q_, 512, true, HV_, CS_, 1>;
             QR_ROWS_ONE(3, false, false) QR_ROWS_ONE(3, true, false)
             QR_ROWS_ONE(1, false, true) QR_ROWS_ONE(1, true, true) QR_ROWS_ONE(2, false, true) QR_ROWS_ONE(2, true, true)

@@ -317,14 +317,17 @@ def test_rows_kernel(fixtures, monkeypatch, name, REGT, Q, R, SL, HV):
             assert np.array_equal(ip, np.arange(lo, hi + 1, dtype=np.uint64) * G)
 
 
-@pytest.mark.parametrize("dec", ["1", "2"])
+@pytest.mark.parametrize("dec,exthv", [("1", "0"), ("2", "0"), ("0", "1"), ("1", "1")])
 @pytest.mark.parametrize("Q,R,HV", [(1, 1, None), (2, 5, None), (1, 4, "2"), (2, 7, "2"), (2, 3, "0"), (1, 6, None)])
 @pytest.mark.parametrize("name", ["H4", "H6", "random_n10", "xxz_n10", "C1", "H2", "tfim_3x3"])
-def test_rows_kernel_decoupled_whole_rows(fixtures, monkeypatch, name, Q, R, HV, dec):
-    """The decoupled hand-over (DEC, see test_rows_kernel_split) forced on the whole-row register variant, where the default
-    keeps the batch barrier: in-CTA heavy phase between two named barriers, first-arriver hand-over of whole batches."""
+def test_rows_kernel_decoupled_whole_rows(fixtures, monkeypatch, name, Q, R, HV, dec, exthv):
+    """Two options of the whole-row register variant forced on small cases.  dec: the decoupled hand-over (DEC, see
+    test_rows_kernel_split) where the default keeps the batch barrier -- in-CTA heavy phase between two named barriers,
+    first-arriver hand-over of whole batches.  exthv = 1: the heavy groups' values come from heavy_values_kernel instead of the
+    CTA's own heavy phase (the default when that lets a batch hold more rows: H8)."""
     monkeypatch.setenv("QR_FILL_ROWS", "1")
     monkeypatch.setenv("QR_FILL_ROWS_DEC", dec)
+    monkeypatch.setenv("QR_FILL_ROWS_EXTHV", exthv)
     monkeypatch.setenv("QR_FILL_ROWS_REGT", "1")
     monkeypatch.setenv("QR_FILL_ROWS_SL", "0")
     monkeypatch.setenv("QR_FILL_ROWS_Q", str(Q))
@@ -337,7 +340,7 @@ def test_rows_kernel_decoupled_whole_rows(fixtures, monkeypatch, name, Q, R, HV,
     plan = make_op(labels, coeffs).plan()
     assert plan.fill_kernel == "fill_rows_kernel"
     G, dim = plan.n_groups, 1 << n
-    assert_same(device_build(plan, 0, dim), ref, f"{name} Q={Q} R={R} HV={HV} dec={dec}")
+    assert_same(device_build(plan, 0, dim), ref, f"{name} Q={Q} R={R} HV={HV} dec={dec} exthv={exthv}")
     if dim >= 128:
         for lo, hi in [(5, dim - 3), (32, 64), (dim // 2 - 1, dim // 2 + 33)]:
             ip, ix, dt = device_build(plan, lo, hi, flags=_ffi.QR_INDPTR_GLOBAL)
