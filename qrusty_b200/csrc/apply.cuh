@@ -52,6 +52,10 @@ __device__ __forceinline__ void wait_flag(const uint64_t *flag, uint64_t epoch)
 struct ApplyPeerArgs {
     const double2 *peer[APPLY_MAX_PEERS];     // v shard of rank q, pre-offset so that it is indexed by the GLOBAL row id
     uint32_t n_peers, shard_bits;
+    // CTA order (local apply on a power-of-two number of row blocks): launch index t -> row block
+    // ((t & (2^swz_f - 1)) << (swz_nb - swz_f)) | (t >> swz_f): the TOP swz_f bits of the row-block index vary fastest in
+    // time, so the CTAs that are resident together are each other's partners along the top row bits (which otherwise miss L2)
+    uint32_t swz_f, swz_nb;
 };
 
 // One CTA before the fused apply: tell every peer that this rank's shard is complete (stream order: whatever produced it
@@ -139,7 +143,8 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
     __shared__ GroupDesc sd[APPLY_BATCH];
     __shared__ const double2 *sv[APPLY_BATCH];
     const bool PEERS = pa.n_peers > 1u;
-    const uint64_t cta_base = row_lo + (uint64_t)blockIdx.x * (APPLY_THREADS * E);
+    const uint32_t blk = pa.swz_f ? ((blockIdx.x & ((1u << pa.swz_f) - 1u)) << (pa.swz_nb - pa.swz_f)) | (blockIdx.x >> pa.swz_f) : blockIdx.x;
+    const uint64_t cta_base = row_lo + (uint64_t)blk * (APPLY_THREADS * E);
     const uint32_t my_rank = PEERS ? (uint32_t)(row_lo >> pa.shard_bits) : 0u;
     const double2 *v_own = PEERS ? pa.peer[my_rank] : v;
     uint32_t r[E];
@@ -201,7 +206,7 @@ apply_direct_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi,
 #pragma unroll
         for (int e = 0; e < E; e++)
             if (live[e]) cdot_acc(dr, di, ld_nc_double2(&v_own[r[e]]), yr[e], yi[e]);
-        block_dot_store(dr, di, &dotp[blockIdx.x]);
+        block_dot_store(dr, di, &dotp[blk]);
     }
 }
 

@@ -2146,7 +2146,13 @@ static int apply_rows(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, const doubl
         return dot_out ? dot_fold(pl, fctas, dot_out, st) : QR_OK;
     }
     if (dot_out) { rc = dot_partials(pl, ctas, st); if (rc != QR_OK) return rc; }
-    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re, qr::ApplyPeerArgs{},
+    qr::ApplyPeerArgs pa_local{};
+    if (const char *env = getenv("QR_APPLY_SWZ")) {
+        const int f = atoi(env);
+        const uint32_t nb = (ctas & (ctas - 1)) == 0 ? (uint32_t)(63 - __builtin_clzll(ctas)) : 0u;
+        if (f > 0 && nb >= (uint32_t)f + 5u) { pa_local.swz_f = (uint32_t)f; pa_local.swz_nb = nb; }
+    }
+    qr::apply_direct_kernel<<<(unsigned)ctas, qr::APPLY_THREADS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, v, y, diag, diag_re, pa_local,
                                                                           nullptr, 0u, dot_out ? pl->dot_partials : nullptr);
     QR_LAUNCH_CHECK("apply_direct_kernel");
     return dot_out ? dot_fold(pl, ctas, dot_out, st) : QR_OK;
