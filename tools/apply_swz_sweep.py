@@ -13,7 +13,7 @@ from qrusty_b200._runtime import DeviceBuffer
 from fill_sweep import get_workload
 
 ap = argparse.ArgumentParser(); ap.add_argument("workload"); ap.add_argument("--reps", type=int, default=20)
-ap.add_argument("--fs", default="0 2 3 4 5 6 7 8")
+ap.add_argument("--fs", default="0 2 3 4 5 6 7 8"); ap.add_argument("--var", default="QR_APPLY_SWZ")
 a = ap.parse_args()
 labels, coeffs = get_workload(a.workload)
 op = Q.SparsePauliOp([Q.Pauli(l) for l in labels], coeffs)
@@ -26,7 +26,7 @@ st = C.c_void_p(); call("qr_stream_create", C.byref(st))
 e0, e1 = C.c_void_p(), C.c_void_p(); call("qr_event_create", C.byref(e0)); call("qr_event_create", C.byref(e1))
 ref = None
 for f in a.fs.split():
-    os.environ["QR_APPLY_SWZ"] = f
+    os.environ[a.var] = f
     for _ in range(3):
         call("qr_apply_device", plan.handle, 0, dim, dv.ptr, dy.ptr, st)
     call("qr_event_record", e0, st)
@@ -37,5 +37,5 @@ for f in a.fs.split():
     head = np.empty(1 << 16, dtype=np.complex128)
     call("qr_memcpy_d2h", head.ctypes.data, dy.ptr + (dim // 2) * 16, head.nbytes, None)
     if ref is None: ref = head.copy()
-    print(json.dumps({"workload": a.workload, "swz_f": int(f), "kernel": plan.apply_kernel(), "n": plan.n_qubits, "G": G,
+    print(json.dumps({"workload": a.workload, a.var: int(f), "kernel": plan.apply_kernel(), "n": plan.n_qubits, "G": G,
                       "ms": round(t, 4), "GBps_compulsory": round(32 * dim / t / 1e6, 1), "same_bits": bool(np.array_equal(head.view(np.uint64), ref.view(np.uint64)))}), flush=True)
