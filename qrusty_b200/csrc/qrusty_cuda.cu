@@ -1306,7 +1306,9 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
     uint32_t wcol = wide ? 8u : G <= 256 ? 1u : G <= 65536 ? 2u : 4u;            // bytes per column on the wire
     if (const char *env = getenv("QR_HOST_WIRE_COL")) { const int v = atoi(env); if (!wide && (v == 2 || v == 4) && (uint32_t)v > wcol) wcol = (uint32_t)v; }   // tests
     const uint64_t per_row = G * (16 + wcol);
-    uint64_t win_rows = (64ull << 20) / per_row;
+    uint64_t win_mb = 64;
+    if (const char *env = getenv("QR_HOST_WIN_MB")) { const int v = atoi(env); if (v >= 1 && v <= 1024) win_mb = (uint64_t)v; }
+    uint64_t win_rows = (win_mb << 20) / per_row;
     if (win_rows >= rows) win_rows = rows;
     else { win_rows = win_rows / 256 * 256; if (win_rows == 0) win_rows = 32; }
     const size_t dat_bytes = align_up(win_rows * G * 16, 256), idx_bytes = align_up(win_rows * G * 8, 256);
@@ -1343,11 +1345,16 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
     }
     const uint32_t *gx = pl->host_gx.data();
     HostPool &pool = host_pool();
-    const uint64_t n_win = (rows + win_rows - 1) / win_rows;
+    // window boundaries (cutting the last window into quarters so that less host work trails the final copy was measured:
+    // no difference on C2, the copies land 1.2-1.4 ms apart and the host needs 0.5-0.7 ms per window)
+    std::vector<uint64_t> wb;
+    for (uint64_t r = 0; r < rows; r += win_rows) wb.push_back(r);
+    wb.push_back(rows);
+    const uint64_t n_win = wb.size() - 1;
     uint64_t d2h = 0;
 
     auto submit = [&](uint64_t w) -> int {                          // fill window w, start its copies
-        const uint64_t w0 = row_lo + w * win_rows, w1 = std::min(row_hi, w0 + win_rows), n = w1 - w0, o = (w0 - row_lo) * G;
+        const uint64_t w0 = row_lo + wb[w], w1 = row_lo + wb[w + 1], n = w1 - w0, o = (w0 - row_lo) * G;
         const int k = (int)(w % WIN_RING);
         cudaStream_t st = ws.stream[0];
         char *buf = static_cast<char *>(ws.buf[k]), *h = static_cast<char *>(ws.host[k]);
@@ -1374,7 +1381,7 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
     };
     // host side of window w once its copies have landed: widen the columns / move staged pieces to their destination
     auto finish = [&](uint64_t w) {
-        const uint64_t w0 = row_lo + w * win_rows, n = std::min(row_hi, w0 + win_rows) - w0, o = (w0 - row_lo) * G;
+        const uint64_t w0 = row_lo + wb[w], n = wb[w + 1] - wb[w], o = (w0 - row_lo) * G;
         const char *h = static_cast<const char *>(ws.host[(int)(w % WIN_RING)]);
         const bool move_dat = !data_direct, move_idx = wide ? !idx_direct : true;
         if (!move_dat && !move_idx) return;
@@ -1418,6 +1425,14 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
         // windows w .. w + WIN_RING - 1 in flight: the buffers of every earlier window are free (finish() has returned)
         while (rc == QR_OK && submitted < n_win && submitted < w + WIN_RING) rc = submit(submitted++);
         if (rc != QR_OK) break;
+        if (w == 0 && indptr) {                                     // affine: never crosses the link; written while the first windows fly
+            const uint64_t base = (flags & QR_INDPTR_GLOBAL) ? row_lo * G : 0;
+            const uint64_t per = 1u << 16, n_tasks = (rows + 1 + per - 1) / per;
+            pool.run(n_tasks, [&](size_t t) {
+                const uint64_t i1 = std::min(rows + 1, (t + 1) * per);
+                for (uint64_t i = t * per; i < i1; i++) indptr[i] = base + i * G;
+            });
+        }
         const double t1 = now();
         QR_CUDA(cudaEventSynchronize(ws.done[(int)(w % WIN_RING)]));
         const double t2 = now();
@@ -1427,14 +1442,6 @@ extern "C" int qr_build_host(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, uint
     }
     cudaStreamSynchronize(ws.stream[0]);
     if (rc != QR_OK) return rc;
-    if (indptr) {                                                   // affine: never crosses the link
-        const uint64_t base = (flags & QR_INDPTR_GLOBAL) ? row_lo * G : 0;
-        const uint64_t per = 1u << 16, n_tasks = (rows + 1 + per - 1) / per;
-        pool.run(n_tasks, [&](size_t t) {
-            const uint64_t i1 = std::min(rows + 1, (t + 1) * per);
-            for (uint64_t i = t * per; i < i1; i++) indptr[i] = base + i * G;
-        });
-    }
     g_last_d2h_bytes = d2h;
     return QR_OK;
 }
