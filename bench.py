@@ -682,6 +682,25 @@ def run_b200(args, rank, local_rank, world):
                     del d_v, d_y
                 del mplan, mop
 
+        # (1b) the reference's own H.v: CSR SpMV (accel.rs:338-370) over the bench operator's built matrix, resident in HBM
+        #      (d_ip / d_ix / d_dt hold the last timed build); sampled rows against the oracle's sequential sums, bit for bit
+        if n <= 22:
+            sv_h = H.lanczos_start_vector(0, dim)
+            s_v, s_y = DeviceBuffer(dim * 16, device), DeviceBuffer(rows * 16, device)
+            s_v.upload(sv_h)
+            ms = timed(lambda: call("qr_spmv_device", rows, d_ip.ptr, d_ix.ptr, d_dt.ptr, s_v.ptr, s_y.ptr, stream), 20)
+            y_h = np.empty(rows, np.complex128); s_y.download(y_h)
+            _, prm = O.make_params(labels, coeffs)
+            r_lo = lo + rows // 2
+            ref = O.build_csr(prm, n, r_lo, r_lo + 2048)
+            same = bool(np.array_equal(y_h[r_lo - lo:r_lo - lo + 2048].view(np.uint64), O.spmv(*ref, sv_h).view(np.uint64)))
+            extras["spmv_csr"] = {"workload": name, "kernel": "spmv_csr_unrolled_kernel<4>", "ms": ms, "nnz_per_s": nnz_local / ms * 1e3,
+                                  "GBps_matrix": nnz_local * 24 / ms / 1e6, "frac_of_peak_matrix_bytes": nnz_local * 24 / ms / 1e6 / peak,
+                                  "rows_verified": 2048, "rows_equal_oracle_bitwise": same,
+                                  "note": "spmat_dot_densevec on the device-resident CSR, thread per row, reference summation order; "
+                                          "the matrix-free apply of the same operator is extras-independent (hv)"}
+            del s_v, s_y
+
         # (2) fused drop-zeros build of the bench operator: count_rows + scan + fill_compact
         kept = C.c_uint64()
         z_ip = DeviceBuffer((rows + 1) * 8, device)

@@ -375,6 +375,45 @@ spmv_csr_kernel(uint64_t n_rows, const uint64_t *__restrict__ indptr,
     y[row] = make_double2(re, im);
 }
 
+// Thread <-> row with U entries of the row in flight at a time (their loads are independent of the running sum; the
+// additions stay sequential in stored order, so the sums round exactly as the reference's loop).  U = 4 is the default:
+// C2 0.143 ms against 0.183 for the plain loop above, XXZ n = 24 1.33 / 1.70, H8 0.52 / 0.73, C3 1.32 / 1.45
+// (profiles/r06_spmv3.jsonl; 3.0-3.8 TB/s of matrix bytes, 5.0-6.3 TB/s counting the gathered v).  Measured and dropped:
+// tiles through shared memory (CTA- or warp-owned row blocks, lane <-> entry loads in memory order, then lane <-> row sums):
+// 0.24-0.39 ms on C2 -- sixteen warps per SM do not keep enough loads in flight; sixty-four independent row streams do.
+template <int U>
+__global__ void __launch_bounds__(256)
+spmv_csr_unrolled_kernel(uint64_t n_rows, const uint64_t *__restrict__ indptr,
+                         const uint64_t *__restrict__ indices, const double2 *__restrict__ data,
+                         const double2 *__restrict__ v, double2 *__restrict__ y)
+{
+    const uint64_t row = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t base = indptr[0], k1 = indptr[row + 1] - base;
+    uint64_t k = indptr[row] - base;
+    double re = 0.0, im = 0.0;
+    for (; k + U <= k1; k += U) {
+        double2 a[U], w[U];
+        uint64_t col[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { col[u] = __ldg(&indices[k + u]); a[u] = ld_nc_double2(&data[k + u]); }
+#pragma unroll
+        for (int u = 0; u < U; u++) w[u] = ld_nc_double2(&v[col[u]]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            re = __dadd_rn(re, __dsub_rn(__dmul_rn(a[u].x, w[u].x), __dmul_rn(a[u].y, w[u].y)));
+            im = __dadd_rn(im, __dadd_rn(__dmul_rn(a[u].x, w[u].y), __dmul_rn(a[u].y, w[u].x)));
+        }
+    }
+    for (; k < k1; k++) {
+        const double2 a = ld_nc_double2(&data[k]);
+        const double2 w = ld_nc_double2(&v[__ldg(&indices[k])]);
+        re = __dadd_rn(re, __dsub_rn(__dmul_rn(a.x, w.x), __dmul_rn(a.y, w.y)));
+        im = __dadd_rn(im, __dadd_rn(__dmul_rn(a.x, w.y), __dmul_rn(a.y, w.x)));
+    }
+    y[row] = make_double2(re, im);
+}
+
 // accel.rs:374-393, arithmetic spelled as num_complex's so results are bit-identical.
 __device__ __forceinline__ double2 cmul_rn(double2 a, double2 b)
 {

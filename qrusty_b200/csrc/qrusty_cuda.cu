@@ -2247,9 +2247,13 @@ extern "C" int qr_spmv_device(uint64_t n_rows, const uint64_t *d_indptr, const u
     if (!d_indptr || !d_indices || !d_data || !d_v || !d_y) return fail(QR_ERR_INVALID, "qr_spmv_device: NULL argument");
     if (n_rows == 0) return QR_OK;
     const uint64_t ctas = (n_rows + 255) / 256;
-    qr::spmv_csr_kernel<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(
-        n_rows, d_indptr, d_indices, reinterpret_cast<const double2 *>(d_data),
-        reinterpret_cast<const double2 *>(d_v), reinterpret_cast<double2 *>(d_y));
+    if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "qr_spmv_device: too many rows for one launch");
+    int unroll = 4;                                                 // entries of a row in flight per thread (QR_SPMV_UNROLL: sweeps, tests)
+    if (const char *env = getenv("QR_SPMV_UNROLL")) { const int u = atoi(env); if (u == 1 || u == 2 || u == 4 || u == 8) unroll = u; }
+    auto kern = unroll == 1 ? qr::spmv_csr_kernel : unroll == 2 ? qr::spmv_csr_unrolled_kernel<2> :
+                unroll == 4 ? qr::spmv_csr_unrolled_kernel<4> : qr::spmv_csr_unrolled_kernel<8>;
+    kern<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(n_rows, d_indptr, d_indices, reinterpret_cast<const double2 *>(d_data),
+                                                        reinterpret_cast<const double2 *>(d_v), reinterpret_cast<double2 *>(d_y));
     QR_LAUNCH_CHECK("spmv_csr_kernel");
     return QR_OK;
 }

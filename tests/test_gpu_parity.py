@@ -683,6 +683,31 @@ def test_C4_full_size_properties():
 
 
 # ---- H.v -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("unroll", ["4", "1", "2", "8"])
+@pytest.mark.parametrize("name", ["H2", "H4", "H6", "C1", "random_n10", "xxz_n10", "tfim_3x3"])
+def test_spmv_ragged_rows(fixtures, monkeypatch, name, unroll):
+    """spmat_dot_densevec on a compacted matrix (eliminate_zeros: ragged and empty rows) and on a row shard -- the
+    thread-per-row kernel with 1 / 2 / 4 (default) / 8 entries of a row in flight, every form bit for bit the reference's
+    sequential sums (accel.rs:338-370)."""
+    monkeypatch.setenv("QR_SPMV_UNROLL", unroll)
+    labels, coeffs = SMALL[name](fixtures)
+    n, params = O.make_params(labels, coeffs)
+    rng = np.random.default_rng(11)
+    v = rng.uniform(-3, 3, 1 << n) + 1j * rng.uniform(-5, 5, 1 << n)
+    tol = float(np.median(np.abs(O.build_csr(params, n)[2])))       # drops about half the entries
+    want = O.eliminate_zeros(*O.build_csr(params, n), tolerance=tol)
+    assert len(want[2]) < (1 << n) * len(set(params["x"].tolist())) and len(want[2]) > 0
+    m = make_op(labels, coeffs).to_matrix_mode("Cuda").eliminate_zeros(tol)
+    y = Q.spmat_dot_densevec(m, v)
+    assert np.array_equal(u64(y), u64(O.spmv(*want, v)))
+    dim = 1 << n
+    if dim >= 512:
+        lo, hi = 100, dim - 37                                      # a ragged shard: 256-row tiles with a short last one
+        ref = O.build_csr(params, n, lo, hi)
+        ms = make_op(labels, coeffs).to_matrix_rows(lo, hi)
+        assert np.array_equal(u64(Q.spmat_dot_densevec(ms, v)), u64(O.spmv(*ref, v)))
+
+
 @pytest.mark.parametrize("name", ["H2", "H6", "C1", "random_n10"])
 def test_spmv_bit_exact(fixtures, name):
     """spmat_dot_densevec on the device CSR == accel.rs:338-370 bit for bit (lib.rs:887-919)."""
