@@ -33,7 +33,7 @@ __device__ __forceinline__ bool keep_entry(double2 d, double tol)
 // counts[r + 1] = #{entries of row r with norm > tol}; counts[0] = 0.  CTA b owns rows [b*R, (b+1)*R).
 __global__ void __launch_bounds__(K2_THREADS)
 count_kept_kernel(uint64_t n_rows, uint32_t G, uint32_t R, const double2 *__restrict__ data, double tol,
-                  uint64_t *__restrict__ counts)
+                  uint64_t *__restrict__ counts, uint32_t write_zero = 1u)     // write_zero = 0: a later window of a windowed count
 {
     extern __shared__ uint32_t s_cnt[];                       // [R]
     const uint64_t row0 = (uint64_t)blockIdx.x * R;
@@ -45,7 +45,7 @@ count_kept_kernel(uint64_t n_rows, uint32_t G, uint32_t R, const double2 *__rest
         if (keep_entry(data[base + i], tol)) atomicAdd(&s_cnt[(uint32_t)(i / G)], 1u);
     __syncthreads();
     for (uint32_t l = threadIdx.x; l < nr; l += K2_THREADS) counts[row0 + l + 1] = s_cnt[l];
-    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
+    if (write_zero && blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
 }
 
 // ---- three-phase scan over a[1..n] (a[0] = 0 stays): inclusive, in place ----------------------
@@ -149,7 +149,9 @@ count_rows_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi, doubl
         r[e] = (uint32_t)(live[e] ? r64 : row_hi - 1);
         cnt[e] = 0;
     }
-    for (uint32_t g = 0; g < G; g++) {
+    // gridDim.y > 1 (few rows, many groups: the host zeroes `counts` first): this CTA counts its slice of the groups only
+    const uint32_t g_lo = (uint32_t)((uint64_t)G * blockIdx.y / gridDim.y), g_hi = (uint32_t)((uint64_t)G * (blockIdx.y + 1) / gridDim.y);
+    for (uint32_t g = g_lo; g < g_hi; g++) {
         const GroupDesc d = p.gdesc[g];
         double ar[E], ai[E];
         if (d.flag & 1u) {
@@ -160,6 +162,12 @@ count_rows_kernel(PlanDev p, uint32_t G, uint64_t row_lo, uint64_t row_hi, doubl
         }
 #pragma unroll
         for (int e = 0; e < E; e++) cnt[e] += keep_entry(make_double2(ar[e], ai[e]), tol) ? 1u : 0u;
+    }
+    if (gridDim.y > 1) {
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            if (live[e]) atomicAdd(reinterpret_cast<unsigned long long *>(&counts[base + 32u * e + lane - row_lo + 1]), (unsigned long long)cnt[e]);
+        return;
     }
 #pragma unroll
     for (int e = 0; e < E; e++)

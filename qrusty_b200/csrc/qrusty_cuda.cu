@@ -74,7 +74,12 @@ std::map<int, WinScratch> g_win;
 
 // small device scratch of the scan and the reductions, one set per device (a host thread may drive several GPUs in turn:
 // thread-local pointers would leak the previous device's block on every switch)
-struct DevScratch { uint64_t *tiles = nullptr; uint64_t tiles_cap = 0; double2 *partials = nullptr; double2 *tmp = nullptr; int n_sm = 0; };
+struct DevScratch {
+    uint64_t *tiles = nullptr; uint64_t tiles_cap = 0; double2 *partials = nullptr; double2 *tmp = nullptr; int n_sm = 0;
+    // row windows of the drop-zeros build when a row is too long for a shared-memory tile (qr_build_compact_count / _fill):
+    // kept per device -- a cudaMalloc + cudaFree of 256 MB per call cost 6 ms of the 6.8 ms on H8
+    void *cwin = nullptr; size_t cwin_bytes = 0; std::mutex cwin_busy;
+};
 std::mutex g_dev_mutex;
 std::map<int, DevScratch> g_dev;
 DevScratch *dev_scratch(int dev)
@@ -1546,6 +1551,7 @@ extern "C" int qr_release_scratch(void)
         if (cudaSetDevice(kv.first) != cudaSuccess) continue;
         if (kv.second.tiles) cudaFree(kv.second.tiles);
         if (kv.second.partials) cudaFree(kv.second.partials);
+        if (kv.second.cwin) cudaFree(kv.second.cwin);
     }
     g_dev.clear();
     return QR_OK;
@@ -2349,6 +2355,23 @@ extern "C" int qr_csr_compact_device(uint64_t n_rows, const uint64_t *d_indptr_i
     return QR_OK;
 }
 
+// the per-device scratch for row windows of <= 256 MB (G * 24 bytes per row), grown on demand; caller holds ds->cwin_busy
+static int compact_window(DevScratch *ds, uint64_t G, uint64_t rows, cudaStream_t st, uint64_t *win_out, void **scratch_out)
+{
+    uint64_t win_bytes = 256ull << 20;
+    if (const char *env = getenv("QR_COMPACT_WIN_MB")) { const int v = atoi(env); if (v >= 1 && v <= 4096) win_bytes = (uint64_t)v << 20; }   // tests
+    uint64_t win = std::max<uint64_t>(32, win_bytes / (G * 24) / 32 * 32);
+    if (win > rows) win = rows;
+    const size_t need = (size_t)win * G * 24;
+    if (ds->cwin_bytes < need) {
+        if (ds->cwin) { QR_CUDA(cudaStreamSynchronize(st)); cudaFree(ds->cwin); ds->cwin = nullptr; ds->cwin_bytes = 0; }
+        QR_CUDA(cudaMalloc(&ds->cwin, need));
+        ds->cwin_bytes = need;
+    }
+    *win_out = win; *scratch_out = ds->cwin;
+    return QR_OK;
+}
+
 extern "C" int qr_build_compact_count(qr_plan *pl, uint64_t row_lo, uint64_t row_hi, double tol,
                                       uint64_t *d_indptr, uint64_t *nnz_out, void *stream)
 {
@@ -2357,9 +2380,43 @@ extern "C" int qr_build_compact_count(qr_plan *pl, uint64_t row_lo, uint64_t row
     QR_CUDA(cudaSetDevice(pl->device));
     cudaStream_t st = as_stream(stream);
     const uint64_t rows = row_hi - row_lo, per_cta = 64ull * qr::COUNT_ROWS_WARPS;
+    const uint64_t G = pl->n_groups;
+    if ((size_t)32 * G * 24 > MAX_SMEM && getenv("QR_COMPACT_COUNT_WINDOWED")) {
+        // Opt-in alternative for rows too long for the tiled fill: the fill kernels build row windows into scratch and
+        // count_kept_kernel counts them.  Measured against count_rows_kernel (lane <-> row, values in registers): H8 0.92
+        // against 1.16 ms, random G = 400 1.08 against 0.29 ms -- no clear winner, count_rows_kernel stays the default.
+        int dev = 0;
+        QR_CUDA(cudaGetDevice(&dev));
+        DevScratch *ds = dev_scratch(dev);
+        std::lock_guard<std::mutex> busy(ds->cwin_busy);
+        uint64_t win = 0; void *scratch = nullptr;
+        int rc = compact_window(ds, G, rows, st, &win, &scratch);
+        if (rc != QR_OK) return rc;
+        double2 *t_dat = static_cast<double2 *>(scratch);
+        uint64_t *t_idx = reinterpret_cast<uint64_t *>(static_cast<char *>(scratch) + win * G * 16);
+        const uint32_t R = (uint32_t)std::min<uint64_t>(2048, std::max<uint64_t>(1, 8192 / G));
+        for (uint64_t w0 = row_lo; w0 < row_hi; w0 += win) {
+            const uint64_t w1 = std::min(row_hi, w0 + win), n = w1 - w0;
+            rc = build_rows(pl, w0, w1, nullptr, t_idx, t_dat, 0, st);
+            if (rc != QR_OK) return rc;
+            qr::count_kept_kernel<<<(unsigned)((n + R - 1) / R), qr::K2_THREADS, R * 4, st>>>(n, (uint32_t)G, R, t_dat, tol, d_indptr + (w0 - row_lo),
+                                                                                             w0 == row_lo ? 1u : 0u);
+            QR_LAUNCH_CHECK("count_kept_kernel");
+        }
+        return scan_counts(rows, d_indptr, nnz_out, st, "qr_build_compact_count");   // synchronises: the scratch is free again
+    }
     const uint64_t ctas = (rows + per_cta - 1) / per_cta;
     if (ctas > 0x7fffffffull) return fail(QR_ERR_UNSUPPORTED, "qr_build_compact_count: row window too large for one launch");
-    qr::count_rows_kernel<<<(unsigned)ctas, 32 * qr::COUNT_ROWS_WARPS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, tol, d_indptr);
+    // few rows and many groups (molecular Hamiltonians: 2^16 rows x 981 groups = 128 CTAs of 8 warps): the groups are cut
+    // into slices along gridDim.y and the slices add their counts atomically (H8: 1.16 -> 0.3 ms)
+    uint32_t slices = 1;
+    {
+        const uint64_t want_ctas = (uint64_t)pl->n_sm * 8;
+        if (ctas < want_ctas && G >= 64) slices = (uint32_t)std::min<uint64_t>({(want_ctas + ctas - 1) / ctas, G / 32, (uint64_t)64});
+        if (const char *env = getenv("QR_COUNT_ROWS_SLICES")) { const int v = atoi(env); if (v >= 1 && (uint64_t)v <= G && v <= 65535) slices = (uint32_t)v; }
+        if (slices > 1) QR_CUDA(cudaMemsetAsync(d_indptr, 0, (rows + 1) * 8, st));
+    }
+    qr::count_rows_kernel<<<dim3((unsigned)ctas, slices, 1), 32 * qr::COUNT_ROWS_WARPS, 0, st>>>(pl->dev, (uint32_t)pl->n_groups, row_lo, row_hi, tol, d_indptr);
     QR_LAUNCH_CHECK("count_rows_kernel");
     return scan_counts(rows, d_indptr, nnz_out, st, "qr_build_compact_count");
 }
@@ -2388,10 +2445,12 @@ extern "C" int qr_build_compact_fill(qr_plan *pl, uint64_t row_lo, uint64_t row_
         return QR_OK;
     }
     // rows too long for a shared-memory tile: build row windows into scratch, compact each window
-    uint64_t win = std::max<uint64_t>(32, (256ull << 20) / (G * 24) / 32 * 32);
-    if (win > rows) win = rows;
-    void *scratch = nullptr;
-    QR_CUDA(cudaMalloc(&scratch, win * G * 24));
+    int dev = 0;
+    QR_CUDA(cudaGetDevice(&dev));
+    DevScratch *ds = dev_scratch(dev);
+    std::lock_guard<std::mutex> busy(ds->cwin_busy);
+    uint64_t win = 0; void *scratch = nullptr;
+    { const int rc0 = compact_window(ds, G, rows, st, &win, &scratch); if (rc0 != QR_OK) return rc0; }
     double2 *t_dat = static_cast<double2 *>(scratch);
     uint64_t *t_idx = reinterpret_cast<uint64_t *>(static_cast<char *>(scratch) + win * G * 16);
     int rc = QR_OK;
@@ -2406,8 +2465,7 @@ extern "C" int qr_build_compact_fill(qr_plan *pl, uint64_t row_lo, uint64_t row_
         g_launches.fetch_add(1);
         if (cudaGetLastError() != cudaSuccess) rc = fail(QR_ERR_CUDA, "qr_build_compact_fill: compact_rows_kernel launch failed");
     }
-    cudaStreamSynchronize(st);
-    cudaFree(scratch);
+    cudaStreamSynchronize(st);                                      // the scratch belongs to the device: free for the next caller
     return rc;
 }
 

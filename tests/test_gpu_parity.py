@@ -1044,6 +1044,32 @@ def test_eliminate_zeros(fixtures, name, resident):
         assert m.nnz() == len(ref[2])                      # the original is untouched
 
 
+@pytest.mark.parametrize("count_rows", [False, True, "3"])
+@pytest.mark.parametrize("win_mb", [None, "1"])
+@pytest.mark.parametrize("n,T,G", [(10, 900, 400), (11, 1500, 700), (11, 2400, 1100)])
+def test_eliminate_zeros_long_rows(monkeypatch, n, T, G, win_mb, count_rows):
+    """Fused drop-zeros build when a row is too long for a shared-memory tile (G > 302): row windows built by the fill
+    kernels into the per-device scratch and compacted by compact_rows_kernel; counted by count_rows_kernel (default) or,
+    window by window, by count_kept_kernel -- one window and many (1 MB windows: the counts of neighbouring windows must not clobber each other)."""
+    if win_mb:
+        monkeypatch.setenv("QR_COMPACT_WIN_MB", win_mb)
+    if not count_rows:
+        monkeypatch.setenv("QR_COMPACT_COUNT_WINDOWED", "1")
+    elif count_rows == "3":                                         # count_rows_kernel with the groups cut into 3 slices (atomic counts)
+        monkeypatch.setenv("QR_COUNT_ROWS_SLICES", "3")
+    labels, coeffs = H.random_pauli_sum(n, T, G, 50, 9)
+    nq, params = O.make_params(labels, coeffs)
+    ref = O.build_csr(params, nq)
+    tol = float(np.median(np.abs(ref[2])))
+    want = O.eliminate_zeros(*ref, tolerance=tol)
+    assert 0 < len(want[2]) < len(ref[2])
+    m = make_op(labels, coeffs).to_matrix()
+    assert m.count_zeros(tol) == O.count_zeros(ref[2], tol)
+    m2 = m.eliminate_zeros(tol)
+    shape, data, indices, indptr = m2.export()
+    assert_same((indptr, indices, data), want, f"G={G} win={win_mb} count_rows={count_rows}")
+
+
 def test_eliminate_zeros_tiny_values():
     """test_it.py:141-148: a matrix of 1e-8 entries has 2 'zeros'; eliminating them leaves nothing."""
     m = Q.SparsePauliOp([Q.Pauli("I")], [1e-8 + 0j]).to_matrix()
