@@ -89,6 +89,13 @@ DevScratch *dev_scratch(int dev)
     if (d.n_sm == 0 && (cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.n_sm < 1)) { cudaGetLastError(); d.n_sm = 148; }
     return &d;
 }
+// QR_PLAN_TRACE: wall-clock milestones of plan creation on stderr (where the host-visible latency of a plan goes)
+struct PlanTrace {
+    bool on = getenv("QR_PLAN_TRACE") != nullptr;
+    double t0 = now();
+    static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    void mark(const char *what) { if (on) { const double t = now(); fprintf(stderr, "qr_plan_create: %-28s +%.3f ms\n", what, t - t0); t0 = t; } }
+};
 int current_sm_count()
 {
     int dev = 0;
@@ -368,8 +375,11 @@ bool choose_rows_shape(qr_plan *pl);
 bool choose_rows_inner(qr_plan *pl);
 bool choose_rows(qr_plan *pl)
 {
+    PlanTrace tr;
     const bool ok = choose_rows_inner(pl);
+    tr.mark("  choose_rows_inner");
     if (ok) build_rows_perm(pl);
+    tr.mark("  build_rows_perm");
     return ok;
 }
 bool choose_rows_inner(qr_plan *pl)
@@ -765,8 +775,10 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     const size_t o_gf = carve(T * 4), o_gc = carve(T * 16), o_gd = carve(T * sizeof(qr::GroupDesc));
     const size_t o_ct = carve(T * 128);
     const size_t o_lx = carve(T * 8), o_lz = carve(T * 4 * qr::LANE_TERMS), o_lc = carve(T * 16 * qr::LANE_TERMS);
+    PlanTrace tr;
     cudaError_t e = cudaMalloc(&pl->slab, off);
     if (e != cudaSuccess) { delete pl; return fail(QR_ERR_OOM, std::string("qr_plan_create: cudaMalloc: ") + cudaGetErrorString(e)); }
+    tr.mark("cudaMalloc slab");
     char *b = static_cast<char *>(pl->slab);
     qr::PlanDev &d = pl->dev;
     d.n_qubits = n_qubits; d.n_terms = (uint32_t)T;
@@ -788,10 +800,12 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     auto bail = [&](int code) { cudaFree(pl->slab); delete pl; return code; };
     e = cudaMemcpy(b + o_raw, terms, T * sizeof(qr_term), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: H2D: ") + cudaGetErrorString(e)));
+    tr.mark("H2D terms");
     int rc = run_canonicalise(pl, nullptr);
     if (rc != QR_OK) return bail(rc);
     uint32_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     e = cudaMemcpy(meta, d.meta, sizeof(meta), cudaMemcpyDeviceToHost);
+    tr.mark("K1 canonicalise + meta D2H");
     if (e != cudaSuccess) return bail(fail(QR_ERR_CUDA, std::string("qr_plan_create: canonicalise: ") + cudaGetErrorString(e)));
     pl->n_groups = meta[0];
     pl->n_const = meta[4];
@@ -799,6 +813,7 @@ extern "C" int qr_plan_create(int n_qubits, const qr_term *terms, size_t n_terms
     pl->n_terms_canonical = meta[5];
     if (pl->n_groups == 0 || pl->n_groups > T) return bail(fail(QR_ERR_CUDA, "qr_plan_create: canonicalisation produced no groups"));
     choose_staged(pl);
+    tr.mark("choose kernels");
     if (pl->block_s) {
         rc = run_partition(pl, nullptr);
         if (rc != QR_OK) return bail(rc);
